@@ -1,0 +1,173 @@
+/*
+ * ssf.h -- C ABI of libssf_gpu.so: scan-to-map registration on one B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the registration hot path of
+ * viniciusvidal2/slam-sensor-fusion.  Every entry point names the reference interface it
+ * replaces (paths relative to the reference repository root).  Plain C: opaque handles,
+ * plain pointers and sizes, int status codes; no C++ / torch / PCL / Eigen types.
+ *
+ * Conventions
+ *   - Points are float triples at a caller-given byte stride (16 for pcl::PointXYZ /
+ *     float4, 12 for packed xyz).  All pointers are HOST pointers unless a function says
+ *     "device".  The library copies at set time: the caller may free or overwrite its
+ *     buffer as soon as the call returns, exactly like the reference's deep copies
+ *     (localization/src/icp_point_to_point.cpp:44-55).
+ *   - 4x4 transforms are 16 floats, COLUMN-major, like Eigen::Matrix4f.
+ *   - Every function returns SSF_OK (0) or a negative ssf_status; ssf_last_error() gives
+ *     the message of the calling thread's last failure.  There is no CPU fallback: with no
+ *     usable CUDA device ssf_ctx_create fails with SSF_ERR_CUDA.
+ *   - A handle is not thread-safe (the reference object is used from one single-threaded
+ *     executor, localization/src/main.cpp:18); distinct handles are independent.
+ */
+#ifndef SSF_SSF_H
+#define SSF_SSF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ssf_ctx ssf_ctx;     /* one CUDA device: stream, scratch memory            */
+typedef struct ssf_icp ssf_icp;     /* one ICPPointToPoint object: map in HBM + parameters */
+typedef struct ssf_batch ssf_batch; /* a set of scans resident in HBM, aligned together    */
+
+typedef enum {
+    SSF_OK = 0,
+    SSF_ERR_INVALID = -1, /* bad argument                                   */
+    SSF_ERR_CUDA = -2,    /* CUDA runtime failure (message has the detail)  */
+    SSF_ERR_NOMEM = -3,   /* host or device allocation failed               */
+    SSF_ERR_STATE = -4,   /* call order: no target / no source set          */
+    SSF_ERR_COMM = -5     /* multi-GPU exchange failure                     */
+} ssf_status;
+
+/* Solver run by ssf_icp_align. */
+typedef enum {
+    /* ICPPointToPoint::calculateAlignment as written (icp_point_to_point.cpp:185-254):
+     * one search before the loop, lazy re-search, shrinking source, Kabsch/SVD step.      */
+    SSF_MODE_REFERENCE = 0,
+    /* Gauss-Newton, re-search every iteration, 6x6 normal equations + Cholesky on device. */
+    SSF_MODE_GN_P2P = 1,
+    SSF_MODE_GN_P2PLANE = 2, /* needs target normals */
+    /* Control flow of open3d registration_icp(PointToPoint) used by the Python node
+     * (localization_python/localization_python/localization_node.py:233-237).             */
+    SSF_MODE_O3D_P2P = 3
+} ssf_mode;
+
+/* How the per-iteration sums are formed in SSF_MODE_REFERENCE. */
+typedef enum {
+    /* float, sequential, in source-row order -- the reference's own loops
+     * (icp_point_to_point.cpp:117-121, 126-134, 164-167); results are bit-identical to the
+     * CPU restatement, including which iterations re-search.                              */
+    SSF_REDUCE_STRICT = 0,
+    /* double, parallel tree; fastest, differs from STRICT by float summation noise.       */
+    SSF_REDUCE_FAST = 1
+} ssf_reduce;
+
+/* Replaces the constructor arguments and setters of ICPPointToPoint
+ * (icp_point_to_point.h:49-80, icp_point_to_point.cpp:3-42). */
+typedef struct {
+    float max_correspondence_dist; /* compared with the SQUARED distance (cpp:70) */
+    int32_t num_iterations;
+    float acceptable_mean_error;
+    float transformation_epsilon;
+    int32_t mode;   /* ssf_mode   */
+    int32_t reduce; /* ssf_reduce */
+    int32_t debug;  /* setDebugMode: print the per-iteration trace of cpp:172-183,237-246 */
+    float source_voxel_leaf; /* > 0: voxel-grid downsample each source scan first (north-star step 1) */
+} ssf_icp_params;
+
+/* Replaces struct ICPResult (icp_point_to_point.h:28-39) plus diagnostics. */
+typedef struct {
+    float transformation[16]; /* column-major; = initial transform when aborted           */
+    float error;              /* 1e6 when aborted (ICPResult default)                      */
+    int32_t iterations;
+    int32_t has_converged;
+    int32_t n_searches;       /* correspondence searches run                               */
+    int32_t k_final;          /* correspondences in the last search                        */
+    int32_t aborted;          /* 1: < 10 correspondences on the first search (cpp:196-200) */
+    float fitness;            /* k_final / n_source                                        */
+    int32_t n_source;         /* source points after optional voxel downsample             */
+    float device_ms;          /* device time of the call (CUDA events)                     */
+} ssf_icp_result;
+
+const char *ssf_last_error(void);
+const char *ssf_version(void);
+
+/* ---- context ------------------------------------------------------------------------- */
+int ssf_ctx_create(int device_ordinal, ssf_ctx **out);
+void ssf_ctx_destroy(ssf_ctx *ctx);
+int ssf_ctx_synchronize(ssf_ctx *ctx);
+/* cudaStream_t of the context (as void*), for callers that time with their own events. */
+void *ssf_ctx_stream(ssf_ctx *ctx);
+
+/* ---- registration object: ICPPointToPoint -------------------------------------------- */
+/* ICPPointToPoint::ICPPointToPoint (icp_point_to_point.cpp:3-12). */
+int ssf_icp_create(ssf_ctx *ctx, const ssf_icp_params *params, ssf_icp **out);
+void ssf_icp_destroy(ssf_icp *icp);
+/* setMaxCorrespondenceDist / setNumIterations / setTransformationEpsilon /
+ * setAcceptableMeanError / setDebugMode (icp_point_to_point.cpp:14-42). */
+int ssf_icp_set_params(ssf_icp *icp, const ssf_icp_params *params);
+int ssf_icp_get_params(const ssf_icp *icp, ssf_icp_params *out);
+/* setTargetPointCloud (icp_point_to_point.cpp:49-55): copy the map to HBM and build the
+ * voxel-hash index that replaces kdtree_.setInputCloud.  normals (optional, same count)
+ * are required by SSF_MODE_GN_P2PLANE.  The map stays resident until the next call. */
+int ssf_icp_set_target(ssf_icp *icp, const float *xyz, size_t n, size_t stride_bytes, const float *normals,
+                       size_t normals_stride_bytes);
+/* setSourcePointCloud (icp_point_to_point.cpp:44-47). */
+int ssf_icp_set_source(ssf_icp *icp, const float *xyz, size_t n, size_t stride_bytes);
+/* setInitialTransformation (icp_point_to_point.cpp:34-37). */
+int ssf_icp_set_initial(ssf_icp *icp, const float T_colmajor[16]);
+/* calculateAlignment (icp_point_to_point.cpp:185-254). */
+int ssf_icp_align(ssf_icp *icp, ssf_icp_result *out);
+/* Correspondence of every ORIGINAL source row after the last align: target index or -1
+ * (the std::vector filled at icp_point_to_point.cpp:60-75, kept per row).  n = n_source. */
+int ssf_icp_get_correspondences(ssf_icp *icp, int32_t *idx_out, size_t n);
+/* Per-pass trace of the last align (REFERENCE mode): error measured at the top of pass i
+ * (printStepDebug, cpp:172-183) and whether pass i re-searched.  NaN / 0 for passes not run. */
+int ssf_icp_get_trace(ssf_icp *icp, float *iter_err, int32_t *iter_searched, size_t n);
+size_t ssf_icp_target_size(const ssf_icp *icp);
+
+/* kdtree_.nearestKSearch(p, 1, ..) + the d2 < max_sqdist test for n query points
+ * (icp_point_to_point.cpp:64-70) against the handle's target.  idx[i] = index of the
+ * nearest target point (lowest index on equal distance), d2[i] its squared distance; -1 /
+ * FLT_MAX when no target point has d2 < max_sqdist.  Parity and benchmark entry. */
+int ssf_nn_search(ssf_icp *icp, const float *queries, size_t n, size_t stride_bytes, float max_sqdist, int32_t *idx,
+                  float *d2);
+
+/* pcl::VoxelGrid<PointXYZ> with setLeafSize(leaf, leaf, leaf)
+ * (localization/src/global_map_frames_manager.cpp:143-146).  out must hold n float4
+ * (16-byte stride, w = 1).  *refused = 1 when PCL's index-overflow guard fires, in which
+ * case the input is returned unchanged like PCL does. */
+int ssf_voxel_downsample(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, float leaf, float *out,
+                         size_t *n_out, int *refused);
+
+/* ---- batches: offline reprocessing of scan sequences (BASELINE.json config 4) --------- */
+/* Every scan of a batch is aligned against the handle's target with the handle's
+ * parameters; scans are independent (the per-scan loop of
+ * localization/src/localization_node.cpp:335-338 over a recorded sequence). */
+int ssf_batch_create(ssf_icp *icp, size_t max_scans, size_t max_total_points, ssf_batch **out);
+void ssf_batch_destroy(ssf_batch *b);
+/* Copy n_scans scans to HBM.  xyz: concatenated points of all scans; n_pts[s] their sizes. */
+int ssf_batch_upload(ssf_batch *b, const float *xyz, const size_t *n_pts, size_t n_scans, size_t stride_bytes);
+/* Initial transforms, n_scans x 16 floats column-major. */
+int ssf_batch_set_initial(ssf_batch *b, const float *T_colmajor);
+/* Run the whole batch on the device; asynchronous on the context stream. */
+int ssf_batch_run(ssf_batch *b);
+/* Wait and copy the n_scans results back. */
+int ssf_batch_results(ssf_batch *b, ssf_icp_result *out, size_t n_scans);
+/* upload + set_initial + run + results in one call (host buffers in, host results out). */
+int ssf_icp_align_batch(ssf_icp *icp, const float *xyz, const size_t *n_pts, size_t n_scans, size_t stride_bytes,
+                        const float *T_colmajor, ssf_icp_result *out);
+
+/* ---- counters ------------------------------------------------------------------------- */
+/* Kernels launched by this library since process start (all contexts). */
+uint64_t ssf_kernel_launches(void);
+/* NN queries issued by search kernels since process start. */
+uint64_t ssf_nn_queries(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSF_SSF_H */

@@ -1,0 +1,628 @@
+// abi.cu -- the extern "C" surface declared in include/ssf/ssf.h.
+//
+// Host-side orchestration only: handles own HBM buffers, copy caller data in (deep copy at
+// set time, like reference localization/src/icp_point_to_point.cpp:44-55), enqueue the
+// kernels of map_build.cu / icp_kernels.cu / voxel_grid.cu on the context stream and copy
+// the small results out.  There is no CPU implementation of any step behind these calls.
+#include <cmath>
+#include <cstdlib>
+#include <new>
+#include <vector>
+
+#include "icp.cuh"
+#include "map_index.cuh"
+#include "voxel_grid.cuh"
+
+namespace ssf {
+
+std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_queries{0};
+static thread_local char t_err[1024] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace ssf
+
+using namespace ssf;
+
+struct ssf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Scratch scratch;
+    DevBuf<unsigned char> stage;  // raw bytes of caller clouds before packing
+};
+
+struct ssf_batch {
+    ssf_icp *icp = nullptr;
+    BatchBuffers buf;
+    size_t max_scans = 0, max_points = 0;
+    DevBuf<float> T_init_dev;
+    DevBuf<uint32_t> meta_dev;  // per scan: raw_begin, n_raw, pt_begin, tile_begin, tile_cap
+    std::vector<uint32_t> meta_host;
+    std::vector<uint32_t> n_raw;
+    size_t total_points = 0;
+    bool uploaded = false, initial_set = false, ran = false;
+    float last_ms = 0.f;
+};
+
+struct ssf_icp {
+    ssf_ctx *ctx = nullptr;
+    ssf_icp_params prm{};
+    MapIndex map;
+    bool has_target = false;
+    float T_init[16];
+    ssf_batch *single = nullptr;  // the one-scan batch behind set_source / align
+    bool has_source = false;
+    size_t n_source = 0;
+    DevBuf<float4> q_dev;  // ssf_nn_search temporaries
+    DevBuf<int32_t> q_idx;
+    DevBuf<float> q_d2;
+};
+
+#define SSF_ARG(cond, msg)                 \
+    do {                                   \
+        if (!(cond)) {                     \
+            ssf::set_error("%s", msg);     \
+            return SSF_ERR_INVALID;        \
+        }                                  \
+    } while (0)
+
+static int use_device(const ssf_ctx *ctx)
+{
+    SSF_CUDA(cudaSetDevice(ctx->device));
+    return SSF_OK;
+}
+
+// ---- packing kernels ------------------------------------------------------------------------
+// caller cloud (floats at a byte stride) -> float4
+__global__ void __launch_bounds__(256) pack_points_kernel(const unsigned char *__restrict__ raw, size_t n,
+                                                          size_t stride_bytes, float4 *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = reinterpret_cast<const float *>(raw + i * stride_bytes);
+    out[i] = make_float4(p[0], p[1], p[2], 1.0f);
+}
+
+// concatenated scans -> tile-aligned per-scan slots; one block column per scan
+__global__ void __launch_bounds__(256)
+    pack_scans_kernel(const unsigned char *__restrict__ raw, size_t stride_bytes, const uint32_t *__restrict__ meta,
+                      float4 *__restrict__ out)
+{
+    const uint32_t s = blockIdx.y;
+    const uint32_t raw_begin = meta[5 * s + 0], n = meta[5 * s + 1], pt_begin = meta[5 * s + 2];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float *p = reinterpret_cast<const float *>(raw + (size_t)(raw_begin + i) * stride_bytes);
+        out[(size_t)pt_begin + i] = make_float4(p[0], p[1], p[2], 1.0f);
+    }
+}
+
+__global__ void layout_kernel(ScanState *st, const uint32_t *__restrict__ meta, uint32_t n_scans,
+                              uint32_t *__restrict__ tile_scan)
+{
+    const uint32_t s = blockIdx.x;
+    if (s >= n_scans) return;
+    const uint32_t n = meta[5 * s + 1], pt_begin = meta[5 * s + 2], tile_begin = meta[5 * s + 3],
+                   tile_cap = meta[5 * s + 4];
+    if (threadIdx.x == 0) {
+        st[s].pt_begin = pt_begin;
+        st[s].n_pts = n;
+        st[s].tile_begin = tile_begin;
+        st[s].tile_cap = tile_cap;
+    }
+    for (uint32_t t = threadIdx.x; t < tile_cap; t += blockDim.x) tile_scan[tile_begin + t] = s;
+}
+
+// ---- misc -------------------------------------------------------------------------------------
+extern "C" const char *ssf_last_error(void) { return t_err; }
+extern "C" const char *ssf_version(void) { return "ssf-gpu 0.1 (sm_100a)"; }
+extern "C" uint64_t ssf_kernel_launches(void) { return g_launches.load(); }
+extern "C" uint64_t ssf_nn_queries(void) { return g_queries.load(); }
+
+// ---- context ----------------------------------------------------------------------------------
+extern "C" int ssf_ctx_create(int device_ordinal, ssf_ctx **out)
+{
+    SSF_ARG(out, "ssf_ctx_create: out == NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no usable CUDA device (%s); libssf_gpu has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        cudaGetLastError();
+        return SSF_ERR_CUDA;
+    }
+    SSF_ARG(device_ordinal >= 0 && device_ordinal < count, "ssf_ctx_create: device ordinal out of range");
+    ssf_ctx *c = new (std::nothrow) ssf_ctx;
+    if (!c) return SSF_ERR_NOMEM;
+    c->device = device_ordinal;
+    SSF_CUDA(cudaSetDevice(device_ordinal));
+    SSF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    SSF_CUDA(cudaEventCreate(&c->ev0));
+    SSF_CUDA(cudaEventCreate(&c->ev1));
+    *out = c;
+    return SSF_OK;
+}
+
+extern "C" void ssf_ctx_destroy(ssf_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int ssf_ctx_synchronize(ssf_ctx *ctx)
+{
+    SSF_ARG(ctx, "ssf_ctx_synchronize: ctx == NULL");
+    SSF_TRY(use_device(ctx));
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SSF_OK;
+}
+
+extern "C" void *ssf_ctx_stream(ssf_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+// ---- helpers ------------------------------------------------------------------------------------
+static int check_params(const ssf_icp_params *p)
+{
+    SSF_ARG(p, "params == NULL");
+    SSF_ARG(p->num_iterations >= 0 && p->num_iterations <= 100000, "num_iterations out of range");
+    SSF_ARG(p->mode >= SSF_MODE_REFERENCE && p->mode <= SSF_MODE_O3D_P2P, "unknown mode");
+    SSF_ARG(p->reduce == SSF_REDUCE_STRICT || p->reduce == SSF_REDUCE_FAST, "unknown reduce");
+    SSF_ARG(!(p->max_correspondence_dist != p->max_correspondence_dist), "max_correspondence_dist is NaN");
+    SSF_ARG(!(p->source_voxel_leaf < 0.f), "source_voxel_leaf < 0");
+    return SSF_OK;
+}
+
+// cell edge for a rejection threshold thr (compared with SQUARED distances): one cell >= the
+// search radius so a query visits at most 3 cells per axis
+static float cell_size_for(float max_corr)
+{
+    const char *env = getenv("SSF_CELL_SIZE");
+    if (env && atof(env) > 0.0) return (float)atof(env);
+    float r = (max_corr > 0.f && std::isfinite(max_corr)) ? sqrtf(max_corr) : 1.0f;
+    float h = r * 1.01f;
+    if (h < 0.05f) h = 0.05f;
+    if (h > 4.0f) h = 4.0f;
+    return h;
+}
+
+// copy n points (stride) from the host into ctx->stage and pack them as float4 into dst
+static int upload_cloud(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, float4 *dst)
+{
+    if (n == 0) return SSF_OK;
+    SSF_ARG(xyz, "cloud pointer == NULL");
+    SSF_ARG(stride_bytes >= 12 && stride_bytes % 4 == 0, "stride_bytes must be a multiple of 4 and >= 12");
+    const size_t bytes = (n - 1) * stride_bytes + 12;
+    SSF_TRY(ctx->stage.reserve(bytes));
+    SSF_CUDA(cudaMemcpyAsync(ctx->stage.p, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    pack_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->stage.p, n, stride_bytes, dst);
+    SSF_LAUNCHED();
+    return SSF_OK;
+}
+
+// ---- registration object ------------------------------------------------------------------------
+extern "C" int ssf_icp_create(ssf_ctx *ctx, const ssf_icp_params *params, ssf_icp **out)
+{
+    SSF_ARG(ctx && out, "ssf_icp_create: NULL argument");
+    *out = nullptr;
+    SSF_TRY(check_params(params));
+    ssf_icp *h = new (std::nothrow) ssf_icp;
+    if (!h) return SSF_ERR_NOMEM;
+    h->ctx = ctx;
+    h->prm = *params;
+    for (int i = 0; i < 16; ++i) h->T_init[i] = (i % 5 == 0) ? 1.f : 0.f;  // Matrix4f::Identity (cpp:11)
+    *out = h;
+    return SSF_OK;
+}
+
+extern "C" void ssf_icp_destroy(ssf_icp *icp)
+{
+    if (!icp) return;
+    cudaSetDevice(icp->ctx->device);
+    cudaStreamSynchronize(icp->ctx->stream);
+    if (icp->single) ssf_batch_destroy(icp->single);
+    delete icp;
+}
+
+extern "C" int ssf_icp_set_params(ssf_icp *icp, const ssf_icp_params *params)
+{
+    SSF_ARG(icp, "ssf_icp_set_params: icp == NULL");
+    SSF_TRY(check_params(params));
+    icp->prm = *params;
+    return SSF_OK;
+}
+
+extern "C" int ssf_icp_get_params(const ssf_icp *icp, ssf_icp_params *out)
+{
+    SSF_ARG(icp && out, "ssf_icp_get_params: NULL argument");
+    *out = icp->prm;
+    return SSF_OK;
+}
+
+extern "C" size_t ssf_icp_target_size(const ssf_icp *icp) { return icp ? icp->map.n_raw : 0; }
+
+extern "C" int ssf_icp_set_target(ssf_icp *icp, const float *xyz, size_t n, size_t stride_bytes, const float *normals,
+                                  size_t normals_stride_bytes)
+{
+    SSF_ARG(icp, "ssf_icp_set_target: icp == NULL");
+    SSF_ARG(n == 0 || xyz, "ssf_icp_set_target: xyz == NULL");
+    SSF_ARG(n < ((size_t)1 << 31), "ssf_icp_set_target: more than 2^31 - 1 points");
+    ssf_ctx *ctx = icp->ctx;
+    SSF_TRY(use_device(ctx));
+    icp->has_target = false;
+    MapIndex &m = icp->map;
+    m.n_raw = n;
+    m.has_normals = normals != nullptr && n > 0;
+    SSF_TRY(m.raw.reserve(n ? n : 1));
+    SSF_TRY(upload_cloud(ctx, xyz, n, stride_bytes, m.raw.p));
+    if (m.has_normals) {
+        SSF_TRY(m.raw_nrm.reserve(n));
+        SSF_CUDA(cudaStreamSynchronize(ctx->stream));  // stage buffer is reused
+        SSF_TRY(upload_cloud(ctx, normals, n, normals_stride_bytes, m.raw_nrm.p));
+    }
+    SSF_TRY(build_map_index(m, cell_size_for(icp->prm.max_correspondence_dist), ctx->scratch, ctx->stream));
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    icp->has_target = true;
+    return SSF_OK;
+}
+
+// re-index when the threshold moved far from the one the cells were sized for
+static int maybe_reindex(ssf_icp *icp)
+{
+    const float want = cell_size_for(icp->prm.max_correspondence_dist);
+    const float have = icp->map.cell_size;
+    if (have > 0.f && (want > 1.6f * have || want < 0.6f * have)) {
+        SSF_TRY(build_map_index(icp->map, want, icp->ctx->scratch, icp->ctx->stream));
+    }
+    return SSF_OK;
+}
+
+extern "C" int ssf_icp_set_initial(ssf_icp *icp, const float T_colmajor[16])
+{
+    SSF_ARG(icp && T_colmajor, "ssf_icp_set_initial: NULL argument");
+    memcpy(icp->T_init, T_colmajor, sizeof(icp->T_init));
+    return SSF_OK;
+}
+
+extern "C" int ssf_icp_set_source(ssf_icp *icp, const float *xyz, size_t n, size_t stride_bytes)
+{
+    SSF_ARG(icp, "ssf_icp_set_source: icp == NULL");
+    SSF_ARG(n == 0 || xyz, "ssf_icp_set_source: xyz == NULL");
+    SSF_TRY(use_device(icp->ctx));
+    if (!icp->single || icp->single->max_points < n) {
+        if (icp->single) ssf_batch_destroy(icp->single);
+        icp->single = nullptr;
+        SSF_TRY(ssf_batch_create(icp, 1, n + n / 4 + 1024, &icp->single));
+    }
+    const size_t cnt = n;
+    SSF_TRY(ssf_batch_upload(icp->single, xyz, &cnt, 1, stride_bytes ? stride_bytes : 16));
+    icp->has_source = true;
+    icp->n_source = n;
+    return SSF_OK;
+}
+
+extern "C" int ssf_icp_align(ssf_icp *icp, ssf_icp_result *out)
+{
+    SSF_ARG(icp && out, "ssf_icp_align: NULL argument");
+    if (!icp->has_target) {
+        set_error("ssf_icp_align: no target set (call ssf_icp_set_target first)");
+        return SSF_ERR_STATE;
+    }
+    if (!icp->has_source) {
+        set_error("ssf_icp_align: no source set (call ssf_icp_set_source first)");
+        return SSF_ERR_STATE;
+    }
+    SSF_TRY(ssf_batch_set_initial(icp->single, icp->T_init));
+    SSF_TRY(ssf_batch_run(icp->single));
+    SSF_TRY(ssf_batch_results(icp->single, out, 1));
+    if (out->aborted) fprintf(stderr, "[ICP ERROR] Not enough valid correspondences found. Aborting.\n");  // cpp:198
+    if (icp->prm.debug && icp->prm.mode == SSF_MODE_REFERENCE && !out->aborted) {
+        // printStepDebug / tail of calculateAlignment (cpp:172-183, 237-246)
+        std::vector<float> err(icp->prm.num_iterations);
+        std::vector<int32_t> srch(icp->prm.num_iterations);
+        if (ssf_icp_get_trace(icp, err.data(), srch.data(), err.size()) == SSF_OK) {
+            for (size_t i = 0; i < err.size(); ++i) {
+                if (err[i] != err[i]) break;
+                printf("[ICP INFO] Iteration %zu - Error: %g\n", i, err[i]);
+                if (err[i] < icp->prm.acceptable_mean_error)
+                    printf("[ICP INFO] Acceptable error reached. Stopping iterations.\n");
+                if (srch[i]) printf("[ICP INFO] Transformation epsilon reached. Stopping iterations.\n");
+            }
+        }
+        if (out->iterations == icp->prm.num_iterations)
+            printf("[ICP INFO] We reached the maximum number of iterations. Returning best transform found.\n");
+        printf("[ICP INFO] Total iterations taken: %d\n[ICP INFO] Final error: %g\n", out->iterations, out->error);
+    }
+    return SSF_OK;
+}
+
+extern "C" int ssf_icp_get_correspondences(ssf_icp *icp, int32_t *idx_out, size_t n)
+{
+    SSF_ARG(icp && (idx_out || n == 0), "ssf_icp_get_correspondences: NULL argument");
+    if (!icp->single || !icp->single->ran) {
+        set_error("ssf_icp_get_correspondences: no alignment has run");
+        return SSF_ERR_STATE;
+    }
+    SSF_ARG(n <= icp->single->n_raw[0], "ssf_icp_get_correspondences: n larger than the source");
+    SSF_TRY(use_device(icp->ctx));
+    if (n == 0) return SSF_OK;
+    SSF_CUDA(cudaMemcpyAsync(idx_out, icp->single->buf.corr.p + icp->single->meta_host[2], n * sizeof(int32_t),
+                             cudaMemcpyDeviceToHost, icp->ctx->stream));
+    SSF_CUDA(cudaStreamSynchronize(icp->ctx->stream));
+    return SSF_OK;
+}
+
+extern "C" int ssf_icp_get_trace(ssf_icp *icp, float *iter_err, int32_t *iter_searched, size_t n)
+{
+    SSF_ARG(icp, "ssf_icp_get_trace: icp == NULL");
+    if (!icp->single || !icp->single->ran) {
+        set_error("ssf_icp_get_trace: no alignment has run");
+        return SSF_ERR_STATE;
+    }
+    SSF_TRY(use_device(icp->ctx));
+    const size_t have = (size_t)icp->single->buf.trace_len;
+    for (size_t i = 0; i < n; ++i) {
+        if (iter_err) iter_err[i] = NAN;
+        if (iter_searched) iter_searched[i] = 0;
+    }
+    const size_t m = n < have ? n : have;
+    if (m == 0) return SSF_OK;
+    if (iter_err)
+        SSF_CUDA(cudaMemcpyAsync(iter_err, icp->single->buf.trace_err.p, m * sizeof(float), cudaMemcpyDeviceToHost,
+                                 icp->ctx->stream));
+    if (iter_searched)
+        SSF_CUDA(cudaMemcpyAsync(iter_searched, icp->single->buf.trace_search.p, m * sizeof(int32_t),
+                                 cudaMemcpyDeviceToHost, icp->ctx->stream));
+    SSF_CUDA(cudaStreamSynchronize(icp->ctx->stream));
+    return SSF_OK;
+}
+
+extern "C" int ssf_nn_search(ssf_icp *icp, const float *queries, size_t n, size_t stride_bytes, float max_sqdist,
+                             int32_t *idx, float *d2)
+{
+    SSF_ARG(icp, "ssf_nn_search: icp == NULL");
+    SSF_ARG(n == 0 || (queries && idx && d2), "ssf_nn_search: NULL argument");
+    if (!icp->has_target) {
+        set_error("ssf_nn_search: no target set");
+        return SSF_ERR_STATE;
+    }
+    if (n == 0) return SSF_OK;
+    ssf_ctx *ctx = icp->ctx;
+    SSF_TRY(use_device(ctx));
+    SSF_TRY(icp->q_dev.reserve(n));
+    SSF_TRY(icp->q_idx.reserve(n));
+    SSF_TRY(icp->q_d2.reserve(n));
+    SSF_TRY(upload_cloud(ctx, queries, n, stride_bytes, icp->q_dev.p));
+    SSF_TRY(nn_search_device(icp->map.view, icp->q_dev.p, n, max_sqdist, icp->q_idx.p, icp->q_d2.p, ctx->stream));
+    SSF_CUDA(cudaMemcpyAsync(idx, icp->q_idx.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SSF_CUDA(cudaMemcpyAsync(d2, icp->q_d2.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SSF_OK;
+}
+
+// ---- voxel grid ---------------------------------------------------------------------------------
+extern "C" int ssf_voxel_downsample(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, float leaf,
+                                    float *out, size_t *n_out, int *refused)
+{
+    SSF_ARG(ctx && n_out, "ssf_voxel_downsample: NULL argument");
+    SSF_ARG(n == 0 || (xyz && out), "ssf_voxel_downsample: NULL cloud");
+    SSF_ARG(leaf > 0.f && std::isfinite(leaf), "ssf_voxel_downsample: leaf must be > 0");
+    SSF_ARG(n < ((size_t)1 << 31), "ssf_voxel_downsample: more than 2^31 - 1 points");
+    *n_out = 0;
+    if (refused) *refused = 0;
+    if (n == 0) return SSF_OK;
+    SSF_TRY(use_device(ctx));
+    VoxelWork w;
+    SSF_TRY(w.in.reserve(n));
+    SSF_TRY(w.out.reserve(n));
+    SSF_TRY(upload_cloud(ctx, xyz, n, stride_bytes, w.in.p));
+    uint32_t cnt = 0;
+    int ref = 0;
+    SSF_TRY(voxel_downsample_device(w, n, leaf, ctx->scratch, ctx->stream, &cnt, &ref));
+    SSF_CUDA(cudaMemcpyAsync(out, w.out.p, (size_t)cnt * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_out = cnt;
+    if (refused) *refused = ref;
+    return SSF_OK;
+}
+
+// ---- batches ------------------------------------------------------------------------------------
+extern "C" int ssf_batch_create(ssf_icp *icp, size_t max_scans, size_t max_total_points, ssf_batch **out)
+{
+    SSF_ARG(icp && out, "ssf_batch_create: NULL argument");
+    SSF_ARG(max_scans >= 1 && max_scans < (1u << 24), "ssf_batch_create: max_scans out of range");
+    SSF_ARG(max_total_points + max_scans * kTile < ((size_t)1 << 31), "ssf_batch_create: too many points");
+    *out = nullptr;
+    SSF_TRY(use_device(icp->ctx));
+    ssf_batch *b = new (std::nothrow) ssf_batch;
+    if (!b) return SSF_ERR_NOMEM;
+    b->icp = icp;
+    b->max_scans = max_scans;
+    b->max_points = max_total_points;
+    const size_t slots = max_total_points + max_scans * kTile;  // tile alignment padding
+    const size_t tiles = slots / kTile + 1;
+    int rc = SSF_OK;
+    auto chk = [&](int r) { if (rc == SSF_OK) rc = r; };
+    chk(b->buf.src.reserve(slots));
+    chk(b->buf.corr.reserve(slots));
+    chk(b->buf.tile_scan.reserve(tiles));
+    chk(b->buf.partials.reserve(tiles * kAccum));
+    chk(b->buf.state.reserve(max_scans));
+    chk(b->buf.results.reserve(max_scans));
+    chk(b->T_init_dev.reserve(max_scans * 16));
+    chk(b->meta_dev.reserve(max_scans * 5));
+    if (rc != SSF_OK) {
+        delete b;
+        return rc;
+    }
+    *out = b;
+    return SSF_OK;
+}
+
+extern "C" void ssf_batch_destroy(ssf_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->icp->ctx->device);
+    cudaStreamSynchronize(b->icp->ctx->stream);
+    delete b;
+}
+
+extern "C" int ssf_batch_upload(ssf_batch *b, const float *xyz, const size_t *n_pts, size_t n_scans,
+                                size_t stride_bytes)
+{
+    SSF_ARG(b && n_pts, "ssf_batch_upload: NULL argument");
+    SSF_ARG(n_scans >= 1 && n_scans <= b->max_scans, "ssf_batch_upload: n_scans exceeds the batch capacity");
+    SSF_ARG(stride_bytes >= 12 && stride_bytes % 4 == 0, "stride_bytes must be a multiple of 4 and >= 12");
+    ssf_ctx *ctx = b->icp->ctx;
+    SSF_TRY(use_device(ctx));
+    size_t total = 0;
+    for (size_t s = 0; s < n_scans; ++s) total += n_pts[s];
+    SSF_ARG(total <= b->max_points, "ssf_batch_upload: points exceed the batch capacity");
+    SSF_ARG(total == 0 || xyz, "ssf_batch_upload: xyz == NULL");
+    b->meta_host.assign(5 * n_scans, 0);
+    b->n_raw.assign(n_scans, 0);
+    size_t raw = 0, tile = 0;
+    uint32_t max_n = 0;
+    for (size_t s = 0; s < n_scans; ++s) {
+        const uint32_t n = (uint32_t)n_pts[s];
+        const uint32_t cap = (n + kTile - 1) / kTile;
+        b->meta_host[5 * s + 0] = (uint32_t)raw;
+        b->meta_host[5 * s + 1] = n;
+        b->meta_host[5 * s + 2] = (uint32_t)(tile * kTile);
+        b->meta_host[5 * s + 3] = (uint32_t)tile;
+        b->meta_host[5 * s + 4] = cap;
+        b->n_raw[s] = n;
+        raw += n;
+        tile += cap;
+        if (n > max_n) max_n = n;
+    }
+    b->buf.n_scans = n_scans;
+    b->buf.n_tiles = tile;
+    b->buf.n_slots = tile * kTile;
+    b->total_points = total;
+    // previous work on the stream may still read meta/stage: the stream orders it
+    SSF_CUDA(cudaMemcpyAsync(b->meta_dev.p, b->meta_host.data(), b->meta_host.size() * sizeof(uint32_t),
+                             cudaMemcpyHostToDevice, ctx->stream));
+    if (total > 0) {
+        const size_t bytes = (total - 1) * stride_bytes + 12;
+        SSF_TRY(ctx->stage.reserve(bytes));
+        SSF_CUDA(cudaMemcpyAsync(ctx->stage.p, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        unsigned bx = (max_n + 255) / 256;
+        if (bx > 64) bx = 64;
+        if (bx == 0) bx = 1;
+        pack_scans_kernel<<<dim3(bx, (unsigned)n_scans), 256, 0, ctx->stream>>>(ctx->stage.p, stride_bytes, b->meta_dev.p,
+                                                                              b->buf.src.p);
+        SSF_LAUNCHED();
+    }
+    layout_kernel<<<(unsigned)n_scans, 128, 0, ctx->stream>>>(b->buf.state.p, b->meta_dev.p, (uint32_t)n_scans,
+                                                             b->buf.tile_scan.p);
+    SSF_LAUNCHED();
+    // the host vectors are pageable: make sure the copies above have consumed them
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    b->uploaded = true;
+    b->initial_set = false;
+    b->ran = false;
+    return SSF_OK;
+}
+
+extern "C" int ssf_batch_set_initial(ssf_batch *b, const float *T_colmajor)
+{
+    SSF_ARG(b && T_colmajor, "ssf_batch_set_initial: NULL argument");
+    if (!b->uploaded) {
+        set_error("ssf_batch_set_initial: upload scans first");
+        return SSF_ERR_STATE;
+    }
+    ssf_ctx *ctx = b->icp->ctx;
+    SSF_TRY(use_device(ctx));
+    SSF_CUDA(cudaMemcpyAsync(b->T_init_dev.p, T_colmajor, b->buf.n_scans * 16 * sizeof(float), cudaMemcpyHostToDevice,
+                             ctx->stream));
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    b->initial_set = true;
+    return SSF_OK;
+}
+
+extern "C" int ssf_batch_run(ssf_batch *b)
+{
+    SSF_ARG(b, "ssf_batch_run: b == NULL");
+    ssf_icp *icp = b->icp;
+    if (!icp->has_target) {
+        set_error("ssf_batch_run: no target set");
+        return SSF_ERR_STATE;
+    }
+    if (!b->uploaded || !b->initial_set) {
+        set_error("ssf_batch_run: upload scans and set initial transforms first");
+        return SSF_ERR_STATE;
+    }
+    ssf_ctx *ctx = icp->ctx;
+    SSF_TRY(use_device(ctx));
+    SSF_TRY(maybe_reindex(icp));
+    const ssf_icp_params &p = icp->prm;
+    BatchBuffers &buf = b->buf;
+    const int trace_len = p.mode == SSF_MODE_REFERENCE ? p.num_iterations : 0;
+    buf.trace_len = trace_len;
+    SSF_TRY(buf.trace_err.reserve(buf.n_scans * (size_t)(trace_len ? trace_len : 1)));
+    SSF_TRY(buf.trace_search.reserve(buf.n_scans * (size_t)(trace_len ? trace_len : 1)));
+    if (p.mode == SSF_MODE_REFERENCE) {
+        SSF_TRY(buf.P.reserve(buf.src.cap));
+        SSF_TRY(buf.Q.reserve(buf.src.cap));
+    }
+    SSF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    SSF_TRY(init_states(buf, b->T_init_dev.p, ctx->stream));
+    IcpConfig cfg{p.max_correspondence_dist, p.num_iterations, p.acceptable_mean_error, p.transformation_epsilon,
+                  p.mode, p.reduce};
+    SSF_TRY(run_batch(icp->map.view, cfg, buf, ctx->stream));
+    SSF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    b->ran = true;
+    return SSF_OK;
+}
+
+extern "C" int ssf_batch_results(ssf_batch *b, ssf_icp_result *out, size_t n_scans)
+{
+    SSF_ARG(b && out, "ssf_batch_results: NULL argument");
+    if (!b->ran) {
+        set_error("ssf_batch_results: the batch has not run");
+        return SSF_ERR_STATE;
+    }
+    SSF_ARG(n_scans <= b->buf.n_scans, "ssf_batch_results: n_scans larger than the batch");
+    ssf_ctx *ctx = b->icp->ctx;
+    SSF_TRY(use_device(ctx));
+    SSF_CUDA(cudaMemcpyAsync(out, b->buf.results.p, n_scans * sizeof(ssf_icp_result), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) {
+        cudaGetLastError();
+        ms = 0.f;
+    }
+    b->last_ms = ms;
+    for (size_t s = 0; s < n_scans; ++s) out[s].device_ms = ms;
+    return SSF_OK;
+}
+
+extern "C" int ssf_icp_align_batch(ssf_icp *icp, const float *xyz, const size_t *n_pts, size_t n_scans,
+                                   size_t stride_bytes, const float *T_colmajor, ssf_icp_result *out)
+{
+    SSF_ARG(icp && n_pts && T_colmajor && out, "ssf_icp_align_batch: NULL argument");
+    SSF_ARG(n_scans >= 1, "ssf_icp_align_batch: n_scans == 0");
+    size_t total = 0;
+    for (size_t s = 0; s < n_scans; ++s) total += n_pts[s];
+    ssf_batch *b = nullptr;
+    SSF_TRY(ssf_batch_create(icp, n_scans, total + 1, &b));
+    int rc = ssf_batch_upload(b, xyz, n_pts, n_scans, stride_bytes);
+    if (rc == SSF_OK) rc = ssf_batch_set_initial(b, T_colmajor);
+    if (rc == SSF_OK) rc = ssf_batch_run(b);
+    if (rc == SSF_OK) rc = ssf_batch_results(b, out, n_scans);
+    ssf_batch_destroy(b);
+    return rc;
+}

@@ -1,0 +1,66 @@
+// icp.cuh -- device-side state of a batch of scans and the host entry points of the solver.
+#pragma once
+#include "common.cuh"
+#include "map_index.cuh"
+
+namespace ssf {
+
+constexpr int kTile = 256;  // queries per block of the search kernels; scans are tile-aligned
+constexpr int kAccum = 32;  // doubles per partial row
+
+// One scan of a batch (device memory).
+struct ScanState {
+    float T[16];       // composed transform, column-major
+    float T_step[16];  // REFERENCE: last step, applied to P by ref_step_kernel
+    float T_init[16];
+    float last_error;  // ICPPointToPoint::last_error_
+    float error;       // error reported in the result
+    float pend_error;  // REFERENCE: error of the pass that decided to re-search
+    int iterations, done, converged, aborted, n_searches, k_last, need_search, have_step;
+    double fitness, rmse;  // O3D
+    uint32_t pt_begin;     // first slot in the packed arrays (multiple of kTile)
+    uint32_t n_pts;        // source points (after optional voxel downsample)
+    uint32_t tile_begin, tile_cap;
+};
+
+struct BatchBuffers {
+    // packed, tile-aligned per scan
+    DevBuf<float4> src;        // source points (sensor frame)
+    DevBuf<float4> P;          // REFERENCE: transformed source, advanced in place
+    DevBuf<float4> Q;          // REFERENCE: matched target point per row
+    DevBuf<int32_t> corr;      // correspondence (original target index) or -1
+    DevBuf<uint32_t> tile_scan;
+    DevBuf<double> partials;   // [tile][kAccum]
+    DevBuf<ScanState> state;
+    DevBuf<ssf_icp_result> results;
+    DevBuf<float> trace_err;       // [scan][num_iterations]
+    DevBuf<int32_t> trace_search;  // [scan][num_iterations]
+    // voxel-downsample stage
+    DevBuf<float4> raw;            // raw scans when source_voxel_leaf > 0
+    DevBuf<unsigned long long> vkeys;
+    DevBuf<uint32_t> vvals;
+    DevBuf<uint32_t> vflags, vscan;
+    DevBuf<float> vbox;            // per scan: min xyz, max xyz (ordered ints during reduce)
+    DevBuf<int32_t> vgrid;         // per scan: minb[3], divb[3], refused, pad
+    size_t n_scans = 0, n_tiles = 0, n_slots = 0;
+    int trace_len = 0;
+};
+
+struct IcpConfig {
+    float max_corr;
+    int num_iterations;
+    float acc_err;
+    float eps;
+    int mode;
+    int reduce;
+};
+
+// Enqueue the whole alignment of every scan in the batch on `st` (no host sync inside).
+int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStream_t st);
+// standalone search over n already-transformed queries (device pointers)
+int nn_search_device(const MapView &map, const float4 *queries, size_t n, float limit, int32_t *idx, float *d2,
+                     cudaStream_t st);
+// initialise ScanState from T_init (device array n_scans x 16) -- also resets counters
+int init_states(BatchBuffers &b, const float *T_init_dev, cudaStream_t st);
+
+}  // namespace ssf

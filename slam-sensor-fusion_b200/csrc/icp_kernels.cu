@@ -1,0 +1,654 @@
+// icp_kernels.cu -- K3/K4/K5: the registration loop on the device.
+//
+// Replaces ICPPointToPoint::calculateAlignment and its helpers (reference
+// localization/src/icp_point_to_point.cpp:57-84, 99-110, 112-159, 161-170, 185-254) for a
+// batch of independent scans against one HBM-resident map.  No host round trip inside an
+// alignment: the data-dependent control flow (abort, early break, lazy re-search) lives in
+// per-scan device state, and every kernel of the fixed launch sequence exits early for
+// scans that are done.
+//
+//   search_accum_kernel<GN|KABSCH>  transform + exact NN + rejection + per-block partial sums
+//   solve_gn_kernel / solve_o3d_kernel   ordered sum of the partial rows + 6x6 Cholesky or
+//                                         3x3 SVD + pose update + stop rules
+//   ref_search_kernel / ref_reduce_kernel / ref_step_kernel   the reference's own state
+//                                         machine, STRICT (sequential float chains) or FAST
+#include <cmath>
+
+#include "icp.cuh"
+#include "nn_device.cuh"
+#include "small_math.cuh"
+
+namespace ssf {
+
+// =========================================================================================
+// state init / results
+// =========================================================================================
+__global__ void init_states_kernel(ScanState *st, const float *T_init, uint32_t n_scans, float *trace_err,
+                                   int32_t *trace_search, int trace_len)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scans) return;
+    ScanState &z = st[s];
+    for (int i = 0; i < 16; ++i) {
+        const float v = T_init[16 * s + i];
+        z.T[i] = v;
+        z.T_init[i] = v;
+        z.T_step[i] = (i % 5 == 0) ? 1.f : 0.f;
+    }
+    z.last_error = FLT_MAX;
+    z.error = 1e6f;
+    z.pend_error = 0.f;
+    z.iterations = 0;
+    z.done = 0;
+    z.converged = 0;
+    z.aborted = 0;
+    z.n_searches = 0;
+    z.k_last = 0;
+    z.need_search = 0;
+    z.have_step = 0;
+    z.fitness = 0.0;
+    z.rmse = 0.0;
+    for (int i = 0; i < trace_len; ++i) {
+        trace_err[(size_t)s * trace_len + i] = nanf("");
+        trace_search[(size_t)s * trace_len + i] = 0;
+    }
+}
+
+int init_states(BatchBuffers &b, const float *T_init_dev, cudaStream_t st)
+{
+    if (b.n_scans == 0) return SSF_OK;
+    init_states_kernel<<<(unsigned)((b.n_scans + 127) / 128), 128, 0, st>>>(b.state.p, T_init_dev, (uint32_t)b.n_scans,
+                                                                          b.trace_err.p, b.trace_search.p, b.trace_len);
+    SSF_LAUNCHED();
+    return SSF_OK;
+}
+
+__global__ void results_kernel(ScanState *st, ssf_icp_result *out, uint32_t n_scans, int mode, float acc_err)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scans) return;
+    ScanState &z = st[s];
+    ssf_icp_result r;
+    if (mode == SSF_MODE_REFERENCE && !z.aborted) {
+        // cpp:249-253: error = last_error_, has_converged = last_error_ < acceptable_mean_error_
+        z.error = z.last_error;
+        z.converged = z.last_error < acc_err ? 1 : 0;
+    }
+    for (int i = 0; i < 16; ++i) r.transformation[i] = z.aborted ? z.T_init[i] : z.T[i];
+    r.error = z.aborted ? 1e6f : z.error;
+    r.iterations = z.aborted ? 0 : z.iterations;
+    r.has_converged = z.aborted ? 0 : z.converged;
+    r.n_searches = z.n_searches;
+    r.k_final = z.k_last;
+    r.aborted = z.aborted;
+    r.n_source = (int32_t)z.n_pts;
+    r.fitness = z.n_pts ? (float)((double)z.k_last / (double)z.n_pts) : 0.f;
+    r.device_ms = 0.f;
+    out[s] = r;
+}
+
+// =========================================================================================
+// K3 + K4 fused: transform, exact NN, rejection, partial sums (GN and Open3D-flow modes)
+// =========================================================================================
+enum AccumKind { ACC_GN_P2P = 0, ACC_GN_P2PLANE = 1, ACC_KABSCH = 2 };
+
+// layout of a partial row (kAccum doubles)
+//   GN:     [0..20] upper triangle of J^T J (row-major), [21..26] J^T r, [27] sum r^2, [28] K
+//   KABSCH: [0] K, [1..3] sum (p-c), [4..6] sum (q-c), [7..15] sum (p-c)(q-c)^T (row r, col c),
+//           [16] sum |p-q|^2, c = translation of the initial transform (pivot against cancellation)
+
+template <int KIND>
+__global__ void __launch_bounds__(kTile)
+    search_accum_kernel(MapView map, const float4 *__restrict__ src, const uint32_t *__restrict__ tile_scan,
+                        const ScanState *__restrict__ states, float limit, int32_t *__restrict__ corr,
+                        double *__restrict__ partials)
+{
+    __shared__ float sT[16];
+    __shared__ double sred[kTile / 32][kAccum];
+    const uint32_t scan = tile_scan[blockIdx.x];
+    const ScanState &z = states[scan];
+    if (z.done) return;
+    const uint32_t row0 = (blockIdx.x - z.tile_begin) * kTile;
+    if (row0 >= z.n_pts) return;
+    if (threadIdx.x < 16) sT[threadIdx.x] = z.T[threadIdx.x];
+    __syncthreads();
+    const uint32_t row = row0 + threadIdx.x;
+    const bool valid = row < z.n_pts;
+    double v[kAccum];
+#pragma unroll
+    for (int i = 0; i < kAccum; ++i) v[i] = 0.0;
+    if (valid) {
+        const size_t slot = (size_t)z.pt_begin + row;
+        const float4 s4 = src[slot];
+        const float3 p = transform_point(sT, s4.x, s4.y, s4.z);
+        const NNHit h = nn_query(map, p.x, p.y, p.z, limit);
+        corr[slot] = h.idx;
+        if (h.idx >= 0) {
+            const float4 q = __ldg(&map.pts[h.pos]);
+            if (KIND == ACC_KABSCH) {
+                const double cx = z.T_init[12], cy = z.T_init[13], cz = z.T_init[14];
+                const double a[3] = {(double)p.x - cx, (double)p.y - cy, (double)p.z - cz};
+                const double b[3] = {(double)q.x - cx, (double)q.y - cy, (double)q.z - cz};
+                v[0] = 1.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    v[1 + k] = a[k];
+                    v[4 + k] = b[k];
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[7 + 3 * r + c] = a[r] * b[c];
+                const double ex = (double)p.x - q.x, ey = (double)p.y - q.y, ez = (double)p.z - q.z;
+                v[16] = ex * ex + ey * ey + ez * ez;
+            } else {
+                const double px = p.x, py = p.y, pz = p.z;
+                const double e[3] = {px - (double)q.x, py - (double)q.y, pz - (double)q.z};
+                if (KIND == ACC_GN_P2PLANE) {
+                    const float4 nf = __ldg(&map.nrm[h.pos]);
+                    const double n[3] = {nf.x, nf.y, nf.z};
+                    const double a[6] = {py * n[2] - pz * n[1], pz * n[0] - px * n[2], px * n[1] - py * n[0],
+                                         n[0], n[1], n[2]};
+                    const double r = n[0] * e[0] + n[1] * e[1] + n[2] * e[2];
+                    int t = 0;
+#pragma unroll
+                    for (int u = 0; u < 6; ++u)
+#pragma unroll
+                        for (int w = u; w < 6; ++w) v[t++] = a[u] * a[w];
+#pragma unroll
+                    for (int u = 0; u < 6; ++u) v[21 + u] = a[u] * r;
+                    v[27] = r * r;
+                } else {
+                    // J = [-[p]x | I]; J^T J = [[ -[p]x^T -[p]x , [p]x ], [ -[p]x , I ]]
+                    const double J[3][6] = {{0, pz, -py, 1, 0, 0}, {-pz, 0, px, 0, 1, 0}, {py, -px, 0, 0, 0, 1}};
+                    int t = 0;
+#pragma unroll
+                    for (int u = 0; u < 6; ++u)
+#pragma unroll
+                        for (int w = u; w < 6; ++w) v[t++] = J[0][u] * J[0][w] + J[1][u] * J[1][w] + J[2][u] * J[2][w];
+#pragma unroll
+                    for (int u = 0; u < 6; ++u) v[21 + u] = J[0][u] * e[0] + J[1][u] * e[1] + J[2][u] * e[2];
+                    v[27] = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+                }
+                v[28] = 1.0;
+            }
+        }
+    }
+    const double w = warp_transpose_reduce32(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    sred[warp][lane] = w;
+    __syncthreads();
+    if (threadIdx.x < kAccum) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < kTile / 32; ++k) s += sred[k][threadIdx.x];
+        partials[(size_t)blockIdx.x * kAccum + threadIdx.x] = s;
+    }
+}
+
+// ordered sum of the partial rows of one scan; one warp per scan, lane = value index
+__device__ __forceinline__ double sum_partials(const ScanState &z, const double *partials)
+{
+    const uint32_t n_tiles = (z.n_pts + kTile - 1) / kTile;
+    double s = 0.0;
+    for (uint32_t t = 0; t < n_tiles; ++t) s += partials[(size_t)(z.tile_begin + t) * kAccum + threadIdx.x];
+    return s;
+}
+
+__global__ void __launch_bounds__(32) solve_gn_kernel(ScanState *states, const double *__restrict__ partials, int pass,
+                                                      float acc_err, float eps)
+{
+    __shared__ double sv[kAccum];
+    ScanState &z = states[blockIdx.x];
+    if (z.done) return;
+    sv[threadIdx.x] = sum_partials(z, partials);
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const long long K = (long long)(sv[28] + 0.5);
+    z.n_searches += 1;
+    z.k_last = (int)K;
+    if (pass == 0 && K < 10) {  // same guard as the reference's first search (cpp:196-200)
+        z.aborted = 1;
+        z.done = 1;
+        return;
+    }
+    if (K < 6) { z.done = 1; return; }
+    const float err = (float)sqrt(sv[27] / (double)K);
+    z.error = err;
+    if (err < acc_err) { z.converged = 1; z.done = 1; return; }
+    double A[36], nb[6], x[6];
+    int t = 0;
+    for (int u = 0; u < 6; ++u)
+        for (int w = u; w < 6; ++w) {
+            A[u * 6 + w] = sv[t];
+            A[w * 6 + u] = sv[t];
+            ++t;
+        }
+    for (int u = 0; u < 6; ++u) nb[u] = -sv[21 + u];
+    if (!cholesky_solve6(A, nb, x)) { z.done = 1; return; }
+    double Ts[16];
+    se3_from_twist(x, Ts);
+    compose_round(Ts, z.T);
+    z.iterations += 1;
+    double mx = 0.0;
+    for (int u = 0; u < 6; ++u) mx = fmax(mx, fabs(x[u]));
+    if (mx < (double)eps) { z.converged = 1; z.done = 1; }
+}
+
+__global__ void __launch_bounds__(32) solve_o3d_kernel(ScanState *states, const double *__restrict__ partials,
+                                                       int pass, int max_iteration)
+{
+    __shared__ double sv[kAccum];
+    ScanState &z = states[blockIdx.x];
+    if (z.done) return;
+    sv[threadIdx.x] = sum_partials(z, partials);
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    const long long K = (long long)(sv[0] + 0.5);
+    z.n_searches += 1;
+    z.k_last = (int)K;
+    const double prev_fit = z.fitness, prev_rmse = z.rmse;
+    z.fitness = z.n_pts ? (double)K / (double)z.n_pts : 0.0;
+    z.rmse = K > 0 ? sqrt(sv[16] / (double)K) : 0.0;
+    z.error = (float)z.rmse;
+    if (pass > 0 && fabs(prev_fit - z.fitness) < 1e-6 && fabs(prev_rmse - z.rmse) < 1e-6) {
+        z.converged = 1;
+        z.done = 1;
+        return;
+    }
+    if (pass == max_iteration || K == 0) { z.done = 1; return; }
+    // un-pivot: centroids and centred cross-covariance
+    const double c[3] = {z.T_init[12], z.T_init[13], z.T_init[14]};
+    double ma[3], mb[3], sp[3], sq[3], H[9];
+    for (int k = 0; k < 3; ++k) {
+        ma[k] = sv[1 + k] / (double)K;
+        mb[k] = sv[4 + k] / (double)K;
+        sp[k] = ma[k] + c[k];
+        sq[k] = mb[k] + c[k];
+    }
+    for (int r = 0; r < 3; ++r)
+        for (int cc = 0; cc < 3; ++cc) H[cc * 3 + r] = sv[7 + 3 * r + cc] - (double)K * ma[r] * mb[cc];
+    double Ts[16];
+    kabsch_from_moments_d(sp, sq, H, Ts);
+    compose_round(Ts, z.T);
+    z.iterations += 1;
+}
+
+// =========================================================================================
+// REFERENCE mode (icp_point_to_point.cpp:185-254)
+// =========================================================================================
+
+// sourceTargetCorrespondences (cpp:57-84).  first != 0: P = T_init * src (cpp:191-192) and
+// every row is searched; later searches only touch rows that still have a correspondence
+// (the source shrinks, cpp:77-83).  Rows are not physically compacted: corr < 0 marks a row
+// as dropped, and dropped rows add exact zeros to the ordered sums.
+__global__ void __launch_bounds__(kTile)
+    ref_search_kernel(MapView map, const float4 *__restrict__ src, float4 *__restrict__ P, float4 *__restrict__ Q,
+                      int32_t *__restrict__ corr, const uint32_t *__restrict__ tile_scan,
+                      const ScanState *__restrict__ states, float limit, int first)
+{
+    __shared__ float sT[16];
+    const uint32_t scan = tile_scan[blockIdx.x];
+    const ScanState &z = states[scan];
+    if (z.done || (!first && !z.need_search)) return;
+    const uint32_t row0 = (blockIdx.x - z.tile_begin) * kTile;
+    if (row0 >= z.n_pts) return;
+    if (first) {
+        if (threadIdx.x < 16) sT[threadIdx.x] = z.T_init[threadIdx.x];
+        __syncthreads();
+    }
+    const uint32_t row = row0 + threadIdx.x;
+    if (row >= z.n_pts) return;
+    const size_t slot = (size_t)z.pt_begin + row;
+    float3 p;
+    if (first) {
+        const float4 s4 = src[slot];
+        p = transform_point(sT, s4.x, s4.y, s4.z);
+        P[slot] = make_float4(p.x, p.y, p.z, 1.f);
+    } else {
+        if (corr[slot] < 0) return;
+        const float4 p4 = P[slot];
+        p = make_float3(p4.x, p4.y, p4.z);
+    }
+    const NNHit h = nn_query(map, p.x, p.y, p.z, limit);
+    corr[slot] = h.idx;
+    if (h.idx >= 0) {
+        float4 q = __ldg(&map.pts[h.pos]);
+        q.w = 1.f;
+        Q[slot] = q;
+    }
+}
+
+// applyTransformation(T_step, P) (cpp:230)
+__global__ void __launch_bounds__(kTile)
+    ref_step_kernel(float4 *__restrict__ P, const int32_t *__restrict__ corr, const uint32_t *__restrict__ tile_scan,
+                    ScanState *states)
+{
+    __shared__ float sT[16];
+    const uint32_t scan = tile_scan[blockIdx.x];
+    const ScanState &z = states[scan];
+    if (z.done || !z.have_step) return;
+    const uint32_t row0 = (blockIdx.x - z.tile_begin) * kTile;
+    if (row0 >= z.n_pts) return;
+    if (threadIdx.x < 16) sT[threadIdx.x] = z.T_step[threadIdx.x];
+    __syncthreads();
+    const uint32_t row = row0 + threadIdx.x;
+    if (row >= z.n_pts) return;
+    const size_t slot = (size_t)z.pt_begin + row;
+    if (corr[slot] < 0) return;
+    const float4 p4 = P[slot];
+    const float3 p = transform_point(sT, p4.x, p4.y, p4.z);
+    P[slot] = make_float4(p.x, p.y, p.z, 1.f);
+}
+
+// ---- ordered float chains (STRICT) ------------------------------------------------------------
+constexpr int kRefThreads = 256;
+constexpr int kChainTile = 512;
+constexpr int kChainMax = 9;
+
+struct ChainBuf {
+    float v[2][kChainMax][kChainTile + 1];
+};
+
+// per-row values of the first pass: |p - q| (cpp:166), p (cpp:119), q (cpp:120)
+__device__ __forceinline__ void rowvals_pass1(const float4 &p, const float4 &q, bool alive, float *o)
+{
+    if (!alive) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) o[i] = 0.f;
+        return;
+    }
+    const float dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+    const float yz = dy * dy + dz * dz;  // Eigen fixed-size-3 reduction: a0 + (a1 + a2)
+    o[0] = sqrtf(dx * dx + yz);
+    o[1] = p.x; o[2] = p.y; o[3] = p.z;
+    o[4] = q.x; o[5] = q.y; o[6] = q.z;
+}
+
+// per-row values of the second pass: (p - cs)(q - ct)^T, H(r,c) at index c*3 + r (cpp:126-134)
+__device__ __forceinline__ void rowvals_pass2(const float4 &p, const float4 &q, bool alive, const float *cs,
+                                              const float *ct, float *o)
+{
+    if (!alive) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) o[i] = 0.f;
+        return;
+    }
+    const float a[3] = {p.x - cs[0], p.y - cs[1], p.z - cs[2]};
+    const float b[3] = {q.x - ct[0], q.y - ct[1], q.z - ct[2]};
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) o[c * 3 + r] = a[r] * b[c];
+}
+
+// Sequential float sums of NCH per-row value streams over the rows of one scan, in row order.
+// Warp 0 walks the chains (lane = chain) while warps 1.. compute the next tile's values.
+template <int NCH, int PASS>
+__device__ void strict_chains(const float4 *P, const float4 *Q, const int32_t *corr, size_t base, uint32_t n,
+                              const float *cs, const float *ct, ChainBuf &buf, float *out /*[NCH] in smem*/)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_tiles = (n + kChainTile - 1) / kChainTile;
+    auto fill = [&](uint32_t t, int which) {
+        for (uint32_t j = threadIdx.x - 32; j < (uint32_t)kChainTile; j += kRefThreads - 32) {
+            const uint32_t row = t * kChainTile + j;
+            float o[kChainMax];
+            if (row < n) {
+                const bool alive = corr[base + row] >= 0;
+                float4 p = make_float4(0, 0, 0, 0), q = p;
+                if (alive) { p = P[base + row]; q = Q[base + row]; }
+                if (PASS == 1) rowvals_pass1(p, q, alive, o);
+                else rowvals_pass2(p, q, alive, cs, ct, o);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) o[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) buf.v[which][i][j] = o[i];
+        }
+    };
+    float acc = 0.f;
+    if (warp != 0 && n_tiles > 0) fill(0, 0);
+    __syncthreads();
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        if (warp == 0) {
+            if (lane < NCH) {
+                const float *col = buf.v[t & 1][lane];
+#pragma unroll 8
+                for (int j = 0; j < kChainTile; ++j) acc = __fadd_rn(acc, col[j]);
+            }
+        } else if (t + 1 < n_tiles) {
+            fill(t + 1, (t + 1) & 1);
+        }
+        __syncthreads();
+    }
+    if (warp == 0 && lane < NCH) out[lane] = acc;
+    __syncthreads();
+}
+
+// ---- parallel double sums (FAST) ----------------------------------------------------------------
+template <int NV, int PASS>
+__device__ void fast_sums(const float4 *P, const float4 *Q, const int32_t *corr, size_t base, uint32_t n,
+                          const float *cs, const float *ct, double *scratch /*[kRefThreads]*/, float *out)
+{
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    for (uint32_t row = threadIdx.x; row < n; row += kRefThreads) {
+        if (corr[base + row] < 0) continue;
+        const float4 p = P[base + row], q = Q[base + row];
+        float o[kChainMax];
+        if (PASS == 1) rowvals_pass1(p, q, true, o);
+        else rowvals_pass2(p, q, true, cs, ct, o);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] += (double)o[i];
+    }
+    for (int i = 0; i < NV; ++i) {
+        scratch[threadIdx.x] = acc[i];
+        __syncthreads();
+        for (int s = kRefThreads / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) scratch[threadIdx.x] += scratch[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[i] = (float)scratch[0];
+        __syncthreads();
+    }
+}
+
+__device__ uint32_t block_count_alive(const int32_t *corr, size_t base, uint32_t n, uint32_t *scratch)
+{
+    uint32_t c = 0;
+    for (uint32_t row = threadIdx.x; row < n; row += kRefThreads) c += corr[base + row] >= 0 ? 1u : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = c;
+    __syncthreads();
+    uint32_t tot = 0;
+    for (int w = 0; w < kRefThreads / 32; ++w) tot += scratch[w];
+    __syncthreads();
+    return tot;
+}
+
+// The per-pass control of calculateAlignment, one block per scan.
+//   phase 0: after the pre-loop search (cpp:195-205), then falls through to phase 1 of pass 0
+//   phase 1: top of pass i  -- error, break test, re-search test, else Kabsch step (cpp:209-234)
+//   phase 2: after a re-search -- Kabsch step on the new correspondences (cpp:226-234)
+__global__ void __launch_bounds__(kRefThreads)
+    ref_reduce_kernel(ScanState *states, const float4 *__restrict__ P, const float4 *__restrict__ Q,
+                      const int32_t *__restrict__ corr, int phase, int pass, int reduce, float acc_err, float eps,
+                      float *trace_err, int32_t *trace_search, int trace_len)
+{
+    __shared__ ChainBuf buf;
+    __shared__ double dscratch[kRefThreads];
+    __shared__ uint32_t uscratch[kRefThreads / 32];
+    __shared__ float sums1[7], sums2[9], cs[3], ct[3];
+    __shared__ int s_action;  // 0 stop, 1 kabsch
+    ScanState &z = states[blockIdx.x];
+    if (z.done) return;
+    if (phase == 2 && !z.need_search) return;
+    const size_t base = z.pt_begin;
+    const uint32_t n = z.n_pts;
+    uint32_t K = 0;
+    if (phase != 2 && threadIdx.x == 0) z.have_step = 0;  // the previous pass's step has been applied
+    if (phase != 1) K = block_count_alive(corr, base, n, uscratch);
+    if (phase == 0) {
+        if (threadIdx.x == 0) {
+            z.n_searches = 1;
+            z.k_last = (int)K;
+            if (K < 10) {  // cpp:196-200
+                z.aborted = 1;
+                z.done = 1;
+            }
+        }
+        if (K < 10) return;
+        phase = 1;
+    } else if (phase == 2) {
+        if (threadIdx.x == 0) {
+            z.n_searches += 1;
+            z.k_last = (int)K;
+            z.need_search = 0;
+            if (pass < trace_len) trace_search[(size_t)blockIdx.x * trace_len + pass] = 1;
+            if (K == 0) {  // contract: the reference divides by zero here (cpp:122-123)
+                z.last_error = z.pend_error;
+                z.done = 1;
+            }
+        }
+        if (K == 0) return;
+    }
+    // centroid / error chains (phase 1 needs the error; both need the centroids)
+    if (reduce == SSF_REDUCE_STRICT) strict_chains<7, 1>(P, Q, corr, base, n, nullptr, nullptr, buf, sums1);
+    else fast_sums<7, 1>(P, Q, corr, base, n, nullptr, nullptr, dscratch, sums1);
+    if (threadIdx.x == 0) {
+        s_action = 1;
+        const float kf = (float)z.k_last;
+        if (phase == 1) {
+            const float error = sums1[0] / kf;  // cpp:169
+            if (pass < trace_len) trace_err[(size_t)blockIdx.x * trace_len + pass] = error;
+            if (error < acc_err) {  // cpp:215-219
+                z.last_error = error;
+                z.done = 1;
+                s_action = 0;
+            } else if (fabsf(z.last_error - error) < eps) {  // cpp:221-224
+                z.need_search = 1;
+                z.pend_error = error;
+                s_action = 0;
+            } else {
+                z.pend_error = error;
+            }
+        }
+        for (int k = 0; k < 3; ++k) {  // cpp:122-123
+            cs[k] = sums1[1 + k] / kf;
+            ct[k] = sums1[4 + k] / kf;
+        }
+    }
+    __syncthreads();
+    if (!s_action) return;
+    if (reduce == SSF_REDUCE_STRICT) strict_chains<9, 2>(P, Q, corr, base, n, cs, ct, buf, sums2);
+    else fast_sums<9, 2>(P, Q, corr, base, n, cs, ct, dscratch, sums2);
+    if (threadIdx.x == 0) {
+        float H[9], T_step[16];
+        for (int i = 0; i < 9; ++i) H[i] = sums2[i];
+        kabsch_from_moments_f(cs, ct, H, T_step);  // cpp:137-158
+        mat4_mul_f(T_step, z.T, z.T);              // cpp:228
+        for (int i = 0; i < 16; ++i) z.T_step[i] = T_step[i];
+        z.have_step = 1;
+        z.last_error = z.pend_error;  // cpp:232
+        z.iterations += 1;            // cpp:234
+    }
+}
+
+// =========================================================================================
+// standalone search (parity / benchmark entry)
+// =========================================================================================
+__global__ void __launch_bounds__(kTile)
+    nn_only_kernel(MapView map, const float4 *__restrict__ q, uint32_t n, float limit, int32_t *__restrict__ idx,
+                   float *__restrict__ d2)
+{
+    const uint32_t i = blockIdx.x * kTile + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = q[i];
+    const NNHit h = nn_query(map, p.x, p.y, p.z, limit);
+    idx[i] = h.idx;
+    d2[i] = h.idx >= 0 ? h.d2 : FLT_MAX;
+}
+
+int nn_search_device(const MapView &map, const float4 *queries, size_t n, float limit, int32_t *idx, float *d2,
+                     cudaStream_t st)
+{
+    if (n == 0) return SSF_OK;
+    nn_only_kernel<<<(unsigned)((n + kTile - 1) / kTile), kTile, 0, st>>>(map, queries, (uint32_t)n, limit, idx, d2);
+    SSF_LAUNCHED();
+    g_queries.fetch_add(n, std::memory_order_relaxed);
+    return SSF_OK;
+}
+
+// =========================================================================================
+// host: the fixed launch sequence of one batch alignment
+// =========================================================================================
+int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStream_t st)
+{
+    if (b.n_scans == 0) return SSF_OK;
+    const unsigned tiles = (unsigned)b.n_tiles, scans = (unsigned)b.n_scans;
+    const float limit = cfg.max_corr;
+    ScanState *S = b.state.p;
+    if (tiles == 0) {
+        results_kernel<<<(scans + 127) / 128, 128, 0, st>>>(S, b.results.p, scans, cfg.mode, cfg.acc_err);
+        SSF_LAUNCHED();
+        return SSF_OK;
+    }
+    if (cfg.mode == SSF_MODE_GN_P2P || cfg.mode == SSF_MODE_GN_P2PLANE) {
+        if (cfg.mode == SSF_MODE_GN_P2PLANE && !map.nrm) {
+            set_error("SSF_MODE_GN_P2PLANE needs target normals (ssf_icp_set_target normals == NULL)");
+            return SSF_ERR_STATE;
+        }
+        for (int i = 0; i < cfg.num_iterations; ++i) {
+            if (cfg.mode == SSF_MODE_GN_P2PLANE)
+                search_accum_kernel<ACC_GN_P2PLANE><<<tiles, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, S, limit,
+                                                                            b.corr.p, b.partials.p);
+            else
+                search_accum_kernel<ACC_GN_P2P><<<tiles, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, S, limit, b.corr.p,
+                                                                        b.partials.p);
+            SSF_LAUNCHED();
+            g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
+            solve_gn_kernel<<<scans, 32, 0, st>>>(S, b.partials.p, i, cfg.acc_err, cfg.eps);
+            SSF_LAUNCHED();
+        }
+    } else if (cfg.mode == SSF_MODE_O3D_P2P) {
+        for (int i = 0; i <= cfg.num_iterations; ++i) {
+            search_accum_kernel<ACC_KABSCH><<<tiles, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, S, limit, b.corr.p,
+                                                                    b.partials.p);
+            SSF_LAUNCHED();
+            g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
+            solve_o3d_kernel<<<scans, 32, 0, st>>>(S, b.partials.p, i, cfg.num_iterations);
+            SSF_LAUNCHED();
+        }
+    } else if (cfg.mode == SSF_MODE_REFERENCE) {
+        ref_search_kernel<<<tiles, kTile, 0, st>>>(map, b.src.p, b.P.p, b.Q.p, b.corr.p, b.tile_scan.p, S, limit, 1);
+        SSF_LAUNCHED();
+        g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
+        for (int i = 0; i < cfg.num_iterations; ++i) {
+            ref_reduce_kernel<<<scans, kRefThreads, 0, st>>>(S, b.P.p, b.Q.p, b.corr.p, i == 0 ? 0 : 1, i, cfg.reduce,
+                                                             cfg.acc_err, cfg.eps, b.trace_err.p, b.trace_search.p,
+                                                             b.trace_len);
+            SSF_LAUNCHED();
+            ref_search_kernel<<<tiles, kTile, 0, st>>>(map, b.src.p, b.P.p, b.Q.p, b.corr.p, b.tile_scan.p, S, limit, 0);
+            SSF_LAUNCHED();
+            ref_reduce_kernel<<<scans, kRefThreads, 0, st>>>(S, b.P.p, b.Q.p, b.corr.p, 2, i, cfg.reduce, cfg.acc_err,
+                                                             cfg.eps, b.trace_err.p, b.trace_search.p, b.trace_len);
+            SSF_LAUNCHED();
+            if (i + 1 < cfg.num_iterations) {
+                ref_step_kernel<<<tiles, kTile, 0, st>>>(b.P.p, b.corr.p, b.tile_scan.p, S);
+                SSF_LAUNCHED();
+            }
+        }
+    } else {
+        set_error("unknown mode %d", cfg.mode);
+        return SSF_ERR_INVALID;
+    }
+    results_kernel<<<(scans + 127) / 128, 128, 0, st>>>(S, b.results.p, scans, cfg.mode, cfg.acc_err);
+    SSF_LAUNCHED();
+    return SSF_OK;
+}
+
+}  // namespace ssf

@@ -1,0 +1,349 @@
+"""ssf_gpu -- Python host side of libssf_gpu.so (ctypes + numpy only, no PyTorch).
+
+Mirrors the two registration interfaces of viniciusvidal2/slam-sensor-fusion:
+
+* ``ICPPointToPoint`` -- same constructor, setters and ``calculateAlignment`` as the C++
+  class of ``localization/include/localization/icp_point_to_point.h:41-85`` (clouds are
+  (N, 3|4) float32 arrays instead of ``pcl::PointCloud``, transforms are 4x4 arrays);
+* ``registration_icp`` / ``voxel_down_sample`` -- the Open3D calls made by
+  ``localization_python/localization_python/localization_node.py:47,233-237``.
+
+Every call runs on the GPU through the C ABI; nothing here computes a result on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+from .capi import (MODE_GN_P2P, MODE_GN_P2PLANE, MODE_O3D_P2P, MODE_REFERENCE, REDUCE_FAST, REDUCE_STRICT, IcpParams,
+                   IcpResult, SsfError)
+
+__all__ = ["Context", "ICPPointToPoint", "ICPResult", "Batch", "registration_icp", "voxel_down_sample",
+           "RegistrationResult", "ICPConvergenceCriteria", "TransformationEstimationPointToPoint",
+           "TransformationEstimationPointToPlane", "SsfError", "default_context",
+           "MODE_REFERENCE", "MODE_GN_P2P", "MODE_GN_P2PLANE", "MODE_O3D_P2P", "REDUCE_STRICT", "REDUCE_FAST"]
+
+
+def _cloud(a) -> np.ndarray:
+    a = np.asarray(a)
+    if a.ndim != 2 or a.shape[1] not in (3, 4):
+        raise ValueError(f"cloud must be (N, 3) or (N, 4), got {a.shape}")
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _colmajor(T) -> np.ndarray:
+    T = np.asarray(T, dtype=np.float32)
+    if T.shape != (4, 4):
+        raise ValueError("transform must be 4x4")
+    return np.ascontiguousarray(T.T).reshape(16)
+
+
+def _rowmajor(t16) -> np.ndarray:
+    return np.array(t16, dtype=np.float32).reshape(4, 4).T.copy()
+
+
+class Context:
+    """One CUDA device (``ssf_ctx``)."""
+
+    def __init__(self, device: int = 0):
+        self._h = ctypes.c_void_p()
+        capi.check(capi.lib().ssf_ctx_create(device, ctypes.byref(self._h)))
+        self.device = device
+
+    def synchronize(self) -> None:
+        capi.check(capi.lib().ssf_ctx_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(capi.lib().ssf_ctx_stream(self._h) or 0)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            capi.lib().ssf_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx: Context | None = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+@dataclass
+class ICPResult:
+    """``struct ICPResult`` (icp_point_to_point.h:28-39) plus diagnostics."""
+    transformation: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=np.float32))
+    error: float = 1e6
+    iterations: int = 0
+    has_converged: bool = False
+    n_searches: int = 0
+    k_final: int = 0
+    aborted: bool = False
+    fitness: float = 0.0
+    n_source: int = 0
+    device_ms: float = 0.0
+
+    @staticmethod
+    def from_c(r: IcpResult) -> "ICPResult":
+        return ICPResult(_rowmajor(r.transformation), float(r.error), int(r.iterations), bool(r.has_converged),
+                         int(r.n_searches), int(r.k_final), bool(r.aborted), float(r.fitness), int(r.n_source),
+                         float(r.device_ms))
+
+
+class ICPPointToPoint:
+    """Drop-in for the reference class of the same name (icp_point_to_point.h:41-85).
+
+    ``mode`` / ``reduce`` select the solver (see ssf.h); the defaults reproduce the reference.
+    """
+
+    def __init__(self, max_correspondence_dist: float, num_iterations: int, acceptable_mean_error: float,
+                 transformation_epsilon: float, *, mode: int = MODE_REFERENCE, reduce: int = REDUCE_STRICT,
+                 context: Context | None = None):
+        self._ctx = context or default_context()
+        self._p = IcpParams(max_correspondence_dist, num_iterations, acceptable_mean_error, transformation_epsilon,
+                            mode, reduce, 0, 0.0)
+        self._h = ctypes.c_void_p()
+        capi.check(capi.lib().ssf_icp_create(self._ctx._h, ctypes.byref(self._p), ctypes.byref(self._h)))
+        self._n_source = 0
+
+    # -- setters (icp_point_to_point.cpp:14-55) ------------------------------------------------
+    def _push(self) -> None:
+        capi.check(capi.lib().ssf_icp_set_params(self._h, ctypes.byref(self._p)))
+
+    def setMaxCorrespondenceDist(self, v: float) -> None:
+        self._p.max_correspondence_dist = v
+        self._push()
+
+    def setNumIterations(self, v: int) -> None:
+        self._p.num_iterations = v
+        self._push()
+
+    def setTransformationEpsilon(self, v: float) -> None:
+        self._p.transformation_epsilon = v
+        self._push()
+
+    def setAcceptableMeanError(self, v: float) -> None:
+        self._p.acceptable_mean_error = v
+        self._push()
+
+    def setDebugMode(self, v: bool) -> None:
+        self._p.debug = 1 if v else 0
+        self._push()
+
+    def setMode(self, mode: int, reduce: int | None = None) -> None:
+        self._p.mode = mode
+        if reduce is not None:
+            self._p.reduce = reduce
+        self._push()
+
+    def setInitialTransformation(self, T) -> None:
+        t = _colmajor(T)
+        capi.check(capi.lib().ssf_icp_set_initial(self._h, t.ctypes.data))
+
+    def setSourcePointCloud(self, cloud) -> None:
+        c = _cloud(cloud)
+        capi.check(capi.lib().ssf_icp_set_source(self._h, c.ctypes.data, c.shape[0], c.strides[0]))
+        self._n_source = c.shape[0]
+
+    def setTargetPointCloud(self, cloud, normals=None) -> None:
+        c = _cloud(cloud)
+        if normals is not None:
+            n = _cloud(normals)
+            if n.shape[0] != c.shape[0]:
+                raise ValueError("normals and cloud sizes differ")
+            capi.check(capi.lib().ssf_icp_set_target(self._h, c.ctypes.data, c.shape[0], c.strides[0], n.ctypes.data,
+                                                     n.strides[0]))
+        else:
+            capi.check(capi.lib().ssf_icp_set_target(self._h, c.ctypes.data, c.shape[0], c.strides[0], None, 0))
+
+    # -- calculateAlignment (icp_point_to_point.cpp:185-254) ---------------------------------------
+    def calculateAlignment(self) -> ICPResult:
+        r = IcpResult()
+        capi.check(capi.lib().ssf_icp_align(self._h, ctypes.byref(r)))
+        return ICPResult.from_c(r)
+
+    # -- extras ----------------------------------------------------------------------------------
+    def correspondences(self) -> np.ndarray:
+        out = np.empty(self._n_source, np.int32)
+        capi.check(capi.lib().ssf_icp_get_correspondences(self._h, out.ctypes.data, out.shape[0]))
+        return out
+
+    def trace(self):
+        n = max(1, int(self._p.num_iterations))
+        err = np.empty(n, np.float32)
+        srch = np.empty(n, np.int32)
+        capi.check(capi.lib().ssf_icp_get_trace(self._h, err.ctypes.data, srch.ctypes.data, n))
+        return err, srch
+
+    def nearest(self, queries, max_sqdist: float):
+        """k=1 search + ``d2 < max_sqdist`` for already-transformed queries (cpp:64-70)."""
+        q = _cloud(queries)
+        idx = np.empty(q.shape[0], np.int32)
+        d2 = np.empty(q.shape[0], np.float32)
+        capi.check(capi.lib().ssf_nn_search(self._h, q.ctypes.data, q.shape[0], q.strides[0], max_sqdist,
+                                            idx.ctypes.data, d2.ctypes.data))
+        return idx, d2
+
+    def align_batch(self, scans: list, inits) -> list[ICPResult]:
+        """Register a list of scans against the target in one call (offline reprocessing)."""
+        clouds = [_cloud(s) for s in scans]
+        width = clouds[0].shape[1] if clouds else 4
+        if any(c.shape[1] != width for c in clouds):
+            clouds = [np.ascontiguousarray(np.pad(c, ((0, 0), (0, 4 - c.shape[1])))) if c.shape[1] == 3 else c
+                      for c in clouds]
+            width = 4
+        cat = np.ascontiguousarray(np.concatenate(clouds, axis=0)) if clouds else np.zeros((0, 4), np.float32)
+        n_pts = (ctypes.c_size_t * len(clouds))(*[c.shape[0] for c in clouds])
+        T = np.ascontiguousarray(np.stack([_colmajor(t) for t in inits]))
+        res = (IcpResult * len(clouds))()
+        capi.check(capi.lib().ssf_icp_align_batch(self._h, cat.ctypes.data, n_pts, len(clouds), 4 * width,
+                                                  T.ctypes.data, res))
+        return [ICPResult.from_c(r) for r in res]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            capi.lib().ssf_icp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Batch:
+    """Scans resident in HBM, aligned together (``ssf_batch``)."""
+
+    def __init__(self, icp: ICPPointToPoint, max_scans: int, max_total_points: int):
+        self._icp = icp
+        self._h = ctypes.c_void_p()
+        capi.check(capi.lib().ssf_batch_create(icp._h, max_scans, max_total_points, ctypes.byref(self._h)))
+        self.n_scans = 0
+
+    def upload_ptr(self, ptr: int, n_pts, stride_bytes: int = 16) -> None:
+        arr = (ctypes.c_size_t * len(n_pts))(*[int(n) for n in n_pts])
+        capi.check(capi.lib().ssf_batch_upload(self._h, ptr, arr, len(n_pts), stride_bytes))
+        self.n_scans = len(n_pts)
+
+    def upload(self, scans: list) -> None:
+        clouds = [_cloud(s) for s in scans]
+        clouds = [np.ascontiguousarray(np.pad(c, ((0, 0), (0, 1)))) if c.shape[1] == 3 else c for c in clouds]
+        cat = np.ascontiguousarray(np.concatenate(clouds, axis=0))
+        self.upload_ptr(cat.ctypes.data, [c.shape[0] for c in clouds], 16)
+
+    def set_initial_ptr(self, ptr: int) -> None:
+        capi.check(capi.lib().ssf_batch_set_initial(self._h, ptr))
+
+    def set_initial(self, inits) -> None:
+        T = np.ascontiguousarray(np.stack([_colmajor(t) for t in inits]))
+        self.set_initial_ptr(T.ctypes.data)
+
+    def run(self) -> None:
+        capi.check(capi.lib().ssf_batch_run(self._h))
+
+    def results_into(self, res_array) -> None:
+        capi.check(capi.lib().ssf_batch_results(self._h, res_array, self.n_scans))
+
+    def results(self) -> list[ICPResult]:
+        res = (IcpResult * self.n_scans)()
+        self.results_into(res)
+        return [ICPResult.from_c(r) for r in res]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            capi.lib().ssf_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- Open3D-shaped surface (localization_node.py:47,233-237) ------------------------------------
+@dataclass
+class ICPConvergenceCriteria:
+    max_iteration: int = 30
+    relative_fitness: float = 1e-6
+    relative_rmse: float = 1e-6
+
+
+class TransformationEstimationPointToPoint:
+    mode = MODE_O3D_P2P
+
+
+class TransformationEstimationPointToPlane:
+    mode = MODE_GN_P2PLANE
+
+
+@dataclass
+class RegistrationResult:
+    transformation: np.ndarray
+    fitness: float
+    inlier_rmse: float
+    correspondence_set: np.ndarray
+    iterations: int = 0
+    converged: bool = False
+
+
+def registration_icp(source, target, max_correspondence_distance: float, init=None, estimation_method=None,
+                     criteria: ICPConvergenceCriteria | None = None, *, target_normals=None,
+                     context: Context | None = None) -> RegistrationResult:
+    """``o3d.pipelines.registration.registration_icp`` shaped call on the GPU.
+
+    ``source``/``target``: (N, 3) arrays (float64 accepted, cast to float32 at the boundary);
+    ``target`` may also be an ``ICPPointToPoint`` whose target is already resident in HBM.
+    The metric radius is squared here because the C ABI compares squared distances.
+    """
+    criteria = criteria or ICPConvergenceCriteria()
+    estimation_method = estimation_method or TransformationEstimationPointToPoint()
+    mode = estimation_method.mode
+    thr = float(np.float32(max_correspondence_distance) * np.float32(max_correspondence_distance))
+    if isinstance(target, ICPPointToPoint):
+        icp = target
+        icp._p.max_correspondence_dist = thr
+        icp._p.num_iterations = criteria.max_iteration
+        icp._p.mode = mode
+        icp._p.acceptable_mean_error = 0.0
+        icp._p.transformation_epsilon = 1e-6 if mode != MODE_O3D_P2P else 0.0
+        icp._push()
+    else:
+        icp = ICPPointToPoint(thr, criteria.max_iteration, 0.0, 1e-6 if mode != MODE_O3D_P2P else 0.0, mode=mode,
+                              context=context)
+        icp.setTargetPointCloud(target, target_normals)
+    icp.setSourcePointCloud(source)
+    icp.setInitialTransformation(np.eye(4) if init is None else init)
+    r = icp.calculateAlignment()
+    corr = icp.correspondences()
+    rows = np.nonzero(corr >= 0)[0]
+    cs = np.stack([rows, corr[rows]], axis=1).astype(np.int32) if rows.size else np.zeros((0, 2), np.int32)
+    return RegistrationResult(r.transformation.astype(np.float64), r.fitness, r.error, cs, r.iterations,
+                              r.has_converged)
+
+
+def voxel_down_sample(xyz, voxel_size: float, context: Context | None = None):
+    """Voxel-grid downsample with pcl::VoxelGrid semantics (global_map_frames_manager.cpp:143-146;
+    stands in for ``pcd.voxel_down_sample`` at localization_node.py:47).  Returns (M, 3) float32."""
+    ctx = context or default_context()
+    c = _cloud(xyz)
+    out = np.empty((max(1, c.shape[0]), 4), np.float32)
+    n_out = ctypes.c_size_t(0)
+    refused = ctypes.c_int(0)
+    capi.check(capi.lib().ssf_voxel_downsample(ctx._h, c.ctypes.data, c.shape[0], c.strides[0], voxel_size,
+                                               out.ctypes.data, ctypes.byref(n_out), ctypes.byref(refused)))
+    return out[:n_out.value, :3].copy()
