@@ -161,6 +161,13 @@ int ssf_batch_results(ssf_batch *b, ssf_icp_result *out, size_t n_scans);
 int ssf_icp_align_batch(ssf_icp *icp, const float *xyz, const size_t *n_pts, size_t n_scans, size_t stride_bytes,
                         const float *T_colmajor, ssf_icp_result *out);
 
+/* ---- profiling hook ------------------------------------------------------------------- */
+/* When enabled, every launch of the NN-search kernels (K3) on this context is bracketed by a
+ * pair of CUDA events on the context stream.  ssf_ctx_search_time waits for the stream, adds
+ * the elapsed times up and clears the list: *ms = total, *launches = how many. */
+int ssf_ctx_time_searches(ssf_ctx *ctx, int enable);
+int ssf_ctx_search_time(ssf_ctx *ctx, double *ms, uint64_t *launches);
+
 /* ---- counters ------------------------------------------------------------------------- */
 /* Kernels launched by this library since process start (all contexts). */
 uint64_t ssf_kernel_launches(void);

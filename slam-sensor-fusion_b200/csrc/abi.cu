@@ -37,6 +37,7 @@ struct ssf_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     Scratch scratch;
     DevBuf<unsigned char> stage;  // raw bytes of caller clouds before packing
+    SearchTimer timer;
 };
 
 struct ssf_batch {
@@ -49,6 +50,7 @@ struct ssf_batch {
     std::vector<uint32_t> n_raw;
     size_t total_points = 0;
     bool uploaded = false, initial_set = false, ran = false;
+    bool uploaded_raw = false;  // scans went to buf.raw (voxel stage in front of the loop)
     float last_ms = 0.f;
 };
 
@@ -158,6 +160,7 @@ extern "C" void ssf_ctx_destroy(ssf_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->timer.pool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -171,6 +174,33 @@ extern "C" int ssf_ctx_synchronize(ssf_ctx *ctx)
 }
 
 extern "C" void *ssf_ctx_stream(ssf_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" int ssf_ctx_time_searches(ssf_ctx *ctx, int enable)
+{
+    SSF_ARG(ctx, "ssf_ctx_time_searches: ctx == NULL");
+    SSF_TRY(use_device(ctx));
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->timer.enabled = enable != 0;
+    ctx->timer.used = 0;
+    return SSF_OK;
+}
+
+extern "C" int ssf_ctx_search_time(ssf_ctx *ctx, double *ms, uint64_t *launches)
+{
+    SSF_ARG(ctx && ms && launches, "ssf_ctx_search_time: NULL argument");
+    SSF_TRY(use_device(ctx));
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < ctx->timer.used; i += 2) {
+        float t = 0.f;
+        SSF_CUDA(cudaEventElapsedTime(&t, ctx->timer.pool[i], ctx->timer.pool[i + 1]));
+        tot += t;
+    }
+    *ms = tot;
+    *launches = ctx->timer.used / 2;
+    ctx->timer.used = 0;
+    return SSF_OK;
+}
 
 // ---- helpers ------------------------------------------------------------------------------------
 static int check_params(const ssf_icp_params *p)
@@ -521,10 +551,16 @@ extern "C" int ssf_batch_upload(ssf_batch *b, const float *xyz, const size_t *n_
         unsigned bx = (max_n + 255) / 256;
         if (bx > 64) bx = 64;
         if (bx == 0) bx = 1;
+        float4 *dst = b->buf.src.p;
+        if (b->icp->prm.source_voxel_leaf > 0.f) {
+            SSF_TRY(b->buf.raw.reserve(b->buf.src.cap));
+            dst = b->buf.raw.p;
+        }
         pack_scans_kernel<<<dim3(bx, (unsigned)n_scans), 256, 0, ctx->stream>>>(ctx->stage.p, stride_bytes, b->meta_dev.p,
-                                                                              b->buf.src.p);
+                                                                              dst);
         SSF_LAUNCHED();
     }
+    b->uploaded_raw = b->icp->prm.source_voxel_leaf > 0.f;
     layout_kernel<<<(unsigned)n_scans, 128, 0, ctx->stream>>>(b->buf.state.p, b->meta_dev.p, (uint32_t)n_scans,
                                                              b->buf.tile_scan.p);
     SSF_LAUNCHED();
@@ -577,11 +613,17 @@ extern "C" int ssf_batch_run(ssf_batch *b)
         SSF_TRY(buf.P.reserve(buf.src.cap));
         SSF_TRY(buf.Q.reserve(buf.src.cap));
     }
+    if ((p.source_voxel_leaf > 0.f) != b->uploaded_raw) {
+        set_error("ssf_batch_run: source_voxel_leaf changed after the scans were uploaded; upload again");
+        return SSF_ERR_STATE;
+    }
     SSF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (p.source_voxel_leaf > 0.f && b->total_points > 0)
+        SSF_TRY(voxel_downsample_batch(buf, b->meta_dev.p, p.source_voxel_leaf, ctx->scratch, ctx->stream));
     SSF_TRY(init_states(buf, b->T_init_dev.p, ctx->stream));
     IcpConfig cfg{p.max_correspondence_dist, p.num_iterations, p.acceptable_mean_error, p.transformation_epsilon,
                   p.mode, p.reduce};
-    SSF_TRY(run_batch(icp->map.view, cfg, buf, ctx->stream));
+    SSF_TRY(run_batch(icp->map.view, cfg, buf, ctx->stream, &ctx->timer));
     SSF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     b->ran = true;
     return SSF_OK;

@@ -159,6 +159,13 @@ __device__ __forceinline__ int cell_coord(float v, float o, float inv_h, int n)
     u = fminf(fmaxf(u, -2.0f), (float)n + 1.0f);
     return (int)floorf(u);
 }
+// order-preserving float <-> int map, so float min/max can use integer atomics
+__device__ __forceinline__ int float_ordered(float f)
+{
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
 #endif
 
 // ---- primitives.cu -----------------------------------------------------------------------

@@ -1,5 +1,7 @@
 // icp.cuh -- device-side state of a batch of scans and the host entry points of the solver.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 #include "map_index.cuh"
 
@@ -46,6 +48,15 @@ struct BatchBuffers {
     int trace_len = 0;
 };
 
+// optional event bracket around the search kernels (roofline measurement, see ssf.h)
+struct SearchTimer {
+    bool enabled = false;
+    std::vector<cudaEvent_t> pool;   // created on demand, reused
+    size_t used = 0;                 // events handed out since the last collect (pairs)
+    int begin(cudaStream_t st);
+    int end(cudaStream_t st);
+};
+
 struct IcpConfig {
     float max_corr;
     int num_iterations;
@@ -56,7 +67,7 @@ struct IcpConfig {
 };
 
 // Enqueue the whole alignment of every scan in the batch on `st` (no host sync inside).
-int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStream_t st);
+int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStream_t st, SearchTimer *timer);
 // standalone search over n already-transformed queries (device pointers)
 int nn_search_device(const MapView &map, const float4 *queries, size_t n, float limit, int32_t *idx, float *d2,
                      cudaStream_t st);

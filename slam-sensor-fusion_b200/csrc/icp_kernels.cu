@@ -586,7 +586,34 @@ int nn_search_device(const MapView &map, const float4 *queries, size_t n, float 
 // =========================================================================================
 // host: the fixed launch sequence of one batch alignment
 // =========================================================================================
-int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStream_t st)
+int SearchTimer::begin(cudaStream_t st)
+{
+    if (!enabled) return SSF_OK;
+    while (pool.size() < used + 2) {
+        cudaEvent_t e;
+        SSF_CUDA(cudaEventCreate(&e));
+        pool.push_back(e);
+    }
+    SSF_CUDA(cudaEventRecord(pool[used], st));
+    return SSF_OK;
+}
+int SearchTimer::end(cudaStream_t st)
+{
+    if (!enabled) return SSF_OK;
+    SSF_CUDA(cudaEventRecord(pool[used + 1], st));
+    used += 2;
+    return SSF_OK;
+}
+
+#define TIMED_SEARCH(launch)                       \
+    do {                                           \
+        if (timer) SSF_TRY(timer->begin(st));      \
+        launch;                                    \
+        SSF_LAUNCHED();                            \
+        if (timer) SSF_TRY(timer->end(st));        \
+    } while (0)
+
+int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStream_t st, SearchTimer *timer)
 {
     if (b.n_scans == 0) return SSF_OK;
     const unsigned tiles = (unsigned)b.n_tiles, scans = (unsigned)b.n_scans;
@@ -604,28 +631,26 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
         }
         for (int i = 0; i < cfg.num_iterations; ++i) {
             if (cfg.mode == SSF_MODE_GN_P2PLANE)
-                search_accum_kernel<ACC_GN_P2PLANE><<<tiles, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, S, limit,
-                                                                            b.corr.p, b.partials.p);
+                TIMED_SEARCH((search_accum_kernel<ACC_GN_P2PLANE><<<tiles, kTile, 0, st>>>(
+                    map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p)));
             else
-                search_accum_kernel<ACC_GN_P2P><<<tiles, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, S, limit, b.corr.p,
-                                                                        b.partials.p);
-            SSF_LAUNCHED();
+                TIMED_SEARCH((search_accum_kernel<ACC_GN_P2P><<<tiles, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, S,
+                                                                                      limit, b.corr.p, b.partials.p)));
             g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
             solve_gn_kernel<<<scans, 32, 0, st>>>(S, b.partials.p, i, cfg.acc_err, cfg.eps);
             SSF_LAUNCHED();
         }
     } else if (cfg.mode == SSF_MODE_O3D_P2P) {
         for (int i = 0; i <= cfg.num_iterations; ++i) {
-            search_accum_kernel<ACC_KABSCH><<<tiles, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, S, limit, b.corr.p,
-                                                                    b.partials.p);
-            SSF_LAUNCHED();
+            TIMED_SEARCH((search_accum_kernel<ACC_KABSCH><<<tiles, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, S, limit,
+                                                                                  b.corr.p, b.partials.p)));
             g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
             solve_o3d_kernel<<<scans, 32, 0, st>>>(S, b.partials.p, i, cfg.num_iterations);
             SSF_LAUNCHED();
         }
     } else if (cfg.mode == SSF_MODE_REFERENCE) {
-        ref_search_kernel<<<tiles, kTile, 0, st>>>(map, b.src.p, b.P.p, b.Q.p, b.corr.p, b.tile_scan.p, S, limit, 1);
-        SSF_LAUNCHED();
+        TIMED_SEARCH((ref_search_kernel<<<tiles, kTile, 0, st>>>(map, b.src.p, b.P.p, b.Q.p, b.corr.p, b.tile_scan.p, S,
+                                                                limit, 1)));
         g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
         for (int i = 0; i < cfg.num_iterations; ++i) {
             ref_reduce_kernel<<<scans, kRefThreads, 0, st>>>(S, b.P.p, b.Q.p, b.corr.p, i == 0 ? 0 : 1, i, cfg.reduce,

@@ -243,13 +243,6 @@ int radix_sort_pairs_u64(unsigned long long *keys, uint32_t *vals, size_t n, int
 // =========================================================================================
 // Finite bounding box
 // =========================================================================================
-__device__ __forceinline__ int float_ordered(float f)
-{
-    int i = __float_as_int(f);
-    return i >= 0 ? i : i ^ 0x7FFFFFFF;
-}
-__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
-
 __global__ void bbox_init_kernel(int *bbox_ord, uint32_t *n_finite)
 {
     if (threadIdx.x < 3) bbox_ord[threadIdx.x] = float_ordered(FLT_MAX);

@@ -9,6 +9,8 @@
 // PCL's sort is not stable, so its in-voxel order is undefined; the contract here (and in the
 // oracle) is ascending original index, which a STABLE radix sort gives.  Each run is summed
 // by one thread in order, so the float centroid is bit-identical to a sequential CPU loop.
+#include <cfloat>
+#include <climits>
 #include <cmath>
 
 #include "voxel_grid.cuh"
@@ -125,6 +127,203 @@ int voxel_downsample_device(VoxelWork &w, size_t n, float leaf, Scratch &s, cuda
     SSF_CUDA(cudaMemcpyAsync(&cnt, cnt_dev + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     SSF_CUDA(cudaStreamSynchronize(st));
     *n_out = cnt;
+    return SSF_OK;
+}
+
+}  // namespace ssf
+
+// =========================================================================================
+// batched form (scan downsample in front of the ICP loop)
+// =========================================================================================
+namespace ssf {
+
+// vbox per scan: 6 ordered ints (min xyz, max xyz), [6] finite count, [7] pad
+__global__ void vb_init_kernel(int *vbox, uint32_t *n_out, uint32_t *first_run, uint32_t n_scans)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scans) return;
+    for (int k = 0; k < 3; ++k) {
+        vbox[8 * s + k] = float_ordered(FLT_MAX);
+        vbox[8 * s + 3 + k] = float_ordered(-FLT_MAX);
+    }
+    vbox[8 * s + 6] = 0;
+    vbox[8 * s + 7] = 0;
+    n_out[s] = 0;
+    first_run[s] = 0xFFFFFFFFu;
+}
+
+__global__ void __launch_bounds__(kTile)
+    vb_bbox_kernel(const float4 *__restrict__ raw, const uint32_t *__restrict__ tile_scan,
+                   const uint32_t *__restrict__ meta, int *vbox)
+{
+    const uint32_t s = tile_scan[blockIdx.x];
+    const uint32_t n = meta[5 * s + 1], pt_begin = meta[5 * s + 2], tile_begin = meta[5 * s + 3];
+    const uint32_t row = (blockIdx.x - tile_begin) * kTile + threadIdx.x;
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    uint32_t cnt = 0;
+    if (row < n) {
+        const float4 p = raw[(size_t)pt_begin + row];
+        if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+            mn[0] = mx[0] = p.x; mn[1] = mx[1] = p.y; mn[2] = mx[2] = p.z;
+            cnt = 1;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], d));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], d));
+        }
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(&vbox[8 * s + k], float_ordered(mn[k]));
+            atomicMax(&vbox[8 * s + 3 + k], float_ordered(mx[k]));
+        }
+        atomicAdd(reinterpret_cast<uint32_t *>(&vbox[8 * s + 6]), cnt);
+    }
+}
+
+// vgrid per scan: minb[3], divb[3], refused, pad
+__global__ void vb_grid_kernel(const int *__restrict__ vbox, int32_t *__restrict__ vgrid, uint32_t n_scans, float inv)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scans) return;
+    int32_t *g = vgrid + 8 * s;
+    for (int k = 0; k < 8; ++k) g[k] = 0;
+    if (vbox[8 * s + 6] == 0) { g[3] = g[4] = g[5] = 1; return; }
+    long long d64[3];
+    for (int k = 0; k < 3; ++k) {
+        const float mn = ordered_float(vbox[8 * s + k]), mx = ordered_float(vbox[8 * s + 3 + k]);
+        d64[k] = (long long)__fmul_rn(__fsub_rn(mx, mn), inv) + 1;
+        g[k] = (int)floorf(__fmul_rn(mn, inv));
+        g[3 + k] = (int)floorf(__fmul_rn(mx, inv)) - g[k] + 1;
+    }
+    if (d64[0] * d64[1] * d64[2] > (long long)INT32_MAX) g[6] = 1;  // PCL refuses: output = input
+}
+
+__global__ void __launch_bounds__(kTile)
+    vb_keys_kernel(const float4 *__restrict__ raw, const uint32_t *__restrict__ tile_scan,
+                   const uint32_t *__restrict__ meta, const int32_t *__restrict__ vgrid, float inv, uint32_t n_scans,
+                   unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const uint32_t s = tile_scan[blockIdx.x];
+    const uint32_t n = meta[5 * s + 1], pt_begin = meta[5 * s + 2], tile_begin = meta[5 * s + 3];
+    const uint32_t row = (blockIdx.x - tile_begin) * kTile + threadIdx.x;
+    const size_t slot = (size_t)blockIdx.x * kTile + threadIdx.x;  // == pt_begin + row
+    unsigned long long k = (unsigned long long)n_scans << 32;      // dropped / padding: sorts last
+    if (row < n) {
+        const int32_t *g = vgrid + 8 * s;
+        const float4 p = raw[(size_t)pt_begin + row];
+        if (g[6]) {
+            k = ((unsigned long long)s << 32) | row;  // refused: every point is its own voxel
+        } else if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+            const int i0 = (int)__fsub_rn(floorf(__fmul_rn(p.x, inv)), (float)g[0]);
+            const int i1 = (int)__fsub_rn(floorf(__fmul_rn(p.y, inv)), (float)g[1]);
+            const int i2 = (int)__fsub_rn(floorf(__fmul_rn(p.z, inv)), (float)g[2]);
+            k = ((unsigned long long)s << 32) | (uint32_t)(i0 + i1 * g[3] + i2 * g[3] * g[4]);
+        }
+    }
+    keys[slot] = k;
+    vals[slot] = (uint32_t)slot;
+}
+
+__global__ void __launch_bounds__(256)
+    vb_flags_kernel(const unsigned long long *__restrict__ keys, uint32_t n_slots, uint32_t n_scans,
+                    uint32_t *__restrict__ flags)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_slots) return;
+    const unsigned long long k = keys[j];
+    const bool live = (uint32_t)(k >> 32) < n_scans;
+    flags[j] = (live && (j == 0 || keys[j - 1] != k)) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+    vb_runs_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ flags,
+                   const uint32_t *__restrict__ scan, uint32_t n_slots, uint32_t *n_out, uint32_t *first_run)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_slots || !flags[j]) return;
+    const uint32_t s = (uint32_t)(keys[j] >> 32);
+    atomicAdd(&n_out[s], 1u);
+    atomicMin(&first_run[s], scan[j]);
+}
+
+__global__ void __launch_bounds__(128)
+    vb_centroid_kernel(const float4 *__restrict__ raw, const unsigned long long *__restrict__ keys,
+                       const uint32_t *__restrict__ vals, const uint32_t *__restrict__ flags,
+                       const uint32_t *__restrict__ scan, uint32_t n_slots, const uint32_t *__restrict__ meta,
+                       const uint32_t *__restrict__ first_run, float4 *__restrict__ src)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_slots || !flags[j]) return;
+    const unsigned long long k = keys[j];
+    const uint32_t s = (uint32_t)(k >> 32);
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    uint32_t e = j;
+    while (e < n_slots && keys[e] == k) {
+        const float4 p = raw[vals[e]];
+        cx = __fadd_rn(cx, p.x);
+        cy = __fadd_rn(cy, p.y);
+        cz = __fadd_rn(cz, p.z);
+        ++e;
+    }
+    const float cnt = (float)(e - j);
+    const uint32_t out = meta[5 * s + 2] + (scan[j] - first_run[s]);
+    src[out] = make_float4(__fdiv_rn(cx, cnt), __fdiv_rn(cy, cnt), __fdiv_rn(cz, cnt), 1.0f);
+}
+
+__global__ void vb_counts_kernel(ScanState *st, const uint32_t *__restrict__ n_out, uint32_t n_scans)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < n_scans) st[s].n_pts = n_out[s];
+}
+
+int voxel_downsample_batch(BatchBuffers &b, const uint32_t *meta_dev, float leaf, Scratch &s, cudaStream_t st)
+{
+    const uint32_t n_scans = (uint32_t)b.n_scans, n_slots = (uint32_t)b.n_slots, tiles = (uint32_t)b.n_tiles;
+    if (n_scans == 0) return SSF_OK;
+    SSF_TRY(b.vbox.reserve((size_t)8 * n_scans));
+    SSF_TRY(b.vgrid.reserve((size_t)8 * n_scans));
+    SSF_TRY(b.vflags.reserve((size_t)n_slots + 2 * n_scans + 2));
+    SSF_TRY(b.vscan.reserve((size_t)n_slots + 1));
+    SSF_TRY(b.vkeys.reserve((size_t)n_slots + 1));
+    SSF_TRY(b.vvals.reserve((size_t)n_slots + 1));
+    int *vbox = reinterpret_cast<int *>(b.vbox.p);
+    uint32_t *n_out = b.vflags.p + n_slots, *first_run = n_out + n_scans;
+    const float inv = 1.0f / leaf;
+    const unsigned sb = (n_scans + 127) / 128;
+    vb_init_kernel<<<sb, 128, 0, st>>>(vbox, n_out, first_run, n_scans);
+    SSF_LAUNCHED();
+    if (tiles > 0) {
+        vb_bbox_kernel<<<tiles, kTile, 0, st>>>(b.raw.p, b.tile_scan.p, meta_dev, vbox);
+        SSF_LAUNCHED();
+    }
+    vb_grid_kernel<<<sb, 128, 0, st>>>(vbox, b.vgrid.p, n_scans, inv);
+    SSF_LAUNCHED();
+    if (tiles > 0) {
+        vb_keys_kernel<<<tiles, kTile, 0, st>>>(b.raw.p, b.tile_scan.p, meta_dev, b.vgrid.p, inv, n_scans, b.vkeys.p,
+                                                b.vvals.p);
+        SSF_LAUNCHED();
+        int scan_bits = 0;
+        while ((1u << scan_bits) <= n_scans) ++scan_bits;
+        SSF_TRY(radix_sort_pairs_u64(b.vkeys.p, b.vvals.p, n_slots, 32 + scan_bits, s, st));
+        const unsigned fb = (n_slots + 255) / 256;
+        vb_flags_kernel<<<fb, 256, 0, st>>>(b.vkeys.p, n_slots, n_scans, b.vflags.p);
+        SSF_LAUNCHED();
+        SSF_TRY(exclusive_scan_u32(b.vflags.p, b.vscan.p, n_slots, nullptr, s, st));
+        vb_runs_kernel<<<fb, 256, 0, st>>>(b.vkeys.p, b.vflags.p, b.vscan.p, n_slots, n_out, first_run);
+        SSF_LAUNCHED();
+        vb_centroid_kernel<<<(n_slots + 127) / 128, 128, 0, st>>>(b.raw.p, b.vkeys.p, b.vvals.p, b.vflags.p, b.vscan.p,
+                                                                 n_slots, meta_dev, first_run, b.src.p);
+        SSF_LAUNCHED();
+    }
+    vb_counts_kernel<<<sb, 128, 0, st>>>(b.state.p, n_out, n_scans);
+    SSF_LAUNCHED();
     return SSF_OK;
 }
 

@@ -60,6 +60,15 @@ class Context:
     def stream(self) -> int:
         return int(capi.lib().ssf_ctx_stream(self._h) or 0)
 
+    def time_searches(self, enable: bool) -> None:
+        capi.check(capi.lib().ssf_ctx_time_searches(self._h, 1 if enable else 0))
+
+    def search_time(self):
+        """(total ms, launches) of the NN-search kernels since the last call (CUDA events)."""
+        ms, n = ctypes.c_double(0), ctypes.c_uint64(0)
+        capi.check(capi.lib().ssf_ctx_search_time(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, int(n.value)
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             capi.lib().ssf_ctx_destroy(self._h)
@@ -141,6 +150,11 @@ class ICPPointToPoint:
 
     def setDebugMode(self, v: bool) -> None:
         self._p.debug = 1 if v else 0
+        self._push()
+
+    def setSourceVoxelLeaf(self, leaf: float) -> None:
+        """> 0: voxel-grid downsample every source scan on the device before the loop."""
+        self._p.source_voxel_leaf = leaf
         self._push()
 
     def setMode(self, mode: int, reduce: int | None = None) -> None:

@@ -13,7 +13,7 @@ MODE_REFERENCE, MODE_GN_P2P, MODE_GN_P2PLANE, MODE_O3D_P2P = 0, 1, 2, 3
 REDUCE_STRICT, REDUCE_FAST = 0, 1
 
 EXPORTS = [
-    "ssf_last_error", "ssf_version", "ssf_ctx_create", "ssf_ctx_destroy", "ssf_ctx_synchronize", "ssf_ctx_stream",
+    "ssf_last_error", "ssf_version", "ssf_ctx_create", "ssf_ctx_destroy", "ssf_ctx_synchronize", "ssf_ctx_stream", "ssf_ctx_time_searches", "ssf_ctx_search_time",
     "ssf_icp_create", "ssf_icp_destroy", "ssf_icp_set_params", "ssf_icp_get_params", "ssf_icp_set_target",
     "ssf_icp_set_source", "ssf_icp_set_initial", "ssf_icp_align", "ssf_icp_get_correspondences", "ssf_icp_get_trace",
     "ssf_icp_target_size", "ssf_nn_search", "ssf_voxel_downsample", "ssf_batch_create", "ssf_batch_destroy",
@@ -61,6 +61,8 @@ def lib() -> ctypes.CDLL:
     L.ssf_ctx_synchronize.argtypes = [vp]
     L.ssf_ctx_stream.argtypes = [vp]
     L.ssf_ctx_stream.restype = vp
+    L.ssf_ctx_time_searches.argtypes = [vp, i32]
+    L.ssf_ctx_search_time.argtypes = [vp, P(ctypes.c_double), P(ctypes.c_uint64)]
     L.ssf_icp_create.argtypes = [vp, P(IcpParams), P(vp)]
     L.ssf_icp_destroy.argtypes = [vp]
     L.ssf_icp_destroy.restype = None

@@ -222,3 +222,31 @@ def test_batch_matches_single(gpu, ora, small_world):
             r1 = icp.calculateAlignment()
             assert np.array_equal(r1.transformation.view(np.uint32), rb.transformation.view(np.uint32))
             assert (r1.iterations, r1.n_searches, r1.k_final) == (rb.iterations, rb.n_searches, rb.k_final)
+
+
+def test_golden_fixture(gpu):
+    """CUDA path against the committed golden vectors (tests/golden/c1_mini.npz)."""
+    import os
+    from conftest import ROOT
+    g = np.load(os.path.join(ROOT, "tests", "golden", "c1_mini.npz"))
+    icp = gpu.ICPPointToPoint(0.5, 10, 0.05, 1e-5)
+    icp.setTargetPointCloud(g["map"], g["normals"])
+    idx, d2 = icp.nearest(g["queries"], 0.5)
+    inside = g["nn_d2"] < np.float32(0.5)
+    assert np.array_equal(idx[inside], g["nn_idx"][inside])
+    assert np.array_equal(d2[inside].view(np.uint32), g["nn_d2"][inside].view(np.uint32))
+    icp.setSourcePointCloud(g["scan"])
+    icp.setInitialTransformation(g["T0"])
+    r = icp.calculateAlignment()
+    assert np.array_equal(r.transformation.view(np.uint32), g["ref_T"].view(np.uint32))
+    assert (r.iterations, r.n_searches, r.k_final) == (int(g["ref_iterations"]), int(g["ref_n_searches"]),
+                                                       int(g["ref_k_final"]))
+    assert np.array_equal(icp.correspondences(), g["ref_corr"])
+    icp.setMode(gpu.MODE_GN_P2PLANE)
+    icp.setAcceptableMeanError(0.0)
+    icp.setTransformationEpsilon(0.0)
+    r = icp.calculateAlignment()
+    dt, dr = pose_delta(r.transformation, g["gn_p2plane_T"])
+    assert dt < TOL_T and dr < TOL_R and abs(r.iterations - int(g["gn_p2plane_iterations"])) <= 1
+    v = gpu.voxel_down_sample(g["scan"], 0.2)
+    assert np.array_equal(v.view(np.uint32), g["vox_02"][:, :3].copy().view(np.uint32))

@@ -1,0 +1,216 @@
+"""Pins the CPU oracle (oracle/ssf_oracle.c).  The reference has no golden vectors and cannot
+be built here ("parity unpinned", see the oracle header), so the restatement is checked against
+independent implementations: O(N*M) brute force, cv2.flann KDTREE_SINGLE (the FLANN lineage PCL
+wraps), scipy cKDTree, numpy SVD / group-by, analytic ground-truth poses, and the committed
+golden fixture tests/golden/c1_mini.npz."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, pose_delta
+from oracle import oracle
+
+
+# ---- nearest neighbour -------------------------------------------------------------------------
+def _f32_sqdist(a, b):
+    d = (a - b).astype(np.float32)
+    r = d[:, 0] * d[:, 0]
+    r = r + d[:, 1] * d[:, 1]
+    r = r + d[:, 2] * d[:, 2]
+    return r.astype(np.float32)
+
+
+def test_kdtree_equals_brute_force():
+    rng = np.random.default_rng(0)
+    m = rng.uniform(-5, 5, (20000, 3)).astype(np.float32)
+    q = rng.uniform(-6, 6, (3000, 3)).astype(np.float32)
+    i1, d1 = oracle.KdTree(m).nn(q)
+    i2, d2 = oracle.nn_brute(m, q)
+    assert np.array_equal(i1, i2) and np.array_equal(d1.view(np.uint32), d2.view(np.uint32))
+    # distance is the float32, left-to-right, non-FMA sum (flann::L2_Simple)
+    assert np.array_equal(d1.view(np.uint32), _f32_sqdist(q, m[i1]).view(np.uint32))
+
+
+def test_kdtree_ties_lowest_index():
+    g = np.stack(np.meshgrid(*[np.arange(8)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    m = np.concatenate([g, g, g[::-1]])
+    q = np.concatenate([g[:300] + 0.5, g[:300]]).astype(np.float32)
+    i1, d1 = oracle.KdTree(m).nn(q)
+    i2, d2 = oracle.nn_brute(m, q)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    # brute force itself: first minimum in ascending index order
+    d_all = ((q[:, None, :] - m[None, :, :]) ** 2).sum(-1)
+    assert np.array_equal(i2, d_all.argmin(1).astype(np.int32))
+
+
+def test_kdtree_multithread_identical():
+    rng = np.random.default_rng(3)
+    m = rng.normal(size=(50000, 3)).astype(np.float32)
+    q = rng.normal(size=(10000, 3)).astype(np.float32)
+    t = oracle.KdTree(m)
+    i1, d1 = t.nn(q, threads=1)
+    i2, d2 = t.nn(q, threads=4)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+
+
+def test_kdtree_vs_cv2_flann_and_scipy():
+    cv2 = pytest.importorskip("cv2")
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(7)
+    m = rng.uniform(0, 50, (200_000, 3)).astype(np.float32)
+    q = rng.uniform(0, 50, (5000, 3)).astype(np.float32)
+    oi, od = oracle.KdTree(m).nn(q)
+    si = cKDTree(m).query(q)[1].astype(np.int32)
+    assert np.array_equal(oi, si)  # tie-free data: indices agree with an independent exact tree
+    index = cv2.flann_Index(m, dict(algorithm=4, leaf_max_size=15))  # KDTREE_SINGLE, as PCL configures FLANN
+    fi, fd = index.knnSearch(q, 1, params=dict(checks=-1, eps=0.0))
+    assert np.array_equal(oi, fi[:, 0].astype(np.int32))
+    assert np.array_equal(od.view(np.uint32), fd[:, 0].astype(np.float32).view(np.uint32))  # bit-equal d2
+
+
+def test_kdtree_empty_and_single():
+    i, d = oracle.KdTree(np.zeros((0, 3), np.float32)).nn(np.zeros((2, 3), np.float32))
+    assert (i == -1).all()
+    i, d = oracle.KdTree(np.array([[1, 2, 3]], np.float32)).nn(np.array([[1, 2, 4]], np.float32))
+    assert i[0] == 0 and d[0] == 1.0
+
+
+# ---- Kabsch / SVD --------------------------------------------------------------------------------
+def test_svd3_reconstructs_and_matches_numpy():
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        H = rng.normal(size=(3, 3)).astype(np.float32) * rng.choice([1e-3, 1.0, 1e3])
+        U, S, V = oracle.svd3(H)
+        assert np.allclose(U @ np.diag(S) @ V.T, H, rtol=0, atol=5e-6 * np.abs(H).max())
+        assert np.allclose(S, np.linalg.svd(H.astype(np.float64))[1], rtol=2e-6, atol=1e-6 * np.abs(H).max())
+        assert np.allclose(U.T @ U, np.eye(3), atol=1e-5) and np.allclose(V.T @ V, np.eye(3), atol=1e-5)
+        assert S[0] >= S[1] >= S[2] >= 0
+
+
+def test_kabsch_recovers_rigid_motion_and_handles_reflection():
+    rng = np.random.default_rng(2)
+    P = rng.normal(size=(500, 3)).astype(np.float32)
+    ang = 0.3
+    R = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    t = np.array([0.5, -0.2, 0.1])
+    Q = (P @ R.T + t).astype(np.float32)
+    T = oracle.kabsch(P, Q)
+    assert np.allclose(T[:3, :3], R, atol=1e-5) and np.allclose(T[:3, 3], t, atol=1e-5)
+    # numpy reference of the same closed form
+    pc, qc = P - P.mean(0), Q - Q.mean(0)
+    U, _, Vt = np.linalg.svd(pc.T.astype(np.float64) @ qc.astype(np.float64))
+    assert np.allclose(T[:3, :3], (Vt.T @ U.T), atol=1e-5)
+    # planar, mirrored data: det fix keeps a proper rotation (cpp:145-149)
+    Pp = P.copy()
+    Pp[:, 2] = 0
+    Qp = Pp.copy()
+    Qp[:, 0] *= -1
+    Tm = oracle.kabsch(Pp, Qp)
+    assert np.linalg.det(Tm[:3, :3].astype(np.float64)) > 0.99
+
+
+# ---- voxel grid ----------------------------------------------------------------------------------
+def _voxel_numpy(xyz, leaf):
+    xyz = xyz[np.isfinite(xyz).all(1)]
+    inv = np.float32(1.0) / np.float32(leaf)
+    mn, mx = xyz.min(0), xyz.max(0)
+    minb = np.floor(mn * inv).astype(np.int64)
+    maxb = np.floor(mx * inv).astype(np.int64)
+    div = maxb - minb + 1
+    ijk = (np.floor(xyz * inv) - minb.astype(np.float32)).astype(np.int64)
+    idx = ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]
+    order = np.argsort(idx, kind="stable")
+    out = []
+    start = 0
+    sidx = idx[order]
+    while start < len(order):
+        end = start
+        acc = np.zeros(3, np.float32)
+        while end < len(order) and sidx[end] == sidx[start]:
+            acc = (acc + xyz[order[end]]).astype(np.float32)
+            end += 1
+        out.append(acc / np.float32(end - start))
+        start = end
+    return np.array(out, np.float32)
+
+
+def test_voxel_grid_vs_numpy_groupby():
+    rng = np.random.default_rng(4)
+    xyz = rng.uniform(-2, 2, (3000, 3)).astype(np.float32)
+    xyz[10] = np.nan
+    o, refused = oracle.voxel_grid(xyz, 0.25)
+    assert not refused
+    ref = _voxel_numpy(xyz, 0.25)
+    assert np.array_equal(o[:, :3].view(np.uint32), ref.view(np.uint32))
+    assert (o[:, 3] == 1.0).all()
+
+
+def test_voxel_grid_refuses_on_index_overflow():
+    c = np.array([[0, 0, 0], [3000, 3000, 3000]], np.float32)
+    o, refused = oracle.voxel_grid(c, 0.001)
+    assert refused and np.array_equal(o[:, :3], c)
+
+
+# ---- whole loop ----------------------------------------------------------------------------------
+def test_reference_icp_moves_towards_ground_truth(small_world):
+    w = small_world
+    tree = oracle.KdTree(w["map"])
+    res, corr, tr = oracle.icp_reference(tree, w["scan"], w["T0"], trace=True)
+    assert not res.aborted and 1 <= res.iterations <= 10
+    assert pose_delta(res.T, w["T_gt"])[0] < pose_delta(w["T0"], w["T_gt"])[0]
+    # errors recorded for every executed pass, searched passes consistent with n_searches
+    assert np.isfinite(tr.iter_err[:res.iterations]).all()
+    assert 1 + tr.iter_searched.sum() == res.n_searches
+    # source shrinks monotonically (cpp:77-83)
+    cnt = tr.count[:res.n_searches]
+    assert (np.diff(cnt) <= 0).all()
+    # corr: rows alive at the end have an index, the rest are -1
+    assert (corr >= 0).sum() == res.k_final
+
+
+def test_reference_icp_iteration_zero_never_researches(small_world):
+    w = small_world
+    tree = oracle.KdTree(w["map"])
+    res, corr, tr = oracle.icp_reference(tree, w["scan"], w["T0"], trace=True, transformation_epsilon=1e9,
+                                         num_iterations=4)
+    # last_error_ starts at FLT_MAX (cpp:205): |FLT_MAX - e| is not < eps even for huge eps < FLT_MAX
+    assert tr.iter_searched[0] == 0 and tr.iter_searched[1:4].all()
+
+
+def test_reference_icp_abort_and_break(small_world):
+    w = small_world
+    tree = oracle.KdTree(w["map"])
+    far = np.eye(4)
+    far[0, 3] = 1e4
+    res, corr, _ = oracle.icp_reference(tree, w["scan"], far)
+    assert res.aborted and res.iterations == 0 and res.error == pytest.approx(1e6) and not res.has_converged
+    assert np.array_equal(res.T, far.astype(np.float32))
+    # acceptable error already met at pass 0 -> break, zero iterations, converged (cpp:215-219, 252)
+    res, corr, _ = oracle.icp_reference(tree, w["scan"], w["T_gt"], acceptable_mean_error=10.0)
+    assert res.iterations == 0 and res.has_converged and res.error < 10.0
+
+
+def test_gn_point_to_plane_recovers_pose(small_world):
+    w = small_world
+    tree = oracle.KdTree(w["map"])
+    r, corr = oracle.icp_gn(tree, w["scan"], w["T0"], mode="p2plane", normals=w["normals"], num_iterations=15)
+    dt, dr = pose_delta(r.T, w["T_gt"])
+    assert dt < 0.02 and dr < 2e-3
+    r2, _ = oracle.icp_gn(tree, w["scan"], w["T0"], mode="p2p", num_iterations=15)
+    assert pose_delta(r2.T, w["T_gt"])[0] < pose_delta(w["T0"], w["T_gt"])[0]
+
+
+def test_golden_fixture_c1_mini():
+    """Frozen outputs of the oracle at fixed seeds (tests/golden/make_golden.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "c1_mini.npz")
+    g = np.load(path)
+    tree = oracle.KdTree(g["map"])
+    idx, d2 = tree.nn(g["queries"])
+    assert np.array_equal(idx, g["nn_idx"]) and np.array_equal(d2.view(np.uint32), g["nn_d2"].view(np.uint32))
+    res, corr, _ = oracle.icp_reference(tree, g["scan"], g["T0"])
+    assert np.array_equal(res.T.view(np.uint32), g["ref_T"].view(np.uint32))
+    assert res.iterations == int(g["ref_iterations"]) and res.n_searches == int(g["ref_n_searches"])
+    assert np.array_equal(corr, g["ref_corr"])
+    vox, _ = oracle.voxel_grid(g["scan"], 0.2)
+    assert np.array_equal(vox.view(np.uint32), g["vox_02"].view(np.uint32))
