@@ -141,12 +141,12 @@ __host__ __device__ inline unsigned long long cell_key(int cx, int cy, int cz, i
 
 __host__ __device__ inline uint32_t hash_key(unsigned long long k)
 {
-    k ^= k >> 33;
-    k *= 0xff51afd7ed558ccdull;
-    k ^= k >> 33;
-    k *= 0xc4ceb9fe1a85ec53ull;
-    k ^= k >> 33;
-    return (uint32_t)k;
+    uint32_t x = (uint32_t)k ^ ((uint32_t)(k >> 32) * 0x9E3779B1u);
+    x *= 0x85EBCA6Bu;
+    x ^= x >> 15;
+    x *= 0xC2B2AE35u;
+    x ^= x >> 13;
+    return x;
 }
 
 #ifdef __CUDACC__

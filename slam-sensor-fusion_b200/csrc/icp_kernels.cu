@@ -20,6 +20,18 @@
 
 namespace ssf {
 
+#ifdef SSF_NN_STATS
+extern "C" int ssf_debug_nn_stats(unsigned long long *out, int reset)
+{
+    if (cudaMemcpyFromSymbol(out, g_nn_stats, sizeof(g_nn_stats)) != cudaSuccess) return -2;
+    if (reset) {
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_nn_stats, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
+
 // =========================================================================================
 // state init / results
 // =========================================================================================

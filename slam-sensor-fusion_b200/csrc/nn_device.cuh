@@ -3,22 +3,39 @@
 // Replaces kdtree_.nearestKSearch(p, 1, idx, d2) + the `d2 < max_correspondence_dist_` test
 // of reference localization/src/icp_point_to_point.cpp:64-70.
 //
-// Exactness contract (tests/test_nn_parity.py): for every query the result equals an
-// O(M) scan of the whole map that keeps the smallest
+// Exactness contract (tests/test_gpu_parity.py): for every query the result equals an O(M)
+// scan of the whole map that keeps the smallest
 //     d2 = fl(fl(fl(dx*dx) + fl(dy*dy)) + fl(dz*dz))      (flann::L2_Simple, no FMA)
 // with d2 < limit, ties broken by the lowest ORIGINAL map index.
 //
 // Why the cell walk is exact: a candidate q can only win if d2(q) <= best, which implies
 // |p.k - q.k| <= rb on every axis k for rb = sqrtf(best) * (1 + 1e-6).  cell_coord() is
-// monotone, so q's cell lies in [cell(p.k - rb), cell(p.k + rb)] when the interval ends
-// are rounded outwards (__fsub_rd / __fadd_ru).  Every row/cell in that box is visited,
-// and the box is re-derived whenever best shrinks.
+// monotone, so q's cell lies in [cell(p.k - rb), cell(p.k + rb)] when the interval ends are
+// rounded outwards (__fsub_rd / __fadd_ru).  Every cell of that box is visited unless the box
+// has shrunk past it, and the box is re-derived whenever best shrinks.
+//
+// (d2, index) pairs are compared as one 64-bit key: d2 >= 0, so its bit pattern orders like
+// the float, and the index in the low word breaks ties towards the lowest index.
+//
+// Divergence: a lane's work is a sequence of contiguous candidate runs (own cell, its two
+// x-neighbours, then up to eight neighbouring rows).  The walk is a FLAT loop -- each trip
+// either evaluates four candidates of the current run or sets up the next run -- so a warp
+// runs for max-over-lanes of the TOTAL work, not the sum over rows of per-row maxima.
 #pragma once
 #include <cfloat>
 
 #include "common.cuh"
 
 namespace ssf {
+
+#ifdef SSF_NN_STATS
+// debug build only (make stats): [0] eval4 calls, [1] probes, [2] probe slots read, [3] queries,
+// [4] wide-path queries, [5] matched queries, [6] outer loop trips, [7] sum over warps of max trips
+__device__ unsigned long long g_nn_stats[8];  // nn_device.cuh is included by one translation unit only
+#define NN_STAT(i, v) atomicAdd(&g_nn_stats[i], (unsigned long long)(v))
+#else
+#define NN_STAT(i, v) ((void)0)
+#endif
 
 struct NNHit {
     float d2;      // best squared distance (== limit when nothing was found)
@@ -45,13 +62,22 @@ __device__ __forceinline__ CellBox cell_box(const MapView &m, float px, float py
     return b;
 }
 
+__device__ __forceinline__ void shrink_box(CellBox &b, const CellBox &nb)
+{
+    b.x0 = max(b.x0, nb.x0); b.x1 = min(b.x1, nb.x1);
+    b.y0 = max(b.y0, nb.y0); b.y1 = min(b.y1, nb.y1);
+    b.z0 = max(b.z0, nb.z0); b.z1 = min(b.z1, nb.z1);
+}
+
 // probe the table for the entry centred on cell (cx, cy, cz); false when none of
 // cx-1, cx, cx+1 holds a point
 __device__ __forceinline__ bool probe(const MapView &m, int cx, int cy, int cz, uint4 &v)
 {
     const unsigned long long k = cell_key(cx, cy, cz, m.nx);
     uint32_t slot = hash_key(k) & m.hmask;
+    NN_STAT(1, 1);
     while (true) {
+        NN_STAT(2, 1);
         const unsigned long long t = __ldg(&m.hkeys[slot]);
         if (t == k) {
             v = __ldg(&m.hvals[slot]);
@@ -62,34 +88,64 @@ __device__ __forceinline__ bool probe(const MapView &m, int cx, int cy, int cz, 
     }
 }
 
-__device__ __forceinline__ void scan_run(const MapView &m, uint32_t s, uint32_t e, float px, float py, float pz,
-                                         NNHit &h)
+__device__ __forceinline__ unsigned long long cand_key(const float4 &q, float px, float py, float pz)
 {
-    for (uint32_t j = s; j < e; ++j) {
-        const float4 q = __ldg(&m.pts[j]);
-        const float dx = __fsub_rn(px, q.x), dy = __fsub_rn(py, q.y), dz = __fsub_rn(pz, q.z);
-        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-        const int qi = __float_as_int(q.w);
-        if (d2 < h.d2 || (d2 == h.d2 && h.idx >= 0 && qi < h.idx)) {
-            h.d2 = d2;
-            h.idx = qi;
-            h.pos = j;
-        }
-    }
+    const float dx = __fsub_rn(px, q.x), dy = __fsub_rn(py, q.y), dz = __fsub_rn(pz, q.z);
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(q.w);
 }
 
-// visit cells [b.x0, b.x1] of row (cy, cz)
-__device__ __forceinline__ void visit_row(const MapView &m, const CellBox &b, int cy, int cz, float px, float py,
-                                          float pz, NNHit &h)
+// four candidates of run [j, e) per call; indices past the end re-read the last one (harmless)
+__device__ __forceinline__ void eval4(const MapView &m, uint32_t j, uint32_t e, float px, float py, float pz,
+                                      unsigned long long &best, uint32_t &pos)
 {
-    for (int c = b.x0; c <= b.x1; c += 3) {
-        uint4 v;
-        if (!probe(m, c + 1, cy, cz, v)) continue;
-        const int last = b.x1 - c;  // 0, 1 or >= 2 further cells wanted
-        const uint32_t e = last >= 2 ? v.w : (last == 1 ? v.z : v.y);
-        scan_run(m, v.x, e, px, py, pz, h);
-    }
+    NN_STAT(0, 1);
+    const uint32_t last = e - 1;
+    const uint32_t j0 = j, j1 = min(j + 1, last), j2 = min(j + 2, last), j3 = min(j + 3, last);
+    const float4 q0 = __ldg(&m.pts[j0]), q1 = __ldg(&m.pts[j1]), q2 = __ldg(&m.pts[j2]), q3 = __ldg(&m.pts[j3]);
+    const unsigned long long k0 = cand_key(q0, px, py, pz), k1 = cand_key(q1, px, py, pz),
+                             k2 = cand_key(q2, px, py, pz), k3 = cand_key(q3, px, py, pz);
+    if (k0 < best) { best = k0; pos = j0; }
+    if (k1 < best) { best = k1; pos = j1; }
+    if (k2 < best) { best = k2; pos = j2; }
+    if (k3 < best) { best = k3; pos = j3; }
 }
+
+// general walk for boxes wider than 3 cells on some axis (threshold radius > cell edge)
+__device__ __noinline__ void nn_walk_wide(const MapView &m, CellBox b, float px, float py, float pz, float limit,
+                                          unsigned long long &best, uint32_t &pos)
+{
+    uint32_t boxed_bits = __float_as_uint(limit);
+    for (int cz = b.z0; cz <= b.z1; ++cz)
+        for (int cy = b.y0; cy <= b.y1; ++cy) {
+            if ((uint32_t)(best >> 32) < boxed_bits) {
+                boxed_bits = (uint32_t)(best >> 32);
+                shrink_box(b, cell_box(m, px, py, pz, __uint_as_float(boxed_bits)));
+            }
+            if (cz < b.z0 || cz > b.z1 || cy < b.y0 || cy > b.y1) continue;
+            for (int c = b.x0; c <= b.x1; c += 3) {
+                uint4 v;
+                if (!probe(m, c + 1, cy, cz, v)) continue;
+                const int more = b.x1 - c;
+                const uint32_t e = more >= 2 ? v.w : (more == 1 ? v.z : v.y);
+                for (uint32_t j = v.x; j < e; j += 4) eval4(m, j, e, px, py, pz, best, pos);
+            }
+        }
+}
+
+// Visiting order of the neighbourhood after the own cell.  (sx, sy, sz) point to the NEAR side
+// of the own cell on each axis (the side the query is closer to); near neighbours come first so
+// the best distance shrinks before the far side is even probed:
+//   item 0 own row, near x | 1 own row, far x | 2 row (sy,0) | 3 row (0,sz) | 4 row (sy,sz)
+//        5 row (-sy,0) | 6 row (0,-sz) | 7 row (sy,-sz) | 8 row (-sy,sz) | 9 row (-sy,-sz)
+// packed as 2-bit fields: multiplier of sy (resp. sz) + 1, field k = item k + 2
+constexpr uint32_t pack8(int a0, int a1, int a2, int a3, int a4, int a5, int a6, int a7)
+{
+    return (uint32_t)(a0 + 1) | (uint32_t)(a1 + 1) << 2 | (uint32_t)(a2 + 1) << 4 | (uint32_t)(a3 + 1) << 6 |
+           (uint32_t)(a4 + 1) << 8 | (uint32_t)(a5 + 1) << 10 | (uint32_t)(a6 + 1) << 12 | (uint32_t)(a7 + 1) << 14;
+}
+constexpr uint32_t kRowY = pack8(1, 0, 1, -1, 0, 1, -1, -1);
+constexpr uint32_t kRowZ = pack8(0, 1, 1, 0, -1, -1, 1, -1);
 
 // limit: accept only d2 < limit (strict), like the reference's threshold test
 __device__ __forceinline__ NNHit nn_query(const MapView &m, float px, float py, float pz, float limit)
@@ -101,24 +157,109 @@ __device__ __forceinline__ NNHit nn_query(const MapView &m, float px, float py, 
     if (!(limit > 0.f) || !isfinite(px) || !isfinite(py) || !isfinite(pz)) return h;
     CellBox b = cell_box(m, px, py, pz, limit);
     if (b.x0 > b.x1 || b.y0 > b.y1 || b.z0 > b.z1) return h;
-    // the query's own row first: it almost always holds the answer and shrinks the box
-    const int cyc = min(max(cell_coord(py, m.oy, m.inv_h, m.ny), b.y0), b.y1);
-    const int czc = min(max(cell_coord(pz, m.oz, m.inv_h, m.nz), b.z0), b.z1);
-    visit_row(m, b, cyc, czc, px, py, pz, h);
-    float boxed_for = limit;
-    for (int cz = b.z0; cz <= b.z1; ++cz) {
-        for (int cy = b.y0; cy <= b.y1; ++cy) {
-            if (cy == cyc && cz == czc) continue;
-            if (h.d2 < boxed_for) {  // best shrank: shrink the box (never grows)
-                const CellBox nb = cell_box(m, px, py, pz, h.d2);
-                b.x0 = max(b.x0, nb.x0); b.x1 = min(b.x1, nb.x1);
-                b.y0 = max(b.y0, nb.y0); b.y1 = min(b.y1, nb.y1);
-                b.z0 = max(b.z0, nb.z0); b.z1 = min(b.z1, nb.z1);
-                boxed_for = h.d2;
+    const unsigned long long none = (unsigned long long)__float_as_uint(limit) << 32;
+    unsigned long long best = none;
+    uint32_t pos = 0;
+    const int cx = cell_coord(px, m.ox, m.inv_h, m.nx), cy = cell_coord(py, m.oy, m.inv_h, m.ny),
+              cz = cell_coord(pz, m.oz, m.inv_h, m.nz);
+    const bool narrow = b.x0 >= cx - 1 && b.x1 <= cx + 1 && b.y0 >= cy - 1 && b.y1 <= cy + 1 && b.z0 >= cz - 1 &&
+                        b.z1 <= cz + 1;
+    NN_STAT(3, 1);
+    if (!narrow) {
+        NN_STAT(4, 1);
+        nn_walk_wide(m, b, px, py, pz, limit, best, pos);
+    } else {
+        // Every run of this query comes from an entry centred on column cx.  Instead of
+        // re-deriving the box, each of the six neighbour directions gets a threshold t such that
+        // best_d2 < t proves the box no longer reaches that neighbour: the neighbour's cells
+        // start at the float where cell_coord() flips, which differs from o + c*h by a few
+        // roundings; `slack` over-covers that, so a neighbour is only ever skipped when the
+        // monotone box of the header comment excludes it too.
+        const float h = __frcp_rn(m.inv_h);
+        float t_lo[3], t_hi[3];
+        {
+            const float pk[3] = {px, py, pz}, ok[3] = {m.ox, m.oy, m.oz};
+            const int ck[3] = {cx, cy, cz};
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float lo = __fadd_rn(ok[k], __fmul_rn((float)ck[k], h));        // ~ lower face of the own cell
+                const float hi = __fadd_rn(ok[k], __fmul_rn((float)(ck[k] + 1), h));  // ~ upper face
+                const float slack = __fmul_rn(4e-6f, fabsf(pk[k]) + fabsf(ok[k]) + __fmul_rn(fabsf((float)ck[k]) + 2.f, h));
+                const float rl = __fsub_rd(__fsub_rd(pk[k], lo), slack), rh = __fsub_rd(__fsub_rd(hi, pk[k]), slack);
+                // rb = sqrt(best)*(1+1e-6)+1e-18 < r  <=  best < r^2*(1-4e-6) - 1e-30   (r > 0)
+                t_lo[k] = rl > 0.f ? __fsub_rd(__fmul_rd(__fmul_rd(rl, rl), 0.999996f), 1e-30f) : 0.f;
+                t_hi[k] = rh > 0.f ? __fsub_rd(__fmul_rd(__fmul_rd(rh, rh), 0.999996f), 1e-30f) : 0.f;
             }
-            if (cz < b.z0 || cz > b.z1 || cy < b.y0 || cy > b.y1) continue;
-            visit_row(m, b, cy, cz, px, py, pz, h);
         }
+        // rows / columns outside the initial box (grid edge, or radius < cell) are never visited
+        const bool in_xl = b.x0 <= cx - 1, in_xh = b.x1 >= cx + 1, in_x0 = cx >= b.x0 && cx <= b.x1;
+        const float uy = __fmul_rn(__fsub_rn(py, m.oy), m.inv_h), uz = __fmul_rn(__fsub_rn(pz, m.oz), m.inv_h),
+                    ux = __fmul_rn(__fsub_rn(px, m.ox), m.inv_h);
+        const bool near_left = !((ux - floorf(ux)) > 0.5f);
+        const int sy = (uy - floorf(uy)) > 0.5f ? 1 : -1, sz = (uz - floorf(uz)) > 0.5f ? 1 : -1;
+        // 1. own cell: one probe, one run; every lane of the warp does this together
+        uint4 own = make_uint4(0, 0, 0, 0);
+        const bool own_ok = cy >= b.y0 && cy <= b.y1 && cz >= b.z0 && cz <= b.z1 && probe(m, cx, cy, cz, own);
+        if (own_ok && in_x0)
+            for (uint32_t j = own.y; j < own.z; j += 4) eval4(m, j, own.z, px, py, pz, best, pos);
+        // 2. which of the ten neighbour items can still hold a better point?
+        float bd = __uint_as_float((uint32_t)(best >> 32));
+        uint32_t mask = 0;
+        {
+            const bool xl = own_ok && in_xl && !(bd < t_lo[0]), xh = own_ok && in_xh && !(bd < t_hi[0]);
+            mask = ((near_left ? xl : xh) ? 1u : 0u) | ((near_left ? xh : xl) ? 2u : 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int dy = sy * ((int)((kRowY >> (2 * k)) & 3u) - 1), dz = sz * ((int)((kRowZ >> (2 * k)) & 3u) - 1);
+                const int ry = cy + dy, rz = cz + dz;
+                const bool out = ry < b.y0 || ry > b.y1 || rz < b.z0 || rz > b.z1 || (dy < 0 && bd < t_lo[1]) ||
+                                 (dy > 0 && bd < t_hi[1]) || (dz < 0 && bd < t_lo[2]) || (dz > 0 && bd < t_hi[2]);
+                mask |= out ? 0u : (4u << k);
+            }
+        }
+        // 3. flat walk over the remaining items: each trip evaluates four candidates or pops an item
+        uint32_t j = 0, e = 0;
+        while (true) {
+            if (j >= e) {
+                bool got = false;
+                while (mask) {
+                    const int s = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    bd = __uint_as_float((uint32_t)(best >> 32));
+                    const bool xl = in_xl && !(bd < t_lo[0]), xh = in_xh && !(bd < t_hi[0]);
+                    if (s < 2) {
+                        const bool left = (s == 0) == near_left;
+                        if (!(left ? xl : xh)) continue;
+                        j = left ? own.x : own.z;
+                        e = left ? own.y : own.w;
+                    } else {
+                        const int k = s - 2;
+                        const int dy = sy * ((int)((kRowY >> (2 * k)) & 3u) - 1), dz = sz * ((int)((kRowZ >> (2 * k)) & 3u) - 1);
+                        if ((dy < 0 && bd < t_lo[1]) || (dy > 0 && bd < t_hi[1]) || (dz < 0 && bd < t_lo[2]) ||
+                            (dz > 0 && bd < t_hi[2]))
+                            continue;
+                        uint4 v;
+                        if (!probe(m, cx, cy + dy, cz + dz, v)) continue;
+                        j = xl ? v.x : (in_x0 ? v.y : v.z);
+                        e = xh ? v.w : (in_x0 ? v.z : v.y);
+                    }
+                    if (j < e) {
+                        got = true;
+                        break;
+                    }
+                }
+                if (!got) break;
+            }
+            eval4(m, j, e, px, py, pz, best, pos);
+            j += 4;
+            NN_STAT(6, 1);
+        }
+    }
+    if (best < none) {
+        NN_STAT(5, 1);
+        h.d2 = __uint_as_float((uint32_t)(best >> 32));
+        h.idx = (int)(uint32_t)(best & 0xFFFFFFFFull);
+        h.pos = pos;
     }
     return h;
 }
@@ -140,7 +281,7 @@ __device__ __forceinline__ float3 transform_point(const float *T, float x, float
     return r;
 }
 
-// ---- warp / block reduction of up to 32 doubles per thread ------------------------------------
+// ---- warp reduction of 32 doubles per thread ---------------------------------------------------
 // After the call lane l holds the warp-wide sum of v[l] (fixed tree order -> deterministic).
 __device__ __forceinline__ double warp_transpose_reduce32(double (&v)[32])
 {

@@ -177,13 +177,31 @@ __global__ void __launch_bounds__(kTile)
         }
         cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
     }
-    if ((threadIdx.x & 31) == 0 && cnt) {
+    // one atomic set per block (a tile belongs to one scan), not per warp
+    __shared__ float smn[kTile / 32][3], smx[kTile / 32][3];
+    __shared__ uint32_t scnt[kTile / 32];
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            atomicMin(&vbox[8 * s + k], float_ordered(mn[k]));
-            atomicMax(&vbox[8 * s + 3 + k], float_ordered(mx[k]));
+        for (int k = 0; k < 3; ++k) { smn[warp][k] = mn[k]; smx[warp][k] = mx[k]; }
+        scnt[warp] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t c = 0;
+        for (int w = 0; w < kTile / 32; ++w) {
+            c += scnt[w];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], smn[w][k]); mx[k] = fmaxf(mx[k], smx[w][k]); }
         }
-        atomicAdd(reinterpret_cast<uint32_t *>(&vbox[8 * s + 6]), cnt);
+        if (c) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                atomicMin(&vbox[8 * s + k], float_ordered(mn[k]));
+                atomicMax(&vbox[8 * s + 3 + k], float_ordered(mx[k]));
+            }
+            atomicAdd(reinterpret_cast<uint32_t *>(&vbox[8 * s + 6]), c);
+        }
     }
 }
 
@@ -242,15 +260,36 @@ __global__ void __launch_bounds__(256)
     flags[j] = (live && (j == 0 || keys[j - 1] != k)) ? 1u : 0u;
 }
 
+// first_run[s] = id of the first run (voxel) of scan s: written by the one element where the
+// scan id changes in the sorted order -- no contended atomics
 __global__ void __launch_bounds__(256)
     vb_runs_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ flags,
-                   const uint32_t *__restrict__ scan, uint32_t n_slots, uint32_t *n_out, uint32_t *first_run)
+                   const uint32_t *__restrict__ scan, uint32_t n_slots, uint32_t n_scans, uint32_t *first_run,
+                   uint32_t *total_runs)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_slots || !flags[j]) return;
+    if (j >= n_slots) return;
     const uint32_t s = (uint32_t)(keys[j] >> 32);
-    atomicAdd(&n_out[s], 1u);
-    atomicMin(&first_run[s], scan[j]);
+    const uint32_t sp = j ? (uint32_t)(keys[j - 1] >> 32) : 0xFFFFFFFFu;
+    if (s != sp) {
+        if (s < n_scans) first_run[s] = scan[j];
+        else *total_runs = scan[j];  // first dropped / padding element: every live run lies before it
+    }
+    if (j == n_slots - 1 && s < n_scans) *total_runs = scan[j] + flags[j];
+}
+
+// n_out[s] = first_run[next non-empty scan] - first_run[s]
+__global__ void vb_nout_kernel(const uint32_t *__restrict__ first_run, const uint32_t *__restrict__ total_runs,
+                               uint32_t n_scans, uint32_t *__restrict__ n_out)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scans) return;
+    const uint32_t f = first_run[s];
+    if (f == 0xFFFFFFFFu) { n_out[s] = 0; return; }
+    uint32_t nxt = *total_runs;
+    for (uint32_t t = s + 1; t < n_scans; ++t)
+        if (first_run[t] != 0xFFFFFFFFu) { nxt = first_run[t]; break; }
+    n_out[s] = nxt - f;
 }
 
 __global__ void __launch_bounds__(128)
@@ -289,12 +328,12 @@ int voxel_downsample_batch(BatchBuffers &b, const uint32_t *meta_dev, float leaf
     if (n_scans == 0) return SSF_OK;
     SSF_TRY(b.vbox.reserve((size_t)8 * n_scans));
     SSF_TRY(b.vgrid.reserve((size_t)8 * n_scans));
-    SSF_TRY(b.vflags.reserve((size_t)n_slots + 2 * n_scans + 2));
+    SSF_TRY(b.vflags.reserve((size_t)n_slots + 2 * n_scans + 4));
     SSF_TRY(b.vscan.reserve((size_t)n_slots + 1));
     SSF_TRY(b.vkeys.reserve((size_t)n_slots + 1));
     SSF_TRY(b.vvals.reserve((size_t)n_slots + 1));
     int *vbox = reinterpret_cast<int *>(b.vbox.p);
-    uint32_t *n_out = b.vflags.p + n_slots, *first_run = n_out + n_scans;
+    uint32_t *n_out = b.vflags.p + n_slots, *first_run = n_out + n_scans, *total_runs = first_run + n_scans;
     const float inv = 1.0f / leaf;
     const unsigned sb = (n_scans + 127) / 128;
     vb_init_kernel<<<sb, 128, 0, st>>>(vbox, n_out, first_run, n_scans);
@@ -316,7 +355,10 @@ int voxel_downsample_batch(BatchBuffers &b, const uint32_t *meta_dev, float leaf
         vb_flags_kernel<<<fb, 256, 0, st>>>(b.vkeys.p, n_slots, n_scans, b.vflags.p);
         SSF_LAUNCHED();
         SSF_TRY(exclusive_scan_u32(b.vflags.p, b.vscan.p, n_slots, nullptr, s, st));
-        vb_runs_kernel<<<fb, 256, 0, st>>>(b.vkeys.p, b.vflags.p, b.vscan.p, n_slots, n_out, first_run);
+        SSF_CUDA(cudaMemsetAsync(total_runs, 0, sizeof(uint32_t), st));
+        vb_runs_kernel<<<fb, 256, 0, st>>>(b.vkeys.p, b.vflags.p, b.vscan.p, n_slots, n_scans, first_run, total_runs);
+        SSF_LAUNCHED();
+        vb_nout_kernel<<<sb, 128, 0, st>>>(first_run, total_runs, n_scans, n_out);
         SSF_LAUNCHED();
         vb_centroid_kernel<<<(n_slots + 127) / 128, 128, 0, st>>>(b.raw.p, b.vkeys.p, b.vvals.p, b.vflags.p, b.vscan.p,
                                                                  n_slots, meta_dev, first_run, b.src.p);
