@@ -161,6 +161,28 @@ int ssf_batch_results(ssf_batch *b, ssf_icp_result *out, size_t n_scans);
 int ssf_icp_align_batch(ssf_icp *icp, const float *xyz, const size_t *n_pts, size_t n_scans, size_t stride_bytes,
                         const float *T_colmajor, ssf_icp_result *out);
 
+/* ---- map sharding across GPUs (BASELINE.json configs 3 and 5) --------------------------- */
+/* One process per GPU holds one spatial shard of the map.  All ranks agree on a global grid
+ * (origin = global minimum corner, cell_size >= sqrt(max_correspondence_dist) * 1.01) and on a
+ * partition of its cell COLUMNS (x index) into ranges [own_lo, own_hi).  A rank's shard must
+ * contain every map point whose column lies in [own_lo - 1, own_hi + 1) (one-cell halo), so the
+ * exact neighbour of every query it owns is local.  Scans are replicated; a rank searches only
+ * the queries whose column it owns, and the per-scan sums (n_scans x 32 doubles) are all-reduced
+ * once per iteration through the caller's hook before every rank runs the identical solve.
+ * global_index (optional): index of each shard point in the unsharded cloud, used for tie-breaks
+ * and reported correspondences.  GN and O3D modes only. */
+typedef struct {
+    float origin[3];
+    float cell_size;
+    int32_t own_lo, own_hi;
+} ssf_shard_info;
+int ssf_icp_set_target_shard(ssf_icp *icp, const float *xyz, size_t n, size_t stride_bytes, const float *normals,
+                             size_t normals_stride_bytes, const int32_t *global_index, const ssf_shard_info *info);
+/* Sum `count` doubles at DEVICE pointer `buf` across ranks, in place, ordered on `cuda_stream`.
+ * Return 0 on success.  (bench.py passes torch.distributed.all_reduce over NCCL.) */
+typedef int (*ssf_allreduce_fn)(void *user, double *buf, size_t count, void *cuda_stream);
+int ssf_icp_set_allreduce(ssf_icp *icp, ssf_allreduce_fn fn, void *user);
+
 /* ---- profiling hook ------------------------------------------------------------------- */
 /* When enabled, every launch of the NN-search kernels (K3) on this context is bracketed by a
  * pair of CUDA events on the context stream.  ssf_ctx_search_time waits for the stream, adds

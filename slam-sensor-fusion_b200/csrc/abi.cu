@@ -4,6 +4,7 @@
 // set time, like reference localization/src/icp_point_to_point.cpp:44-55), enqueue the
 // kernels of map_build.cu / icp_kernels.cu / voxel_grid.cu on the context stream and copy
 // the small results out.  There is no CPU implementation of any step behind these calls.
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <new>
@@ -63,6 +64,10 @@ struct ssf_icp {
     ssf_batch *single = nullptr;  // the one-scan batch behind set_source / align
     bool has_source = false;
     size_t n_source = 0;
+    bool in_shard_call = false;
+    float shard_cell = 0.f;           // cell edge fixed by ssf_shard_info (all ranks must agree)
+    AllreduceFn allreduce = nullptr;  // map sharding hook
+    void *allreduce_user = nullptr;
     DevBuf<float4> q_dev;  // ssf_nn_search temporaries
     DevBuf<int32_t> q_idx;
     DevBuf<float> q_d2;
@@ -292,6 +297,12 @@ extern "C" int ssf_icp_set_target(ssf_icp *icp, const float *xyz, size_t n, size
     SSF_TRY(use_device(ctx));
     icp->has_target = false;
     MapIndex &m = icp->map;
+    if (!icp->in_shard_call) {
+        m.sharded = false;
+        m.has_global_index = false;
+        m.own_lo = INT32_MIN;
+        m.own_hi = INT32_MAX;
+    }
     m.n_raw = n;
     m.has_normals = normals != nullptr && n > 0;
     SSF_TRY(m.raw.reserve(n ? n : 1));
@@ -301,15 +312,53 @@ extern "C" int ssf_icp_set_target(ssf_icp *icp, const float *xyz, size_t n, size
         SSF_CUDA(cudaStreamSynchronize(ctx->stream));  // stage buffer is reused
         SSF_TRY(upload_cloud(ctx, normals, n, normals_stride_bytes, m.raw_nrm.p));
     }
-    SSF_TRY(build_map_index(m, cell_size_for(icp->prm.max_correspondence_dist), ctx->scratch, ctx->stream));
+    SSF_TRY(build_map_index(m, m.sharded ? icp->shard_cell : cell_size_for(icp->prm.max_correspondence_dist),
+                            ctx->scratch, ctx->stream));
     SSF_CUDA(cudaStreamSynchronize(ctx->stream));
     icp->has_target = true;
+    return SSF_OK;
+}
+
+extern "C" int ssf_icp_set_target_shard(ssf_icp *icp, const float *xyz, size_t n, size_t stride_bytes,
+                                        const float *normals, size_t normals_stride_bytes, const int32_t *global_index,
+                                        const ssf_shard_info *info)
+{
+    SSF_ARG(icp && info, "ssf_icp_set_target_shard: NULL argument");
+    SSF_ARG(info->own_lo <= info->own_hi, "ssf_icp_set_target_shard: own_lo > own_hi");
+    SSF_ARG(info->cell_size > 0.f, "ssf_icp_set_target_shard: cell_size must be > 0");
+    MapIndex &m = icp->map;
+    SSF_TRY(use_device(icp->ctx));
+    m.sharded = true;
+    memcpy(m.shard_origin, info->origin, sizeof(m.shard_origin));
+    m.own_lo = info->own_lo;
+    m.own_hi = info->own_hi;
+    m.has_global_index = global_index != nullptr && n > 0;
+    if (m.has_global_index) {
+        SSF_TRY(m.global_index.reserve(n));
+        SSF_CUDA(cudaMemcpyAsync(m.global_index.p, global_index, n * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                 icp->ctx->stream));
+        SSF_CUDA(cudaStreamSynchronize(icp->ctx->stream));
+    }
+    icp->shard_cell = info->cell_size;
+    icp->in_shard_call = true;
+    int rc = ssf_icp_set_target(icp, xyz, n, stride_bytes, normals, normals_stride_bytes);
+    icp->in_shard_call = false;
+    if (rc != SSF_OK) m.sharded = false;
+    return rc;
+}
+
+extern "C" int ssf_icp_set_allreduce(ssf_icp *icp, ssf_allreduce_fn fn, void *user)
+{
+    SSF_ARG(icp, "ssf_icp_set_allreduce: icp == NULL");
+    icp->allreduce = fn;
+    icp->allreduce_user = user;
     return SSF_OK;
 }
 
 // re-index when the threshold moved far from the one the cells were sized for
 static int maybe_reindex(ssf_icp *icp)
 {
+    if (icp->map.sharded) return SSF_OK;  // the cell edge of a sharded map is part of the global grid
     const float want = cell_size_for(icp->prm.max_correspondence_dist);
     const float have = icp->map.cell_size;
     if (have > 0.f && (want > 1.6f * have || want < 0.6f * have)) {
@@ -489,6 +538,7 @@ extern "C" int ssf_batch_create(ssf_icp *icp, size_t max_scans, size_t max_total
     chk(b->buf.tile_scan.reserve(tiles));
     chk(b->buf.partials.reserve(tiles * kAccum));
     chk(b->buf.state.reserve(max_scans));
+    chk(b->buf.sums.reserve(max_scans * kAccum));
     chk(b->buf.results.reserve(max_scans));
     chk(b->T_init_dev.reserve(max_scans * 16));
     chk(b->meta_dev.reserve(max_scans * 5));
@@ -623,6 +673,10 @@ extern "C" int ssf_batch_run(ssf_batch *b)
     SSF_TRY(init_states(buf, b->T_init_dev.p, ctx->stream));
     IcpConfig cfg{p.max_correspondence_dist, p.num_iterations, p.acceptable_mean_error, p.transformation_epsilon,
                   p.mode, p.reduce};
+    if (icp->map.sharded) {
+        cfg.allreduce = icp->allreduce;
+        cfg.allreduce_user = icp->allreduce_user;
+    }
     SSF_TRY(run_batch(icp->map.view, cfg, buf, ctx->stream, &ctx->timer));
     SSF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     b->ran = true;

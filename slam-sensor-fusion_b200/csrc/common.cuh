@@ -118,6 +118,7 @@ struct MapView {
     uint32_t n_pts;  // finite target points
     float ox, oy, oz, inv_h;
     int nx, ny, nz;  // grid extent in cells; NX = nx + 2
+    int own_lo, own_hi;  // map sharding: this rank owns queries whose cell column cx is in [own_lo, own_hi)
 };
 
 constexpr unsigned long long kEmptyKey = ~0ull;

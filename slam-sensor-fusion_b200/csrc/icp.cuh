@@ -33,6 +33,7 @@ struct BatchBuffers {
     DevBuf<int32_t> corr;      // correspondence (original target index) or -1
     DevBuf<uint32_t> tile_scan;
     DevBuf<double> partials;   // [tile][kAccum]
+    DevBuf<double> sums;       // [scan][kAccum]: per-scan totals (all-reduced across ranks when sharded)
     DevBuf<ScanState> state;
     DevBuf<ssf_icp_result> results;
     DevBuf<float> trace_err;       // [scan][num_iterations]
@@ -57,6 +58,9 @@ struct SearchTimer {
     int end(cudaStream_t st);
 };
 
+// all-reduce hook (map sharding): sum `count` doubles at `buf` across ranks, enqueued on `stream`
+typedef int (*AllreduceFn)(void *user, double *buf, size_t count, void *stream);
+
 struct IcpConfig {
     float max_corr;
     int num_iterations;
@@ -64,6 +68,8 @@ struct IcpConfig {
     float eps;
     int mode;
     int reduce;
+    AllreduceFn allreduce = nullptr;
+    void *allreduce_user = nullptr;
 };
 
 // Enqueue the whole alignment of every scan in the batch on `st` (no host sync inside).

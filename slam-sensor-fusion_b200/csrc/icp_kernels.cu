@@ -12,6 +12,7 @@
 //                                         3x3 SVD + pose update + stop rules
 //   ref_search_kernel / ref_reduce_kernel / ref_step_kernel   the reference's own state
 //                                         machine, STRICT (sequential float chains) or FAST
+#include <climits>
 #include <cmath>
 
 #include "icp.cuh"
@@ -133,7 +134,14 @@ __global__ void __launch_bounds__(kTile)
         const size_t slot = (size_t)z.pt_begin + row;
         const float4 s4 = src[slot];
         const float3 p = transform_point(sT, s4.x, s4.y, s4.z);
-        const NNHit h = nn_query(map, p.x, p.y, p.z, limit);
+        // map sharding: only the rank that owns the query's cell column searches it, so every
+        // correspondence is counted exactly once across ranks (halo >= one cell on each side)
+        const int qcx = cell_coord(p.x, map.ox, map.inv_h, map.nx);
+        const bool mine = qcx >= map.own_lo && qcx < map.own_hi;
+        NNHit h;
+        h.idx = -2;
+        h.pos = 0;
+        if (mine) h = nn_query(map, p.x, p.y, p.z, limit);
         corr[slot] = h.idx;
         if (h.idx >= 0) {
             const float4 q = __ldg(&map.pts[h.pos]);
@@ -198,22 +206,36 @@ __global__ void __launch_bounds__(kTile)
     }
 }
 
-// ordered sum of the partial rows of one scan; one warp per scan, lane = value index
-__device__ __forceinline__ double sum_partials(const ScanState &z, const double *partials)
+// ordered sum of the partial rows of one scan -> sums[scan][kAccum].  8 warps take interleaved
+// rows, then the 8 partial totals are added in warp order: fixed order, deterministic.
+__global__ void __launch_bounds__(256) rowsum_kernel(const ScanState *__restrict__ states,
+                                                     const double *__restrict__ partials, double *__restrict__ sums)
 {
-    const uint32_t n_tiles = (z.n_pts + kTile - 1) / kTile;
+    __shared__ double sw[8][kAccum];
+    const ScanState &z = states[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double s = 0.0;
-    for (uint32_t t = 0; t < n_tiles; ++t) s += partials[(size_t)(z.tile_begin + t) * kAccum + threadIdx.x];
-    return s;
+    if (!z.done) {
+        const uint32_t n_tiles = (z.n_pts + kTile - 1) / kTile;
+        for (uint32_t t = warp; t < n_tiles; t += 8) s += partials[(size_t)(z.tile_begin + t) * kAccum + lane];
+    }
+    sw[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += sw[w][lane];
+        sums[(size_t)blockIdx.x * kAccum + lane] = tot;
+    }
 }
 
-__global__ void __launch_bounds__(32) solve_gn_kernel(ScanState *states, const double *__restrict__ partials, int pass,
+__global__ void __launch_bounds__(32) solve_gn_kernel(ScanState *states, const double *__restrict__ sums, int pass,
                                                       float acc_err, float eps)
 {
     __shared__ double sv[kAccum];
     ScanState &z = states[blockIdx.x];
     if (z.done) return;
-    sv[threadIdx.x] = sum_partials(z, partials);
+    sv[threadIdx.x] = sums[(size_t)blockIdx.x * kAccum + threadIdx.x];
     __syncwarp();
     if (threadIdx.x != 0) return;
     const long long K = (long long)(sv[28] + 0.5);
@@ -247,13 +269,13 @@ __global__ void __launch_bounds__(32) solve_gn_kernel(ScanState *states, const d
     if (mx < (double)eps) { z.converged = 1; z.done = 1; }
 }
 
-__global__ void __launch_bounds__(32) solve_o3d_kernel(ScanState *states, const double *__restrict__ partials,
+__global__ void __launch_bounds__(32) solve_o3d_kernel(ScanState *states, const double *__restrict__ sums,
                                                        int pass, int max_iteration)
 {
     __shared__ double sv[kAccum];
     ScanState &z = states[blockIdx.x];
     if (z.done) return;
-    sv[threadIdx.x] = sum_partials(z, partials);
+    sv[threadIdx.x] = sums[(size_t)blockIdx.x * kAccum + threadIdx.x];
     __syncwarp();
     if (threadIdx.x != 0) return;
     const long long K = (long long)(sv[0] + 0.5);
@@ -617,6 +639,21 @@ int SearchTimer::end(cudaStream_t st)
     return SSF_OK;
 }
 
+// per-scan totals of the partial rows; summed across ranks through the caller's hook when the map
+// is sharded (one small all-reduce per iteration: n_scans x 32 doubles)
+static int reduce_sums(const IcpConfig &cfg, BatchBuffers &b, cudaStream_t st)
+{
+    rowsum_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, b.sums.p);
+    SSF_LAUNCHED();
+    if (cfg.allreduce) {
+        if (cfg.allreduce(cfg.allreduce_user, b.sums.p, b.n_scans * kAccum, (void *)st) != 0) {
+            set_error("all-reduce hook failed");
+            return SSF_ERR_COMM;
+        }
+    }
+    return SSF_OK;
+}
+
 #define TIMED_SEARCH(launch)                       \
     do {                                           \
         if (timer) SSF_TRY(timer->begin(st));      \
@@ -649,7 +686,8 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
                 TIMED_SEARCH((search_accum_kernel<ACC_GN_P2P><<<tiles, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, S,
                                                                                       limit, b.corr.p, b.partials.p)));
             g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
-            solve_gn_kernel<<<scans, 32, 0, st>>>(S, b.partials.p, i, cfg.acc_err, cfg.eps);
+            SSF_TRY(reduce_sums(cfg, b, st));
+            solve_gn_kernel<<<scans, 32, 0, st>>>(S, b.sums.p, i, cfg.acc_err, cfg.eps);
             SSF_LAUNCHED();
         }
     } else if (cfg.mode == SSF_MODE_O3D_P2P) {
@@ -657,10 +695,16 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
             TIMED_SEARCH((search_accum_kernel<ACC_KABSCH><<<tiles, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, S, limit,
                                                                                   b.corr.p, b.partials.p)));
             g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
-            solve_o3d_kernel<<<scans, 32, 0, st>>>(S, b.partials.p, i, cfg.num_iterations);
+            SSF_TRY(reduce_sums(cfg, b, st));
+            solve_o3d_kernel<<<scans, 32, 0, st>>>(S, b.sums.p, i, cfg.num_iterations);
             SSF_LAUNCHED();
         }
     } else if (cfg.mode == SSF_MODE_REFERENCE) {
+        if (map.own_lo != INT32_MIN || map.own_hi != INT32_MAX) {
+            set_error("SSF_MODE_REFERENCE does not run on a sharded map (its ordered float sums do not split "
+                      "across ranks); use a GN or O3D mode");
+            return SSF_ERR_STATE;
+        }
         TIMED_SEARCH((ref_search_kernel<<<tiles, kTile, 0, st>>>(map, b.src.p, b.P.p, b.Q.p, b.corr.p, b.tile_scan.p, S,
                                                                 limit, 1)));
         g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);

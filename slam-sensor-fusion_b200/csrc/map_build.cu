@@ -38,14 +38,14 @@ __global__ void __launch_bounds__(256) map_keys_kernel(const float4 *__restrict_
 
 __global__ void __launch_bounds__(256)
     map_gather_kernel(const float4 *__restrict__ raw, const float4 *__restrict__ raw_nrm,
-                      const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n_finite,
+                      const int32_t *__restrict__ global_index, const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n_finite,
                       float4 *__restrict__ pts, float4 *__restrict__ nrm, uint32_t *__restrict__ flags)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_finite) return;
     const uint32_t src = vals[j];
     float4 p = raw[src];
-    p.w = __int_as_float((int)src);
+    p.w = __int_as_float(global_index ? global_index[src] : (int)src);
     pts[j] = p;
     if (raw_nrm) nrm[j] = raw_nrm[src];
     flags[j] = (j == 0 || keys[j] != keys[j - 1]) ? 1u : 0u;
@@ -178,6 +178,8 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
 
     MapView v{};
     v.n_pts = n_finite;
+    v.own_lo = m.own_lo;
+    v.own_hi = m.own_hi;
     v.inv_h = 1.0f / cell_size;
     if (n_finite == 0) {  // empty map: every search misses
         v.ox = v.oy = v.oz = 0.f;
@@ -192,6 +194,13 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
         return SSF_OK;
     }
     v.ox = hb[0]; v.oy = hb[1]; v.oz = hb[2];
+    if (m.sharded) {  // global grid: every rank uses the same origin so cell columns agree
+        if (m.shard_origin[0] > hb[0] || m.shard_origin[1] > hb[1] || m.shard_origin[2] > hb[2]) {
+            set_error("shard origin must not exceed the shard's own minimum");
+            return SSF_ERR_INVALID;
+        }
+        v.ox = m.shard_origin[0]; v.oy = m.shard_origin[1]; v.oz = m.shard_origin[2];
+    }
     // same float expression as cell_coord() on the device (no FMA possible: sub then mul)
     const float ux = (hb[3] - v.ox) * v.inv_h, uy = (hb[4] - v.oy) * v.inv_h, uz = (hb[5] - v.oz) * v.inv_h;
     if (!(ux < 1.0e6f) || !(uy < 65000.f) || !(uz < 65000.f)) {
@@ -216,7 +225,8 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
     SSF_TRY(m.flags.reserve(n_finite));
     SSF_TRY(m.cell_id.reserve(n_finite));
     const unsigned blocks_f = (n_finite + 255) / 256;
-    map_gather_kernel<<<blocks_f, 256, 0, st>>>(m.raw.p, m.has_normals ? m.raw_nrm.p : nullptr, m.keys.p, m.vals.p,
+    map_gather_kernel<<<blocks_f, 256, 0, st>>>(m.raw.p, m.has_normals ? m.raw_nrm.p : nullptr,
+                                                m.has_global_index ? m.global_index.p : nullptr, m.keys.p, m.vals.p,
                                                 n_finite, m.pts.p, m.has_normals ? m.nrm.p : nullptr, m.flags.p);
     SSF_LAUNCHED();
     SSF_TRY(exclusive_scan_u32(m.flags.p, m.cell_id.p, n_finite, cnt_dev + 1, s, st));

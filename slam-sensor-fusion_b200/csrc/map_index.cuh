@@ -1,5 +1,7 @@
 // map_index.cuh -- owner of the HBM-resident voxel-hash map (see MapView in common.cuh).
 #pragma once
+#include <climits>
+
 #include "common.cuh"
 
 namespace ssf {
@@ -7,6 +9,11 @@ namespace ssf {
 struct MapIndex {
     DevBuf<float4> raw;      // target cloud in ORIGINAL order (w unused); kept for re-indexing
     DevBuf<float4> raw_nrm;  // normals in original order (optional)
+    DevBuf<int32_t> global_index;  // map sharding: global index of every raw point (optional)
+    bool has_global_index = false;
+    bool sharded = false;          // origin / ownership given by the caller (ssf_shard_info)
+    float shard_origin[3] = {0, 0, 0};
+    int own_lo = INT32_MIN, own_hi = INT32_MAX;
     DevBuf<float4> pts;      // sorted by cell key, w = original index
     DevBuf<float4> nrm;      // sorted normals
     DevBuf<unsigned long long> keys;

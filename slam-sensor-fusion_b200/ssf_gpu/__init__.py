@@ -183,6 +183,23 @@ class ICPPointToPoint:
         else:
             capi.check(capi.lib().ssf_icp_set_target(self._h, c.ctypes.data, c.shape[0], c.strides[0], None, 0))
 
+    def setTargetShard(self, shard: dict) -> None:
+        """Map sharding: ``shard`` is the dict returned by ``ssf_gpu.shard.shard_map``."""
+        from .shard import ShardInfo
+        c = _cloud(shard["points"])
+        n = _cloud(shard["normals"]) if shard.get("normals") is not None else None
+        gi = np.ascontiguousarray(shard["global_index"], np.int32)
+        info = ShardInfo((ctypes.c_float * 3)(*[float(v) for v in shard["origin"]]), float(shard["cell"]),
+                         int(shard["own"][0]), int(shard["own"][1]))
+        capi.check(capi.lib().ssf_icp_set_target_shard(
+            self._h, c.ctypes.data, c.shape[0], c.strides[0], n.ctypes.data if n is not None else None,
+            n.strides[0] if n is not None else 0, gi.ctypes.data, ctypes.byref(info)))
+
+    def setAllreduce(self, hook) -> None:
+        """``hook``: a ``shard.ALLREDUCE_FN`` (e.g. ``shard.torch_allreduce_hook``); kept alive here."""
+        self._allreduce_hook = hook
+        capi.check(capi.lib().ssf_icp_set_allreduce(self._h, ctypes.cast(hook, ctypes.c_void_p), None))
+
     # -- calculateAlignment (icp_point_to_point.cpp:185-254) ---------------------------------------
     def calculateAlignment(self) -> ICPResult:
         r = IcpResult()
