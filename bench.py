@@ -40,6 +40,10 @@ WORKLOADS = {
                desc="64-beam scan (~130k pts) voxel 0.2 m + point-to-plane GN ICP (10 it, thr 0.5) vs 5M-point map"),
     "c1": dict(map_points=1_000_000, beams=32, azimuths=1024, leaf=0.0, mode="reference", max_range=100.0,
                desc="32-beam scan (~30k pts) reference point-to-point ICP (10 it, thr 0.5) vs 1M-point map"),
+    "c3": dict(map_points=50_000_000, beams=32, azimuths=1024, leaf=0.0, mode="gn_p2plane", max_range=100.0,
+               sharded=True, scans_per_step=16,
+               desc="32-beam scans (~30k pts) point-to-plane GN ICP (10 it, thr 0.5) vs 50M-point map, "
+                    "map sharded by cell columns across ranks, one 32-double all-reduce per scan per iteration"),
     "mini": dict(map_points=200_000, beams=16, azimuths=512, leaf=0.2, mode="gn_p2plane", max_range=60.0,
                  desc="smoke-size variant of c2"),
 }
@@ -61,6 +65,8 @@ def make_workload(name: str, n_scans: int, rank: int, distinct: int = 16):
     """Map + a batch of raw scans with perturbed initial poses (all seeded)."""
     from ssf_gpu import synth
     w = WORKLOADS[name]
+    if w.get("sharded"):
+        rank = 0  # map-sharded workloads: every rank registers the SAME scans against its map shard
     t0 = time.time()
     xyz, nrm, half = synth.make_map(w["map_points"], normals=True)
     log(f"[bench r{rank}] map {xyz.shape[0]} pts, half extent {half} m, {time.time() - t0:.1f}s")
@@ -68,7 +74,7 @@ def make_workload(name: str, n_scans: int, rank: int, distinct: int = 16):
     distinct = min(distinct, n_scans)
     base, scans, inits, gts = [], [], [], []
     for d in range(distinct):
-        k = 1000 * rank + 40 * d
+        k = 1000 * rank + 40 * d + (int(half / 0.15) - 320 if w.get("sharded") else 0)  # sharded: map centre
         T = synth.street_pose(k, half=half)
         base.append((T, synth.make_scan(T, w["beams"], w["azimuths"], scan_id=k, max_range=w["max_range"])))
     for s in range(n_scans):
@@ -205,7 +211,8 @@ def config_of(args, w):
     return {"workload": f"{args.workload}: {w['desc']}", "scans_per_step": args.scans_per_step,
             "map_points": w["map_points"], "scan_rays": w["beams"] * w["azimuths"], "voxel_leaf": w["leaf"],
             "mode": w["mode"], "max_correspondence_dist": THR, "iterations": ITERS,
-            "parallelism": f"scan-sharded x{args.gpus} (map replicated)",
+            "parallelism": (f"map-sharded x{args.gpus} (scans replicated, per-iteration all-reduce)" if w.get("sharded")
+                            else f"scan-sharded x{args.gpus} (map replicated)"),
             "l2": "per-step inputs (raw scans + map + normals) exceed the 126 MB L2"}
 
 
@@ -219,16 +226,33 @@ def run_gpu(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout; keep stdout for the one JSON line
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     B = args.scans_per_step
     w, xyz, nrm, half, scans, inits, gts = make_workload(args.workload, B, rank)
+    sharded = bool(w.get("sharded")) and world > 1
     ctx = ssf_gpu.Context(local_rank)
     mode = {"gn_p2plane": ssf_gpu.MODE_GN_P2PLANE, "reference": ssf_gpu.MODE_REFERENCE}[w["mode"]]
     acc, eps = (0.05, 1e-5) if mode == ssf_gpu.MODE_REFERENCE else (0.0, 0.0)
     icp = ssf_gpu.ICPPointToPoint(THR, ITERS, acc, eps, mode=mode, reduce=ssf_gpu.REDUCE_STRICT, context=ctx)
     icp.setSourceVoxelLeaf(w["leaf"])
     t0 = time.time()
-    icp.setTargetPointCloud(xyz, nrm)
+    if sharded:
+        from ssf_gpu import shard
+        sh = shard.shard_map(xyz, nrm, rank, world, THR)
+        icp.setTargetShard(sh)
+        icp.setAllreduce(shard.torch_allreduce_hook(local_rank))
+        log(f"[bench r{rank}] shard {sh['points'].shape[0]} of {xyz.shape[0]} pts, columns {sh['own']}")
+    else:
+        icp.setTargetPointCloud(xyz, nrm)
     log(f"[bench r{rank}] map index built in {time.time() - t0:.2f}s")
 
     n_pts = [s.shape[0] for s in scans]
@@ -310,8 +334,9 @@ def run_gpu(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
-    value = world * B * args.steps / (dev_ms_max * 1e-3)
-    e2e_val = world * B * args.steps / (e2e_ms_max * 1e-3)
+    job_scans = B if sharded else world * B  # map-sharded ranks cooperate on the same B scans
+    value = job_scans * args.steps / (dev_ms_max * 1e-3)
+    e2e_val = job_scans * args.steps / (e2e_ms_max * 1e-3)
     # roofline of the dominant kernel (search_accum): algorithmic bytes of ONE launch over the batch
     peak, peak_kind = peaks()
     cell = float(np.sqrt(np.float32(THR)) * np.float32(1.01))
@@ -324,16 +349,22 @@ def run_gpu(args, rank, world, local_rank):
     alg_bytes = 20.0 * q_per_launch + 16.0 * n_pts_fp + 8.0 * n_cells_fp
     avg_search_ms = search_ms / max(1, search_launches)
     achieved = alg_bytes / (avg_search_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("workload") == args.workload and tj.get("scans_per_step") == B:
+            traffic = tj.get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": "search_accum_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                "frac": achieved / peak, "traffic": traffic, "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
                 "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_search_ms,
                 "share_of_step": search_ms / dev_ms, "queries_per_launch": q_per_launch,
                 "bytes_per_query": alg_bytes / max(1.0, q_per_launch)}
     line = {"metric": "icp_scans_per_sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_of(args, w),
-            "nn_queries_per_sec": world * queries_per_step * args.steps / (dev_ms_max * 1e-3),
+            "scaling": "strong" if w.get("sharded") else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_of(args, w),
+            "nn_queries_per_sec": (1 if sharded else world) * queries_per_step * args.steps / (dev_ms_max * 1e-3),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "scans/s", "h2d_bytes_per_step": total * 16 + B * 64,
                     "d2h_bytes_per_step": B * ctypes.sizeof(capi.IcpResult)},
@@ -379,10 +410,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--scans-per-step", type=int, default=64)
+    ap.add_argument("--scans-per-step", type=int, default=0, help="default: 64 (16 for c3)")
     ap.add_argument("--cpu-scans", type=int, default=8, help="scans in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.scans_per_step <= 0:
+        args.scans_per_step = WORKLOADS[args.workload].get("scans_per_step", 64)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
