@@ -213,7 +213,7 @@ def config_of(args, w):
             "mode": w["mode"], "max_correspondence_dist": THR, "iterations": ITERS,
             "parallelism": (f"map-sharded x{args.gpus} (scans replicated, per-iteration all-reduce)" if w.get("sharded")
                             else f"scan-sharded x{args.gpus} (map replicated)"),
-            "l2": "per-step inputs (raw scans + map + normals) exceed the 126 MB L2"}
+            "l2": args.l2_note}
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -284,8 +284,14 @@ def run_gpu(args, rank, world, local_rank):
     searches = [int(r.n_searches) for r in res]
     log(f"[bench r{rank}] check: median |t - t_gt| = {np.median(errs):.4f} m, n_source ~{int(np.median(n_src))}, "
         f"searches {int(np.median(searches))}, iterations {int(np.median([r.iterations for r in res]))}")
-    if not (np.median(errs) < 0.1):
+    errs0 = [pose_delta(T0, T)[0] for T0, T in zip(inits, gts)]
+    bar = 0.1 if w["mode"] != "reference" else float(np.median(errs0))  # the reference's lazy p2p loop converges slowly
+    if not (np.median(errs) < bar):
         raise SystemExit("bench: registration did not converge on the benchmark workload")
+    # single-scan latency through the per-object API (ssf_icp_align), device time by CUDA events
+    icp.setSourcePointCloud(scans[0])
+    icp.setInitialTransformation(inits[0])
+    single_ms = float(np.median([icp.calculateAlignment().device_ms for _ in range(5)]))
 
     # ---- value: inputs resident in HBM ----------------------------------------------------------
     for _ in range(args.warmup):
@@ -295,14 +301,22 @@ def run_gpu(args, rank, world, local_rank):
     sampler.start()
     launches0 = capi.lib().ssf_kernel_launches()
     ctx.time_searches(True)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
+    # inputs of one step: raw scans + map (+ normals).  Smaller than the 126 MB L2 -> flush L2 between
+    # timed steps (write a 256 MB buffer); larger -> the step itself streams them
+    input_bytes = total * 16 + xyz.shape[0] * 16 * (2 if w["mode"] == "gn_p2plane" else 1)
+    flush = input_bytes < 126e6
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}") if flush else None
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in evs:
+        if flush:
+            with torch.cuda.stream(stream):
+                flush_buf.zero_()
+        e0.record(stream)
         batch.run()
-    ev1.record(stream)
+        e1.record(stream)
     ctx.synchronize()
-    ev1.synchronize()
-    dev_ms = ev0.elapsed_time(ev1)
+    evs[-1][1].synchronize()
+    dev_ms = float(sum(e0.elapsed_time(e1) for e0, e1 in evs))
     search_ms, search_launches = ctx.search_time()
     ctx.time_searches(False)
     launches = int(capi.lib().ssf_kernel_launches() - launches0)
@@ -360,6 +374,9 @@ def run_gpu(args, rank, world, local_rank):
                 "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_search_ms,
                 "share_of_step": search_ms / dev_ms, "queries_per_launch": q_per_launch,
                 "bytes_per_query": alg_bytes / max(1.0, q_per_launch)}
+    args.l2_note = (f"per-step inputs {input_bytes / 1e6:.0f} MB " +
+                    ("< 126 MB L2: L2 flushed (256 MB write) between timed steps" if flush
+                     else "exceed the 126 MB L2: no flush needed"))
     line = {"metric": "icp_scans_per_sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong" if w.get("sharded") else "weak", "vs_baseline": None, "dtype": "f32",
@@ -368,7 +385,7 @@ def run_gpu(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "scans/s", "h2d_bytes_per_step": total * 16 + B * 64,
                     "d2h_bytes_per_step": B * ctypes.sizeof(capi.IcpResult)},
-            "gpu_launches": launches, "roofline": roofline}
+            "gpu_launches": launches, "single_scan_ms": single_ms, "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, w, xyz, nrm, scans, inits)
     print(json.dumps(line), flush=True)
@@ -414,6 +431,7 @@ def main():
     ap.add_argument("--cpu-scans", type=int, default=8, help="scans in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.l2_note = "n/a (CPU run)"
     if args.scans_per_step <= 0:
         args.scans_per_step = WORKLOADS[args.workload].get("scans_per_step", 64)
     rank = int(os.environ.get("RANK", "0"))

@@ -143,6 +143,20 @@ int ssf_nn_search(ssf_icp *icp, const float *queries, size_t n, size_t stride_by
 int ssf_voxel_downsample(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, float leaf, float *out,
                          size_t *n_out, int *refused);
 
+/* ---- cloud pre-processing (localization/include/localization/point_cloud_processing.hpp) ---- */
+/* out buffers hold n float4 (16-byte stride, w = 1); *n_out receives the number written. */
+/* applyUniformSubsample (hpp:55-74): points 0, step, 2*step, ...; unchanged when n < step. */
+int ssf_cloud_subsample(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, size_t point_step, float *out,
+                        size_t *n_out);
+/* removeFloor (hpp:76-92): keep points with z > 0, order preserved. */
+int ssf_cloud_remove_floor(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, float *out, size_t *n_out);
+/* cropPointCloudThroughRadius (hpp:31-53): points with squared distance to `center` (the pose's
+ * translation T(0..2,3)) < float(radius*radius), ordered by ascending distance, ties by index --
+ * the order pcl::search::KdTree::radiusSearch returns.  indices_out (optional, n ints) receives
+ * the original index of every output point. */
+int ssf_cloud_crop_radius(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, const float center[3],
+                          double radius, float *out, size_t *n_out, int32_t *indices_out);
+
 /* ---- batches: offline reprocessing of scan sequences (BASELINE.json config 4) --------- */
 /* Every scan of a batch is aligned against the handle's target with the handle's
  * parameters; scans are independent (the per-scan loop of

@@ -211,3 +211,44 @@ def voxel_grid(xyz, leaf: float):
     st = ctypes.c_int32(0)
     n = lib().ssf_oracle_voxel_grid(a.ctypes.data, a.shape[0], a.shape[1], leaf, out.ctypes.data, ctypes.addressof(st))
     return out[:n].copy(), bool(st.value)
+
+
+def _preproc_setup():
+    L = lib()
+    if not getattr(L, "_preproc_ready", False):
+        vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+        L.ssf_oracle_subsample.restype = i64
+        L.ssf_oracle_subsample.argtypes = [vp, i64, i32, i64, vp]
+        L.ssf_oracle_remove_floor.restype = i64
+        L.ssf_oracle_remove_floor.argtypes = [vp, i64, i32, vp]
+        L.ssf_oracle_crop_radius.restype = i64
+        L.ssf_oracle_crop_radius.argtypes = [vp, i64, i32, vp, ctypes.c_double, vp, vp]
+        L._preproc_ready = True
+    return L
+
+
+def subsample(xyz, step: int) -> np.ndarray:
+    """applyUniformSubsample (point_cloud_processing.hpp:55-74)."""
+    a = _f32(xyz, (3, 4))
+    out = np.empty((max(1, a.shape[0]), 4), np.float32)
+    n = _preproc_setup().ssf_oracle_subsample(a.ctypes.data, a.shape[0], a.shape[1], step, out.ctypes.data)
+    return out[:n, :3].copy()
+
+
+def remove_floor(xyz) -> np.ndarray:
+    """removeFloor (point_cloud_processing.hpp:76-92)."""
+    a = _f32(xyz, (3, 4))
+    out = np.empty((max(1, a.shape[0]), 4), np.float32)
+    n = _preproc_setup().ssf_oracle_remove_floor(a.ctypes.data, a.shape[0], a.shape[1], out.ctypes.data)
+    return out[:n, :3].copy()
+
+
+def crop_radius(T, radius: float, xyz):
+    """cropPointCloudThroughRadius (point_cloud_processing.hpp:31-53); returns (points, indices)."""
+    a = _f32(xyz, (3, 4))
+    c = np.ascontiguousarray(np.asarray(T, np.float32)[:3, 3])
+    out = np.empty((max(1, a.shape[0]), 4), np.float32)
+    idx = np.empty(max(1, a.shape[0]), np.int32)
+    n = _preproc_setup().ssf_oracle_crop_radius(a.ctypes.data, a.shape[0], a.shape[1], c.ctypes.data, float(radius),
+                                                out.ctypes.data, idx.ctypes.data)
+    return out[:n, :3].copy(), idx[:n].copy()

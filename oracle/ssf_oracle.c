@@ -977,3 +977,67 @@ int64_t ssf_oracle_voxel_grid(const float *in, int64_t n, int stride, float leaf
     free(pairs);
     return n_out;
 }
+
+/* ======================================================================================
+ * 6. Cloud pre-processing, reference localization/include/localization/point_cloud_processing.hpp.
+ *    Outputs are float4 rows (x, y, z, 1); each function returns the number of rows written.
+ * ==================================================================================== */
+
+/* applyUniformSubsample, hpp:55-74: indices 0, step, 2*step, ...; cloud unchanged if size < step */
+int64_t ssf_oracle_subsample(const float *in, int64_t n, int stride, int64_t step, float *out)
+{
+    int64_t m = 0;
+    if (n < step) step = 1; /* hpp:58-61 returns early: every point stays */
+    for (int64_t i = 0; i < n; i += step) {
+        memcpy(out + 4 * m, in + i * stride, 3 * sizeof(float));
+        out[4 * m + 3] = 1.0f;
+        ++m;
+    }
+    return m;
+}
+
+/* removeFloor, hpp:76-92: keep z > 0 */
+int64_t ssf_oracle_remove_floor(const float *in, int64_t n, int stride, float *out)
+{
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (in[i * stride + 2] > 0) {
+            memcpy(out + 4 * m, in + i * stride, 3 * sizeof(float));
+            out[4 * m + 3] = 1.0f;
+            ++m;
+        }
+    return m;
+}
+
+typedef struct { float d2; int32_t idx; } rad_pair_t;
+static int rad_cmp(const void *a, const void *b)
+{
+    const rad_pair_t *x = (const rad_pair_t *)a, *y = (const rad_pair_t *)b;
+    if (x->d2 != y->d2) return x->d2 < y->d2 ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+
+/* cropPointCloudThroughRadius, hpp:31-53: pcl::search::KdTree::radiusSearch(center, radius) then
+ * ExtractIndices.  [ext] FLANN radius search keeps dist < radius^2 (strict), PCL passes
+ * float(radius*radius) and asks for results sorted by distance (FLANN orders ties by index). */
+int64_t ssf_oracle_crop_radius(const float *in, int64_t n, int stride, const float *center, double radius, float *out,
+                               int32_t *idx_out)
+{
+    const float r2 = (float)(radius * radius);
+    rad_pair_t *pairs = (rad_pair_t *)malloc(sizeof(rad_pair_t) * (size_t)(n > 0 ? n : 1));
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float *p = in + i * stride;
+        if (!isfinite(p[0]) || !isfinite(p[1]) || !isfinite(p[2])) continue;
+        float d = sqdist3(center, p);
+        if (d < r2) { pairs[m].d2 = d; pairs[m].idx = (int32_t)i; ++m; }
+    }
+    qsort(pairs, (size_t)m, sizeof(rad_pair_t), rad_cmp);
+    for (int64_t j = 0; j < m; ++j) {
+        memcpy(out + 4 * j, in + (int64_t)pairs[j].idx * stride, 3 * sizeof(float));
+        out[4 * j + 3] = 1.0f;
+        if (idx_out) idx_out[j] = pairs[j].idx;
+    }
+    free(pairs);
+    return m;
+}

@@ -12,6 +12,7 @@
 
 #include "icp.cuh"
 #include "map_index.cuh"
+#include "preprocess.cuh"
 #include "voxel_grid.cuh"
 
 namespace ssf {
@@ -514,6 +515,63 @@ extern "C" int ssf_voxel_downsample(ssf_ctx *ctx, const float *xyz, size_t n, si
     *n_out = cnt;
     if (refused) *refused = ref;
     return SSF_OK;
+}
+
+// ---- cloud pre-processing ---------------------------------------------------------------------------
+static int preproc_io(ssf_ctx *ctx, PreprocWork &w, const float *xyz, size_t n, size_t stride_bytes)
+{
+    SSF_ARG(n < ((size_t)1 << 31), "cloud larger than 2^31 - 1 points");
+    SSF_TRY(use_device(ctx));
+    SSF_TRY(w.in.reserve(n ? n : 1));
+    SSF_TRY(w.out.reserve(n ? n : 1));
+    return upload_cloud(ctx, xyz, n, stride_bytes, w.in.p);
+}
+
+static int preproc_out(ssf_ctx *ctx, PreprocWork &w, uint32_t cnt, float *out, size_t *n_out, int32_t *idx)
+{
+    if (cnt) SSF_CUDA(cudaMemcpyAsync(out, w.out.p, (size_t)cnt * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (cnt && idx) SSF_CUDA(cudaMemcpyAsync(idx, w.idx.p, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_out = cnt;
+    return SSF_OK;
+}
+
+extern "C" int ssf_cloud_subsample(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, size_t point_step,
+                                   float *out, size_t *n_out)
+{
+    SSF_ARG(ctx && n_out && (n == 0 || (xyz && out)), "ssf_cloud_subsample: NULL argument");
+    *n_out = 0;
+    PreprocWork w;
+    SSF_TRY(preproc_io(ctx, w, xyz, n, stride_bytes));
+    uint32_t cnt = 0;
+    SSF_TRY(subsample_device(w, n, point_step, &cnt, ctx->stream));
+    return preproc_out(ctx, w, cnt, out, n_out, nullptr);
+}
+
+extern "C" int ssf_cloud_remove_floor(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, float *out,
+                                      size_t *n_out)
+{
+    SSF_ARG(ctx && n_out && (n == 0 || (xyz && out)), "ssf_cloud_remove_floor: NULL argument");
+    *n_out = 0;
+    PreprocWork w;
+    SSF_TRY(preproc_io(ctx, w, xyz, n, stride_bytes));
+    uint32_t cnt = 0;
+    SSF_TRY(remove_floor_device(w, n, ctx->scratch, &cnt, ctx->stream));
+    return preproc_out(ctx, w, cnt, out, n_out, nullptr);
+}
+
+extern "C" int ssf_cloud_crop_radius(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes,
+                                     const float center[3], double radius, float *out, size_t *n_out,
+                                     int32_t *indices_out)
+{
+    SSF_ARG(ctx && n_out && center && (n == 0 || (xyz && out)), "ssf_cloud_crop_radius: NULL argument");
+    SSF_ARG(radius >= 0.0, "ssf_cloud_crop_radius: radius < 0");
+    *n_out = 0;
+    PreprocWork w;
+    SSF_TRY(preproc_io(ctx, w, xyz, n, stride_bytes));
+    uint32_t cnt = 0;
+    SSF_TRY(crop_radius_device(w, n, center, radius, ctx->scratch, &cnt, ctx->stream));
+    return preproc_out(ctx, w, cnt, out, n_out, indices_out);
 }
 
 // ---- batches ------------------------------------------------------------------------------------

@@ -22,7 +22,7 @@ from .capi import (MODE_GN_P2P, MODE_GN_P2PLANE, MODE_O3D_P2P, MODE_REFERENCE, R
                    IcpResult, SsfError)
 
 __all__ = ["Context", "ICPPointToPoint", "ICPResult", "Batch", "registration_icp", "voxel_down_sample",
-           "RegistrationResult", "ICPConvergenceCriteria", "TransformationEstimationPointToPoint",
+           "RegistrationResult", "applyUniformSubsample", "removeFloor", "cropPointCloudThroughRadius", "ICPConvergenceCriteria", "TransformationEstimationPointToPoint",
            "TransformationEstimationPointToPlane", "SsfError", "default_context",
            "MODE_REFERENCE", "MODE_GN_P2P", "MODE_GN_P2PLANE", "MODE_O3D_P2P", "REDUCE_STRICT", "REDUCE_FAST"]
 
@@ -378,3 +378,41 @@ def voxel_down_sample(xyz, voxel_size: float, context: Context | None = None):
     capi.check(capi.lib().ssf_voxel_downsample(ctx._h, c.ctypes.data, c.shape[0], c.strides[0], voxel_size,
                                                out.ctypes.data, ctypes.byref(n_out), ctypes.byref(refused)))
     return out[:n_out.value, :3].copy()
+
+
+# ---- point_cloud_processing.hpp (reference localization/include/localization/point_cloud_processing.hpp) ----
+def applyUniformSubsample(cloud, point_step: int, context: Context | None = None) -> np.ndarray:
+    """Every ``point_step``-th point; unchanged when the cloud is shorter than the step (hpp:55-74)."""
+    ctx = context or default_context()
+    c = _cloud(cloud)
+    out = np.empty((max(1, c.shape[0]), 4), np.float32)
+    n_out = ctypes.c_size_t(0)
+    capi.check(capi.lib().ssf_cloud_subsample(ctx._h, c.ctypes.data, c.shape[0], c.strides[0], point_step,
+                                              out.ctypes.data, ctypes.byref(n_out)))
+    return out[:n_out.value, :3].copy()
+
+
+def removeFloor(cloud, context: Context | None = None) -> np.ndarray:
+    """Keep points with z > 0, order preserved (hpp:76-92)."""
+    ctx = context or default_context()
+    c = _cloud(cloud)
+    out = np.empty((max(1, c.shape[0]), 4), np.float32)
+    n_out = ctypes.c_size_t(0)
+    capi.check(capi.lib().ssf_cloud_remove_floor(ctx._h, c.ctypes.data, c.shape[0], c.strides[0], out.ctypes.data,
+                                                 ctypes.byref(n_out)))
+    return out[:n_out.value, :3].copy()
+
+
+def cropPointCloudThroughRadius(T, radius: float, cloud, context: Context | None = None, return_indices: bool = False):
+    """Points within ``radius`` of the translation of ``T``, ordered by distance like
+    pcl::search::KdTree::radiusSearch (hpp:31-53)."""
+    ctx = context or default_context()
+    c = _cloud(cloud)
+    center = np.ascontiguousarray(np.asarray(T, np.float32)[:3, 3])
+    out = np.empty((max(1, c.shape[0]), 4), np.float32)
+    idx = np.empty(max(1, c.shape[0]), np.int32)
+    n_out = ctypes.c_size_t(0)
+    capi.check(capi.lib().ssf_cloud_crop_radius(ctx._h, c.ctypes.data, c.shape[0], c.strides[0], center.ctypes.data,
+                                                float(radius), out.ctypes.data, ctypes.byref(n_out), idx.ctypes.data))
+    pts = out[:n_out.value, :3].copy()
+    return (pts, idx[:n_out.value].copy()) if return_indices else pts

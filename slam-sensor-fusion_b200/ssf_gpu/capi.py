@@ -16,7 +16,7 @@ EXPORTS = [
     "ssf_last_error", "ssf_version", "ssf_ctx_create", "ssf_ctx_destroy", "ssf_ctx_synchronize", "ssf_ctx_stream", "ssf_ctx_time_searches", "ssf_ctx_search_time",
     "ssf_icp_create", "ssf_icp_destroy", "ssf_icp_set_params", "ssf_icp_get_params", "ssf_icp_set_target",
     "ssf_icp_set_source", "ssf_icp_set_initial", "ssf_icp_align", "ssf_icp_get_correspondences", "ssf_icp_get_trace",
-    "ssf_icp_target_size", "ssf_icp_set_target_shard", "ssf_icp_set_allreduce", "ssf_nn_search", "ssf_voxel_downsample", "ssf_batch_create", "ssf_batch_destroy",
+    "ssf_icp_target_size", "ssf_icp_set_target_shard", "ssf_icp_set_allreduce", "ssf_nn_search", "ssf_voxel_downsample", "ssf_cloud_subsample", "ssf_cloud_remove_floor", "ssf_cloud_crop_radius", "ssf_batch_create", "ssf_batch_destroy",
     "ssf_batch_upload", "ssf_batch_set_initial", "ssf_batch_run", "ssf_batch_results", "ssf_icp_align_batch",
     "ssf_kernel_launches", "ssf_nn_queries",
 ]
@@ -80,6 +80,9 @@ def lib() -> ctypes.CDLL:
     L.ssf_icp_set_allreduce.argtypes = [vp, vp, vp]
     L.ssf_nn_search.argtypes = [vp, vp, sz, sz, f32, vp, vp]
     L.ssf_voxel_downsample.argtypes = [vp, vp, sz, sz, f32, vp, P(sz), P(i32)]
+    L.ssf_cloud_subsample.argtypes = [vp, vp, sz, sz, sz, vp, P(sz)]
+    L.ssf_cloud_remove_floor.argtypes = [vp, vp, sz, sz, vp, P(sz)]
+    L.ssf_cloud_crop_radius.argtypes = [vp, vp, sz, sz, vp, ctypes.c_double, vp, P(sz), vp]
     L.ssf_batch_create.argtypes = [vp, sz, sz, P(vp)]
     L.ssf_batch_destroy.argtypes = [vp]
     L.ssf_batch_destroy.restype = None
