@@ -157,6 +157,27 @@ int ssf_cloud_remove_floor(ssf_ctx *ctx, const float *xyz, size_t n, size_t stri
 int ssf_cloud_crop_radius(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, const float center[3],
                           double radius, float *out, size_t *n_out, int32_t *indices_out);
 
+/* ---- brute-force pose-grid alignment (localization/src/brute_force_alignment.cpp) ------------- */
+/* setXYZStep / setXYZRange / setRotationStep / setRotationRange / setMeanErrorThreshold
+ * (brute_force_alignment.cpp:12-42; node values at localization_node.cpp:38-43). */
+typedef struct {
+    float x_step, y_step, z_step;
+    float x_range, y_range, z_range;
+    float yaw_step, yaw_range;
+    float mean_error_threshold;
+} ssf_bfa_params;
+/* Number of candidate poses of createTestTransformSequences (brute_force_alignment.cpp:148-180). */
+size_t ssf_bfa_pose_count(const ssf_bfa_params *params);
+/* BruteForceAlignment::alignClouds (brute_force_alignment.cpp:65-136) against the handle's target:
+ * every candidate prev * T(x,y,z,yaw) is scored by the mean squared distance of the n source
+ * points to their nearest target point (unbounded search).  *success = 1 and T_best = the FIRST
+ * candidate in the reference's loop order whose score is below the threshold; otherwise
+ * *success = 0 and T_best = the best-scoring candidate (the reference's next starting pose).
+ * scores_out (optional, ssf_bfa_pose_count floats): every candidate's score, loop order. */
+int ssf_bfa_align(ssf_icp *icp, const float *src_xyz, size_t n, size_t stride_bytes, const float T_prev_colmajor[16],
+                  const ssf_bfa_params *params, float T_best_colmajor[16], float *best_score, int *success,
+                  float *scores_out);
+
 /* ---- batches: offline reprocessing of scan sequences (BASELINE.json config 4) --------- */
 /* Every scan of a batch is aligned against the handle's target with the handle's
  * parameters; scans are independent (the per-scan loop of

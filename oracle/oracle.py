@@ -252,3 +252,49 @@ def crop_radius(T, radius: float, xyz):
     n = _preproc_setup().ssf_oracle_crop_radius(a.ctypes.data, a.shape[0], a.shape[1], c.ctypes.data, float(radius),
                                                 out.ctypes.data, idx.ctypes.data)
     return out[:n, :3].copy(), idx[:n].copy()
+
+
+class BfaParams(ctypes.Structure):
+    """Defaults = localization_node.cpp:38-43."""
+    _fields_ = [("x_step", ctypes.c_float), ("y_step", ctypes.c_float), ("z_step", ctypes.c_float),
+                ("x_range", ctypes.c_float), ("y_range", ctypes.c_float), ("z_range", ctypes.c_float),
+                ("yaw_step", ctypes.c_float), ("yaw_range", ctypes.c_float), ("mean_error_threshold", ctypes.c_float)]
+
+    @staticmethod
+    def node_defaults() -> "BfaParams":
+        pi = np.float32(np.pi)
+        return BfaParams(0.1, 0.1, 0.05, 1.5, 1.5, 0.1, float(pi / np.float32(18.0)), float(pi / np.float32(6.0)), 0.1)
+
+
+def bfa_poses(T_prev, prm: BfaParams) -> np.ndarray:
+    """Candidate transforms prev * T(x, y, z, yaw) in the reference's loop order, (n, 4, 4) row-major."""
+    L = lib()
+    L.ssf_oracle_bfa_poses.restype = ctypes.c_int64
+    L.ssf_oracle_bfa_poses.argtypes = [ctypes.c_void_p, ctypes.POINTER(BfaParams), ctypes.c_void_p]
+    Tc = _colmajor(T_prev)
+    n = L.ssf_oracle_bfa_poses(Tc.ctypes.data, ctypes.byref(prm), None)
+    out = np.empty((n, 16), np.float32)
+    L.ssf_oracle_bfa_poses(Tc.ctypes.data, ctypes.byref(prm), out.ctypes.data)
+    return out.reshape(n, 4, 4).transpose(0, 2, 1).copy()
+
+
+def bfa_align(tree: KdTree, src, T_prev, prm: BfaParams, no_early_exit: bool = False, threads: int = 1):
+    """BruteForceAlignment::alignClouds; returns (success, T_best 4x4, best_score, scores)."""
+    L = lib()
+    L.ssf_oracle_bfa_align.restype = ctypes.c_int
+    L.ssf_oracle_bfa_align.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.POINTER(BfaParams), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    s = _f32(src, (3, 4))
+    n_pose = bfa_poses(T_prev, prm).shape[0]
+    Tc = _colmajor(T_prev)
+    T_out = np.empty(16, np.float32)
+    score = ctypes.c_float(0)
+    ok = ctypes.c_int32(0)
+    scores = np.empty(n_pose, np.float32)
+    rc = L.ssf_oracle_bfa_align(tree._h, s.ctypes.data, s.shape[0], s.shape[1], Tc.ctypes.data, ctypes.byref(prm),
+                                1 if no_early_exit else 0, T_out.ctypes.data, ctypes.addressof(score),
+                                ctypes.addressof(ok), scores.ctypes.data, threads)
+    if rc != 0:
+        raise RuntimeError("oracle bfa_align failed")
+    return bool(ok.value), T_out.reshape(4, 4).T.copy(), float(score.value), scores

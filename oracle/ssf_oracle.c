@@ -1041,3 +1041,94 @@ int64_t ssf_oracle_crop_radius(const float *in, int64_t n, int stride, const flo
     free(pairs);
     return m;
 }
+
+/* ======================================================================================
+ * 7. BruteForceAlignment::alignClouds, reference localization/src/brute_force_alignment.cpp:65-136,
+ *    with the test sequences of createTestTransformSequences (cpp:148-180).
+ *    [ext] Eigen pieces restated: AngleAxisf(yaw, UnitZ).toRotationMatrix() =
+ *    [[c,-s,0],[s,c,0],[0,0,(1-c)+c]] in float; fixed 4x4 products accumulate k = 0..3 in order.
+ * ==================================================================================== */
+typedef struct {
+    float x_step, y_step, z_step;
+    float x_range, y_range, z_range;
+    float yaw_step, yaw_range;
+    float mean_error_threshold;
+} ssf_oracle_bfa_params;
+
+static int bfa_sequence(float range, float step, float *out, int cap)
+{
+    int n = 0;
+    for (int i = 0; (float)i < range / (2 * step) + 1; ++i) { /* cpp:160-179: both signs, i = 0 twice */
+        if (n + 2 > cap) break;
+        out[n++] = -i * step;
+        out[n++] = i * step;
+    }
+    return n;
+}
+
+/* Number of candidate poses and (optionally) their transforms prev * T(x, y, z, yaw) in loop order. */
+int64_t ssf_oracle_bfa_poses(const float *T_prev, const ssf_oracle_bfa_params *p, float *T_out /* n x 16 or NULL */)
+{
+    float xs[4096], ys[4096], zs[4096], ws[4096];
+    int nx = bfa_sequence(p->x_range, p->x_step, xs, 4096), ny = bfa_sequence(p->y_range, p->y_step, ys, 4096);
+    int nz = bfa_sequence(p->z_range, p->z_step, zs, 4096), nw = bfa_sequence(p->yaw_range, p->yaw_step, ws, 4096);
+    int64_t n = 0;
+    for (int a = 0; a < nx; ++a)
+        for (int b = 0; b < ny; ++b)
+            for (int c = 0; c < nz; ++c)
+                for (int d = 0; d < nw; ++d) { /* cpp:80-92 */
+                    if (T_out) {
+                        float T[16];
+                        for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.f : 0.f;
+                        const float cs = cosf(ws[d]), sn = sinf(ws[d]);
+                        M4(T, 0, 0) = cs; M4(T, 0, 1) = -sn; M4(T, 1, 0) = sn; M4(T, 1, 1) = cs;
+                        M4(T, 2, 2) = (1.f - cs) + cs;
+                        M4(T, 0, 3) = xs[a]; M4(T, 1, 3) = ys[b]; M4(T, 2, 3) = zs[c];
+                        mat4_mul_f(T_prev, T, T_out + 16 * n);
+                    }
+                    ++n;
+                }
+    return n;
+}
+
+/* scores_out (optional): mean squared NN distance of every candidate that was evaluated, NaN for
+ * the ones skipped by the early return.  no_early_exit != 0 evaluates all of them (for tests). */
+int ssf_oracle_bfa_align(const void *tree_v, const float *src, int64_t n_src, int stride, const float *T_prev,
+                         const ssf_oracle_bfa_params *p, int no_early_exit, float *T_best_out, float *best_score_out,
+                         int32_t *success_out, float *scores_out, int threads)
+{
+    const kdtree_t *tree = (const kdtree_t *)tree_v;
+    const int64_t n_pose = ssf_oracle_bfa_poses(T_prev, p, NULL);
+    float *Ts = (float *)malloc(sizeof(float) * 16 * (size_t)n_pose);
+    ssf_oracle_bfa_poses(T_prev, p, Ts);
+    float *q = (float *)malloc(sizeof(float) * 3 * (size_t)(n_src > 0 ? n_src : 1));
+    float *d2 = (float *)malloc(sizeof(float) * (size_t)(n_src > 0 ? n_src : 1));
+    int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_src > 0 ? n_src : 1));
+    float best_score = FLT_MAX, best_T[16];
+    for (int i = 0; i < 16; ++i) best_T[i] = (i % 5 == 0) ? 1.f : 0.f; /* cpp:68 */
+    int success = 0, decided = 0;
+    if (scores_out) for (int64_t k = 0; k < n_pose; ++k) scores_out[k] = NAN;
+    for (int64_t k = 0; k < n_pose; ++k) {
+        const float *T = Ts + 16 * k;
+        transform_all(T, src, n_src, stride, q);                           /* cpp:98-99 */
+        ssf_oracle_kdtree_nn(tree, q, n_src, 3, idx, d2, threads);         /* cpp:100-102, unbounded */
+        float score = 0.0f;
+        for (int64_t i = 0; i < n_src; ++i) score += d2[i];                /* cpp:103 */
+        score /= (float)n_src;                                             /* cpp:105 */
+        if (scores_out) scores_out[k] = score;
+        if (decided) continue;
+        if (score < best_score) { best_score = score; memcpy(best_T, T, sizeof(best_T)); } /* cpp:108-112 */
+        if (score < p->mean_error_threshold) {                             /* cpp:114-119 */
+            memcpy(best_T, T, sizeof(best_T));
+            success = 1;
+            decided = 1;
+            if (!no_early_exit) break;
+        }
+    }
+    if (!success && best_score < p->mean_error_threshold) success = 1;     /* cpp:128-134 (unreachable in practice) */
+    memcpy(T_best_out, best_T, sizeof(best_T));
+    *best_score_out = best_score;
+    *success_out = success;
+    free(Ts); free(q); free(d2); free(idx);
+    return 0;
+}

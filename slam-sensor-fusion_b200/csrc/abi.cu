@@ -10,6 +10,7 @@
 #include <new>
 #include <vector>
 
+#include "bfa.cuh"
 #include "icp.cuh"
 #include "map_index.cuh"
 #include "preprocess.cuh"
@@ -572,6 +573,54 @@ extern "C" int ssf_cloud_crop_radius(ssf_ctx *ctx, const float *xyz, size_t n, s
     uint32_t cnt = 0;
     SSF_TRY(crop_radius_device(w, n, center, radius, ctx->scratch, &cnt, ctx->stream));
     return preproc_out(ctx, w, cnt, out, n_out, indices_out);
+}
+
+// ---- brute-force alignment --------------------------------------------------------------------------
+extern "C" size_t ssf_bfa_pose_count(const ssf_bfa_params *params)
+{
+    if (!params) return 0;
+    const float id[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    std::vector<float> poses;
+    if (bfa_poses_host(id, *params, poses) != SSF_OK) return 0;
+    return poses.size() / 16;
+}
+
+extern "C" int ssf_bfa_align(ssf_icp *icp, const float *src_xyz, size_t n, size_t stride_bytes,
+                             const float T_prev_colmajor[16], const ssf_bfa_params *params, float T_best_colmajor[16],
+                             float *best_score, int *success, float *scores_out)
+{
+    SSF_ARG(icp && T_prev_colmajor && params && T_best_colmajor && best_score && success,
+            "ssf_bfa_align: NULL argument");
+    SSF_ARG(n >= 1 && src_xyz, "ssf_bfa_align: empty source cloud");
+    if (!icp->has_target) {
+        set_error("ssf_bfa_align: no target set");
+        return SSF_ERR_STATE;
+    }
+    ssf_ctx *ctx = icp->ctx;
+    SSF_TRY(use_device(ctx));
+    std::vector<float> poses, scores;
+    SSF_TRY(bfa_poses_host(T_prev_colmajor, *params, poses));
+    BfaWork w;
+    SSF_TRY(w.src.reserve(n));
+    SSF_TRY(upload_cloud(ctx, src_xyz, n, stride_bytes, w.src.p));
+    SSF_TRY(bfa_scores_device(icp->map.view, w, n, poses, scores, ctx->stream));
+    // the decisions of cpp:107-134, taken in loop order on the bit-exact scores
+    float best = 3.402823466e+38f;
+    size_t best_k = 0, hit_k = 0;
+    bool hit = false;
+    for (size_t k = 0; k < scores.size(); ++k) {
+        if (scores[k] < best) { best = scores[k]; best_k = k; }
+        if (scores[k] < params->mean_error_threshold) { hit = true; hit_k = k; break; }
+    }
+    if (scores.empty()) {
+        for (int i = 0; i < 16; ++i) T_best_colmajor[i] = (i % 5 == 0) ? 1.f : 0.f;  // cpp:68
+    } else {
+        memcpy(T_best_colmajor, poses.data() + 16 * (hit ? hit_k : best_k), 16 * sizeof(float));
+    }
+    *best_score = best;
+    *success = hit ? 1 : 0;
+    if (scores_out) memcpy(scores_out, scores.data(), scores.size() * sizeof(float));
+    return SSF_OK;
 }
 
 // ---- batches ------------------------------------------------------------------------------------

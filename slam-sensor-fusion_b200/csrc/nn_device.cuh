@@ -31,7 +31,7 @@ namespace ssf {
 #ifdef SSF_NN_STATS
 // debug build only (make stats): [0] eval4 calls, [1] probes, [2] probe slots read, [3] queries,
 // [4] wide-path queries, [5] matched queries, [6] outer loop trips, [7] sum over warps of max trips
-__device__ unsigned long long g_nn_stats[8];  // nn_device.cuh is included by one translation unit only
+static __device__ unsigned long long g_nn_stats[8];  // one copy per translation unit (icp_kernels.cu reports its own)
 #define NN_STAT(i, v) atomicAdd(&g_nn_stats[i], (unsigned long long)(v))
 #else
 #define NN_STAT(i, v) ((void)0)
@@ -112,7 +112,7 @@ __device__ __forceinline__ void eval4(const MapView &m, uint32_t j, uint32_t e, 
 }
 
 // general walk for boxes wider than 3 cells on some axis (threshold radius > cell edge)
-__device__ __noinline__ void nn_walk_wide(const MapView &m, CellBox b, float px, float py, float pz, float limit,
+static __device__ __noinline__ void nn_walk_wide(const MapView &m, CellBox b, float px, float py, float pz, float limit,
                                           unsigned long long &best, uint32_t &pos)
 {
     uint32_t boxed_bits = __float_as_uint(limit);

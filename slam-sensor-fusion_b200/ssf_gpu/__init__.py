@@ -22,7 +22,7 @@ from .capi import (MODE_GN_P2P, MODE_GN_P2PLANE, MODE_O3D_P2P, MODE_REFERENCE, R
                    IcpResult, SsfError)
 
 __all__ = ["Context", "ICPPointToPoint", "ICPResult", "Batch", "registration_icp", "voxel_down_sample",
-           "RegistrationResult", "applyUniformSubsample", "removeFloor", "cropPointCloudThroughRadius", "ICPConvergenceCriteria", "TransformationEstimationPointToPoint",
+           "RegistrationResult", "BruteForceAlignment", "applyUniformSubsample", "removeFloor", "cropPointCloudThroughRadius", "ICPConvergenceCriteria", "TransformationEstimationPointToPoint",
            "TransformationEstimationPointToPlane", "SsfError", "default_context",
            "MODE_REFERENCE", "MODE_GN_P2P", "MODE_GN_P2PLANE", "MODE_O3D_P2P", "REDUCE_STRICT", "REDUCE_FAST"]
 
@@ -416,3 +416,72 @@ def cropPointCloudThroughRadius(T, radius: float, cloud, context: Context | None
                                                 float(radius), out.ctypes.data, ctypes.byref(n_out), idx.ctypes.data))
     pts = out[:n_out.value, :3].copy()
     return (pts, idx[:n_out.value].copy()) if return_indices else pts
+
+
+# ---- BruteForceAlignment (reference localization/include/localization/brute_force_alignment.h) ----
+class BruteForceAlignment:
+    """Same setters / alignClouds / getters as the reference class (brute_force_alignment.cpp), with
+    the pose grid scored on the GPU.  Parameter defaults are unset like in the reference: call the
+    setters (the node's values are at localization_node.cpp:38-43)."""
+
+    def __init__(self, context: Context | None = None):
+        self._p = capi.BfaParams(0.1, 0.1, 0.05, 1.5, 1.5, 0.1, float(np.float32(np.pi) / np.float32(18.0)),
+                                 float(np.float32(np.pi) / np.float32(6.0)), 0.1)
+        self._icp = ICPPointToPoint(1.0, 1, 0.0, 0.0, context=context)  # holds the target's voxel hash
+        self._prev = np.eye(4, dtype=np.float32)
+        self._best = np.eye(4, dtype=np.float32)
+        self._done = False
+        self._src = None
+        self.last_scores = None
+
+    def setXYZStep(self, x, y, z):
+        self._p.x_step, self._p.y_step, self._p.z_step = x, y, z
+
+    def setXYZRange(self, x, y, z):
+        self._p.x_range, self._p.y_range, self._p.z_range = x, y, z
+
+    def setRotationStep(self, yaw):
+        self._p.yaw_step = yaw
+
+    def setRotationRange(self, yaw):
+        self._p.yaw_range = yaw
+
+    def setMeanErrorThreshold(self, v):
+        self._p.mean_error_threshold = v
+
+    def setInitialGuess(self, T):
+        # only the first guess is taken (brute_force_alignment.cpp:44-51: trace() == 4.0f test)
+        if float(np.trace(self._prev)) == 4.0:
+            self._prev = np.asarray(T, np.float32).copy()
+
+    def setSourceCloud(self, cloud):
+        self._src = _cloud(cloud)
+
+    def setTargetCloud(self, cloud):
+        self._icp.setTargetPointCloud(cloud)
+
+    def resetFirstAlignment(self, value: bool):
+        self._done = bool(value)
+
+    def firstAlignmentCompleted(self) -> bool:
+        return self._done
+
+    def getBestTransformation(self) -> np.ndarray:
+        return (self._best if self._done else self._prev).copy()
+
+    def alignClouds(self) -> bool:
+        n_pose = capi.lib().ssf_bfa_pose_count(ctypes.byref(self._p))
+        Tp = _colmajor(self._prev)
+        Tb = np.empty(16, np.float32)
+        score, ok = ctypes.c_float(0), ctypes.c_int(0)
+        scores = np.empty(max(1, n_pose), np.float32)
+        capi.check(capi.lib().ssf_bfa_align(self._icp._h, self._src.ctypes.data, self._src.shape[0],
+                                            self._src.strides[0], Tp.ctypes.data, ctypes.byref(self._p), Tb.ctypes.data,
+                                            ctypes.addressof(score), ctypes.addressof(ok), scores.ctypes.data))
+        self.last_scores, self.best_score = scores[:n_pose], float(score.value)
+        T = Tb.reshape(4, 4).T.copy()
+        if ok.value:  # cpp:114-119
+            self._best, self._done = T, True
+            return True
+        self._prev = T  # cpp:126: the best candidate is the next starting pose
+        return False

@@ -16,7 +16,7 @@ EXPORTS = [
     "ssf_last_error", "ssf_version", "ssf_ctx_create", "ssf_ctx_destroy", "ssf_ctx_synchronize", "ssf_ctx_stream", "ssf_ctx_time_searches", "ssf_ctx_search_time",
     "ssf_icp_create", "ssf_icp_destroy", "ssf_icp_set_params", "ssf_icp_get_params", "ssf_icp_set_target",
     "ssf_icp_set_source", "ssf_icp_set_initial", "ssf_icp_align", "ssf_icp_get_correspondences", "ssf_icp_get_trace",
-    "ssf_icp_target_size", "ssf_icp_set_target_shard", "ssf_icp_set_allreduce", "ssf_nn_search", "ssf_voxel_downsample", "ssf_cloud_subsample", "ssf_cloud_remove_floor", "ssf_cloud_crop_radius", "ssf_batch_create", "ssf_batch_destroy",
+    "ssf_icp_target_size", "ssf_icp_set_target_shard", "ssf_icp_set_allreduce", "ssf_nn_search", "ssf_voxel_downsample", "ssf_cloud_subsample", "ssf_cloud_remove_floor", "ssf_cloud_crop_radius", "ssf_bfa_pose_count", "ssf_bfa_align", "ssf_batch_create", "ssf_batch_destroy",
     "ssf_batch_upload", "ssf_batch_set_initial", "ssf_batch_run", "ssf_batch_results", "ssf_icp_align_batch",
     "ssf_kernel_launches", "ssf_nn_queries",
 ]
@@ -31,6 +31,12 @@ class IcpParams(ctypes.Structure):
                 ("acceptable_mean_error", ctypes.c_float), ("transformation_epsilon", ctypes.c_float),
                 ("mode", ctypes.c_int32), ("reduce", ctypes.c_int32), ("debug", ctypes.c_int32),
                 ("source_voxel_leaf", ctypes.c_float)]
+
+
+class BfaParams(ctypes.Structure):
+    _fields_ = [("x_step", ctypes.c_float), ("y_step", ctypes.c_float), ("z_step", ctypes.c_float),
+                ("x_range", ctypes.c_float), ("y_range", ctypes.c_float), ("z_range", ctypes.c_float),
+                ("yaw_step", ctypes.c_float), ("yaw_range", ctypes.c_float), ("mean_error_threshold", ctypes.c_float)]
 
 
 class IcpResult(ctypes.Structure):
@@ -83,6 +89,9 @@ def lib() -> ctypes.CDLL:
     L.ssf_cloud_subsample.argtypes = [vp, vp, sz, sz, sz, vp, P(sz)]
     L.ssf_cloud_remove_floor.argtypes = [vp, vp, sz, sz, vp, P(sz)]
     L.ssf_cloud_crop_radius.argtypes = [vp, vp, sz, sz, vp, ctypes.c_double, vp, P(sz), vp]
+    L.ssf_bfa_pose_count.argtypes = [vp]
+    L.ssf_bfa_pose_count.restype = sz
+    L.ssf_bfa_align.argtypes = [vp, vp, sz, sz, vp, vp, vp, vp, vp, vp]
     L.ssf_batch_create.argtypes = [vp, sz, sz, P(vp)]
     L.ssf_batch_destroy.argtypes = [vp]
     L.ssf_batch_destroy.restype = None
