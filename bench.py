@@ -325,17 +325,36 @@ def run_gpu(args, rank, world, local_rank):
     barrier()
 
     # ---- e2e: host buffers in, host results out ---------------------------------------------------
-    for _ in range(max(1, args.warmup // 2)):
-        e2e_step()
+    # Two batches in flight: the H2D copy of step i+1 (per-batch copy stream) overlaps the alignment
+    # of step i, and the D2H of step i's results is collected while step i+1 runs.  Every step's
+    # copies are inside the timed region.
+    batch2 = ssf_gpu.Batch(icp, B, total + 1)
+    pair = [batch, batch2]
+
+    def e2e_pipelined(steps):
+        pending = None
+        for i in range(steps):
+            b = pair[i % 2]
+            b.upload_ptr(pinned.data_ptr(), n_pts, 16, wait=False)
+            b.set_initial_ptr(T_pinned.data_ptr())
+            b.run()
+            if pending is not None:
+                pending.results_into(res)
+            pending = b
+        pending.results_into(res)
+
+    e2e_pipelined(max(2, args.warmup))
     barrier()
+    t0 = time.perf_counter()
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ee0.record(stream)
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_pipelined(args.steps)
     ee1.record(stream)
     ctx.synchronize()
     ee1.synchronize()
-    e2e_s = ee0.elapsed_time(ee1) * 1e-3
+    # the first H2D starts on the copy stream before ee0 completes on the compute stream: take the
+    # larger of the device interval and the host wall clock around the same calls
+    e2e_s = max(ee0.elapsed_time(ee1) * 1e-3, time.perf_counter() - t0)
     clocks = sampler.stop()
     barrier()
 

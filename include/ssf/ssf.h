@@ -186,6 +186,10 @@ int ssf_batch_create(ssf_icp *icp, size_t max_scans, size_t max_total_points, ss
 void ssf_batch_destroy(ssf_batch *b);
 /* Copy n_scans scans to HBM.  xyz: concatenated points of all scans; n_pts[s] their sizes. */
 int ssf_batch_upload(ssf_batch *b, const float *xyz, const size_t *n_pts, size_t n_scans, size_t stride_bytes);
+/* Same, but returns without waiting for the copy: the caller's buffer (pinned memory for a true
+ * overlap) must stay untouched until ssf_batch_results of this batch returns.  Uploads run on a
+ * per-batch copy stream, so the upload of one batch overlaps the alignment of another. */
+int ssf_batch_upload_async(ssf_batch *b, const float *xyz, const size_t *n_pts, size_t n_scans, size_t stride_bytes);
 /* Initial transforms, n_scans x 16 floats column-major. */
 int ssf_batch_set_initial(ssf_batch *b, const float *T_colmajor);
 /* Run the whole batch on the device; asynchronous on the context stream. */

@@ -55,6 +55,10 @@ struct ssf_batch {
     bool uploaded = false, initial_set = false, ran = false;
     bool uploaded_raw = false;  // scans went to buf.raw (voxel stage in front of the loop)
     float last_ms = 0.f;
+    // copies run on their own stream so the upload of one batch overlaps the alignment of another
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t uploaded_ev = nullptr, ran_ev = nullptr, ev0 = nullptr, ev1 = nullptr;
+    DevBuf<unsigned char> stage;  // raw bytes of the caller's scans before packing
 };
 
 struct ssf_icp {
@@ -649,8 +653,15 @@ extern "C" int ssf_batch_create(ssf_icp *icp, size_t max_scans, size_t max_total
     chk(b->buf.results.reserve(max_scans));
     chk(b->T_init_dev.reserve(max_scans * 16));
     chk(b->meta_dev.reserve(max_scans * 5));
+    if (rc == SSF_OK && (cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                         cudaEventCreateWithFlags(&b->uploaded_ev, cudaEventDisableTiming) != cudaSuccess ||
+                         cudaEventCreateWithFlags(&b->ran_ev, cudaEventDisableTiming) != cudaSuccess ||
+                         cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess)) {
+        set_error("ssf_batch_create: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = SSF_ERR_CUDA;
+    }
     if (rc != SSF_OK) {
-        delete b;
+        ssf_batch_destroy(b);
         return rc;
     }
     *out = b;
@@ -662,11 +673,17 @@ extern "C" void ssf_batch_destroy(ssf_batch *b)
     if (!b) return;
     cudaSetDevice(b->icp->ctx->device);
     cudaStreamSynchronize(b->icp->ctx->stream);
+    if (b->copy_stream) cudaStreamSynchronize(b->copy_stream);
+    if (b->uploaded_ev) cudaEventDestroy(b->uploaded_ev);
+    if (b->ran_ev) cudaEventDestroy(b->ran_ev);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
     delete b;
 }
 
-extern "C" int ssf_batch_upload(ssf_batch *b, const float *xyz, const size_t *n_pts, size_t n_scans,
-                                size_t stride_bytes)
+static int batch_upload_impl(ssf_batch *b, const float *xyz, const size_t *n_pts, size_t n_scans, size_t stride_bytes,
+                             bool wait)
 {
     SSF_ARG(b && n_pts, "ssf_batch_upload: NULL argument");
     SSF_ARG(n_scans >= 1 && n_scans <= b->max_scans, "ssf_batch_upload: n_scans exceeds the batch capacity");
@@ -677,6 +694,9 @@ extern "C" int ssf_batch_upload(ssf_batch *b, const float *xyz, const size_t *n_
     for (size_t s = 0; s < n_scans; ++s) total += n_pts[s];
     SSF_ARG(total <= b->max_points, "ssf_batch_upload: points exceed the batch capacity");
     SSF_ARG(total == 0 || xyz, "ssf_batch_upload: xyz == NULL");
+    cudaStream_t cs = b->copy_stream;
+    // a previous alignment of THIS batch may still read its buffers
+    if (b->ran) SSF_CUDA(cudaStreamWaitEvent(cs, b->ran_ev, 0));
     b->meta_host.assign(5 * n_scans, 0);
     b->n_raw.assign(n_scans, 0);
     size_t raw = 0, tile = 0;
@@ -698,13 +718,13 @@ extern "C" int ssf_batch_upload(ssf_batch *b, const float *xyz, const size_t *n_
     b->buf.n_tiles = tile;
     b->buf.n_slots = tile * kTile;
     b->total_points = total;
-    // previous work on the stream may still read meta/stage: the stream orders it
+    // meta_host is pageable: cudaMemcpyAsync returns once it has been staged, so it may be reused
     SSF_CUDA(cudaMemcpyAsync(b->meta_dev.p, b->meta_host.data(), b->meta_host.size() * sizeof(uint32_t),
-                             cudaMemcpyHostToDevice, ctx->stream));
+                             cudaMemcpyHostToDevice, cs));
     if (total > 0) {
         const size_t bytes = (total - 1) * stride_bytes + 12;
-        SSF_TRY(ctx->stage.reserve(bytes));
-        SSF_CUDA(cudaMemcpyAsync(ctx->stage.p, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        SSF_TRY(b->stage.reserve(bytes));
+        SSF_CUDA(cudaMemcpyAsync(b->stage.p, xyz, bytes, cudaMemcpyHostToDevice, cs));
         unsigned bx = (max_n + 255) / 256;
         if (bx > 64) bx = 64;
         if (bx == 0) bx = 1;
@@ -713,20 +733,30 @@ extern "C" int ssf_batch_upload(ssf_batch *b, const float *xyz, const size_t *n_
             SSF_TRY(b->buf.raw.reserve(b->buf.src.cap));
             dst = b->buf.raw.p;
         }
-        pack_scans_kernel<<<dim3(bx, (unsigned)n_scans), 256, 0, ctx->stream>>>(ctx->stage.p, stride_bytes, b->meta_dev.p,
-                                                                              dst);
+        pack_scans_kernel<<<dim3(bx, (unsigned)n_scans), 256, 0, cs>>>(b->stage.p, stride_bytes, b->meta_dev.p, dst);
         SSF_LAUNCHED();
     }
     b->uploaded_raw = b->icp->prm.source_voxel_leaf > 0.f;
-    layout_kernel<<<(unsigned)n_scans, 128, 0, ctx->stream>>>(b->buf.state.p, b->meta_dev.p, (uint32_t)n_scans,
-                                                             b->buf.tile_scan.p);
+    layout_kernel<<<(unsigned)n_scans, 128, 0, cs>>>(b->buf.state.p, b->meta_dev.p, (uint32_t)n_scans, b->buf.tile_scan.p);
     SSF_LAUNCHED();
-    // the host vectors are pageable: make sure the copies above have consumed them
-    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    SSF_CUDA(cudaEventRecord(b->uploaded_ev, cs));
+    if (wait) SSF_CUDA(cudaStreamSynchronize(cs));  // the caller's buffer is free again
     b->uploaded = true;
     b->initial_set = false;
     b->ran = false;
     return SSF_OK;
+}
+
+extern "C" int ssf_batch_upload(ssf_batch *b, const float *xyz, const size_t *n_pts, size_t n_scans,
+                                size_t stride_bytes)
+{
+    return batch_upload_impl(b, xyz, n_pts, n_scans, stride_bytes, true);
+}
+
+extern "C" int ssf_batch_upload_async(ssf_batch *b, const float *xyz, const size_t *n_pts, size_t n_scans,
+                                      size_t stride_bytes)
+{
+    return batch_upload_impl(b, xyz, n_pts, n_scans, stride_bytes, false);
 }
 
 extern "C" int ssf_batch_set_initial(ssf_batch *b, const float *T_colmajor)
@@ -738,9 +768,11 @@ extern "C" int ssf_batch_set_initial(ssf_batch *b, const float *T_colmajor)
     }
     ssf_ctx *ctx = b->icp->ctx;
     SSF_TRY(use_device(ctx));
+    if (b->ran) SSF_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ran_ev, 0));
+    // small (64 B per scan): staged by the runtime when pageable, so the caller's array is free on return
     SSF_CUDA(cudaMemcpyAsync(b->T_init_dev.p, T_colmajor, b->buf.n_scans * 16 * sizeof(float), cudaMemcpyHostToDevice,
-                             ctx->stream));
-    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+                             b->copy_stream));
+    SSF_CUDA(cudaEventRecord(b->uploaded_ev, b->copy_stream));
     b->initial_set = true;
     return SSF_OK;
 }
@@ -774,7 +806,8 @@ extern "C" int ssf_batch_run(ssf_batch *b)
         set_error("ssf_batch_run: source_voxel_leaf changed after the scans were uploaded; upload again");
         return SSF_ERR_STATE;
     }
-    SSF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    SSF_CUDA(cudaStreamWaitEvent(ctx->stream, b->uploaded_ev, 0));
+    SSF_CUDA(cudaEventRecord(b->ev0, ctx->stream));
     if (p.source_voxel_leaf > 0.f && b->total_points > 0)
         SSF_TRY(voxel_downsample_batch(buf, b->meta_dev.p, p.source_voxel_leaf, ctx->scratch, ctx->stream));
     SSF_TRY(init_states(buf, b->T_init_dev.p, ctx->stream));
@@ -785,7 +818,8 @@ extern "C" int ssf_batch_run(ssf_batch *b)
         cfg.allreduce_user = icp->allreduce_user;
     }
     SSF_TRY(run_batch(icp->map.view, cfg, buf, ctx->stream, &ctx->timer));
-    SSF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    SSF_CUDA(cudaEventRecord(b->ev1, ctx->stream));
+    SSF_CUDA(cudaEventRecord(b->ran_ev, ctx->stream));
     b->ran = true;
     return SSF_OK;
 }
@@ -800,11 +834,14 @@ extern "C" int ssf_batch_results(ssf_batch *b, ssf_icp_result *out, size_t n_sca
     SSF_ARG(n_scans <= b->buf.n_scans, "ssf_batch_results: n_scans larger than the batch");
     ssf_ctx *ctx = b->icp->ctx;
     SSF_TRY(use_device(ctx));
+    // D2H on the batch's copy stream: waits for THIS batch's alignment only, so another batch may
+    // keep the compute stream busy meanwhile
+    SSF_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ran_ev, 0));
     SSF_CUDA(cudaMemcpyAsync(out, b->buf.results.p, n_scans * sizeof(ssf_icp_result), cudaMemcpyDeviceToHost,
-                             ctx->stream));
-    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+                             b->copy_stream));
+    SSF_CUDA(cudaStreamSynchronize(b->copy_stream));
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) {
+    if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) != cudaSuccess) {
         cudaGetLastError();
         ms = 0.f;
     }

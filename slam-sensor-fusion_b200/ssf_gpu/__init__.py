@@ -265,9 +265,11 @@ class Batch:
         capi.check(capi.lib().ssf_batch_create(icp._h, max_scans, max_total_points, ctypes.byref(self._h)))
         self.n_scans = 0
 
-    def upload_ptr(self, ptr: int, n_pts, stride_bytes: int = 16) -> None:
+    def upload_ptr(self, ptr: int, n_pts, stride_bytes: int = 16, wait: bool = True) -> None:
+        """wait=False: asynchronous copy -- keep the host buffer untouched until results() returns."""
         arr = (ctypes.c_size_t * len(n_pts))(*[int(n) for n in n_pts])
-        capi.check(capi.lib().ssf_batch_upload(self._h, ptr, arr, len(n_pts), stride_bytes))
+        fn = capi.lib().ssf_batch_upload if wait else capi.lib().ssf_batch_upload_async
+        capi.check(fn(self._h, ptr, arr, len(n_pts), stride_bytes))
         self.n_scans = len(n_pts)
 
     def upload(self, scans: list) -> None:

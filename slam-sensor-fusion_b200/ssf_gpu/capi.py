@@ -17,7 +17,7 @@ EXPORTS = [
     "ssf_icp_create", "ssf_icp_destroy", "ssf_icp_set_params", "ssf_icp_get_params", "ssf_icp_set_target",
     "ssf_icp_set_source", "ssf_icp_set_initial", "ssf_icp_align", "ssf_icp_get_correspondences", "ssf_icp_get_trace",
     "ssf_icp_target_size", "ssf_icp_set_target_shard", "ssf_icp_set_allreduce", "ssf_nn_search", "ssf_voxel_downsample", "ssf_cloud_subsample", "ssf_cloud_remove_floor", "ssf_cloud_crop_radius", "ssf_bfa_pose_count", "ssf_bfa_align", "ssf_batch_create", "ssf_batch_destroy",
-    "ssf_batch_upload", "ssf_batch_set_initial", "ssf_batch_run", "ssf_batch_results", "ssf_icp_align_batch",
+    "ssf_batch_upload", "ssf_batch_upload_async", "ssf_batch_set_initial", "ssf_batch_run", "ssf_batch_results", "ssf_icp_align_batch",
     "ssf_kernel_launches", "ssf_nn_queries",
 ]
 
@@ -96,6 +96,7 @@ def lib() -> ctypes.CDLL:
     L.ssf_batch_destroy.argtypes = [vp]
     L.ssf_batch_destroy.restype = None
     L.ssf_batch_upload.argtypes = [vp, vp, vp, sz, sz]
+    L.ssf_batch_upload_async.argtypes = [vp, vp, vp, sz, sz]
     L.ssf_batch_set_initial.argtypes = [vp, vp]
     L.ssf_batch_run.argtypes = [vp]
     L.ssf_batch_results.argtypes = [vp, vp, sz]
