@@ -136,6 +136,12 @@ size_t ssf_icp_target_size(const ssf_icp *icp);
 int ssf_nn_search(ssf_icp *icp, const float *queries, size_t n, size_t stride_bytes, float max_sqdist, int32_t *idx,
                   float *d2);
 
+/* Throughput of the search alone ("NN queries/sec" of BASELINE.json): uploads the n queries once,
+ * runs the search kernel `reps` times back to back and returns the average device time of one
+ * pass in *ms_per_pass (CUDA events).  Results of the last pass go to idx / d2 when non-NULL. */
+int ssf_nn_search_bench(ssf_icp *icp, const float *queries, size_t n, size_t stride_bytes, float max_sqdist, int reps,
+                        float *ms_per_pass, int32_t *idx, float *d2);
+
 /* pcl::VoxelGrid<PointXYZ> with setLeafSize(leaf, leaf, leaf)
  * (localization/src/global_map_frames_manager.cpp:143-146).  out must hold n float4
  * (16-byte stride, w = 1).  *refused = 1 when PCL's index-overflow guard fires, in which

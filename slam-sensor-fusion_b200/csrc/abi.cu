@@ -496,6 +496,34 @@ extern "C" int ssf_nn_search(ssf_icp *icp, const float *queries, size_t n, size_
     return SSF_OK;
 }
 
+extern "C" int ssf_nn_search_bench(ssf_icp *icp, const float *queries, size_t n, size_t stride_bytes, float max_sqdist,
+                                   int reps, float *ms_per_pass, int32_t *idx, float *d2)
+{
+    SSF_ARG(icp && queries && ms_per_pass && n > 0 && reps > 0, "ssf_nn_search_bench: bad argument");
+    if (!icp->has_target) {
+        set_error("ssf_nn_search_bench: no target set");
+        return SSF_ERR_STATE;
+    }
+    ssf_ctx *ctx = icp->ctx;
+    SSF_TRY(use_device(ctx));
+    SSF_TRY(icp->q_dev.reserve(n));
+    SSF_TRY(icp->q_idx.reserve(n));
+    SSF_TRY(icp->q_d2.reserve(n));
+    SSF_TRY(upload_cloud(ctx, queries, n, stride_bytes, icp->q_dev.p));
+    SSF_TRY(nn_search_device(icp->map.view, icp->q_dev.p, n, max_sqdist, icp->q_idx.p, icp->q_d2.p, ctx->stream));  // warm-up
+    SSF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int r = 0; r < reps; ++r)
+        SSF_TRY(nn_search_device(icp->map.view, icp->q_dev.p, n, max_sqdist, icp->q_idx.p, icp->q_d2.p, ctx->stream));
+    SSF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (idx) SSF_CUDA(cudaMemcpyAsync(idx, icp->q_idx.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (d2) SSF_CUDA(cudaMemcpyAsync(d2, icp->q_d2.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    SSF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    *ms_per_pass = ms / (float)reps;
+    return SSF_OK;
+}
+
 // ---- voxel grid ---------------------------------------------------------------------------------
 extern "C" int ssf_voxel_downsample(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, float leaf,
                                     float *out, size_t *n_out, int *refused)

@@ -7,7 +7,7 @@
 
 namespace ssf {
 
-constexpr int kTile = 256;  // queries per block of the search kernels; scans are tile-aligned
+constexpr int kTile = 128;  // queries per block of the search kernels; scans are tile-aligned
 constexpr int kAccum = 32;  // doubles per partial row
 
 // One scan of a batch (device memory).

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(kTile)
 {
     __shared__ float sT[16];
     __shared__ double sred[kTile / 32][kAccum];
+    __shared__ WarpNN wnn[kTile / 32];
     const uint32_t scan = tile_scan[blockIdx.x];
     const ScanState &z = states[scan];
     if (z.done) return;
@@ -130,18 +131,20 @@ __global__ void __launch_bounds__(kTile)
     double v[kAccum];
 #pragma unroll
     for (int i = 0; i < kAccum; ++i) v[i] = 0.0;
+    const size_t slot = (size_t)z.pt_begin + row;
+    float3 p = make_float3(0.f, 0.f, 0.f);
+    bool mine = false;
     if (valid) {
-        const size_t slot = (size_t)z.pt_begin + row;
         const float4 s4 = src[slot];
-        const float3 p = transform_point(sT, s4.x, s4.y, s4.z);
+        p = transform_point(sT, s4.x, s4.y, s4.z);
         // map sharding: only the rank that owns the query's cell column searches it, so every
         // correspondence is counted exactly once across ranks (halo >= one cell on each side)
         const int qcx = cell_coord(p.x, map.ox, map.inv_h, map.nx);
-        const bool mine = qcx >= map.own_lo && qcx < map.own_hi;
-        NNHit h;
-        h.idx = -2;
-        h.pos = 0;
-        if (mine) h = nn_query(map, p.x, p.y, p.z, limit);
+        mine = qcx >= map.own_lo && qcx < map.own_hi;
+    }
+    NNHit h = nn_query_warp(map, p.x, p.y, p.z, limit, valid && mine, wnn[threadIdx.x >> 5]);
+    if (valid && !mine) h.idx = -2;
+    if (valid) {
         corr[slot] = h.idx;
         if (h.idx >= 0) {
             const float4 q = __ldg(&map.pts[h.pos]);
@@ -322,6 +325,7 @@ __global__ void __launch_bounds__(kTile)
                       const ScanState *__restrict__ states, float limit, int first)
 {
     __shared__ float sT[16];
+    __shared__ WarpNN wnn[kTile / 32];
     const uint32_t scan = tile_scan[blockIdx.x];
     const ScanState &z = states[scan];
     if (z.done || (!first && !z.need_search)) return;
@@ -332,19 +336,23 @@ __global__ void __launch_bounds__(kTile)
         __syncthreads();
     }
     const uint32_t row = row0 + threadIdx.x;
-    if (row >= z.n_pts) return;
     const size_t slot = (size_t)z.pt_begin + row;
-    float3 p;
-    if (first) {
-        const float4 s4 = src[slot];
-        p = transform_point(sT, s4.x, s4.y, s4.z);
-        P[slot] = make_float4(p.x, p.y, p.z, 1.f);
-    } else {
-        if (corr[slot] < 0) return;
-        const float4 p4 = P[slot];
-        p = make_float3(p4.x, p4.y, p4.z);
+    bool active = row < z.n_pts;
+    float3 p = make_float3(0.f, 0.f, 0.f);
+    if (active) {
+        if (first) {
+            const float4 s4 = src[slot];
+            p = transform_point(sT, s4.x, s4.y, s4.z);
+            P[slot] = make_float4(p.x, p.y, p.z, 1.f);
+        } else if (corr[slot] < 0) {
+            active = false;  // dropped rows stay dropped
+        } else {
+            const float4 p4 = P[slot];
+            p = make_float3(p4.x, p4.y, p4.z);
+        }
     }
-    const NNHit h = nn_query(map, p.x, p.y, p.z, limit);
+    const NNHit h = nn_query_warp(map, p.x, p.y, p.z, limit, active, wnn[threadIdx.x >> 5]);
+    if (!active) return;
     corr[slot] = h.idx;
     if (h.idx >= 0) {
         float4 q = __ldg(&map.pts[h.pos]);
@@ -599,10 +607,12 @@ __global__ void __launch_bounds__(kTile)
     nn_only_kernel(MapView map, const float4 *__restrict__ q, uint32_t n, float limit, int32_t *__restrict__ idx,
                    float *__restrict__ d2)
 {
+    __shared__ WarpNN wnn[kTile / 32];
     const uint32_t i = blockIdx.x * kTile + threadIdx.x;
-    if (i >= n) return;
-    const float4 p = q[i];
-    const NNHit h = nn_query(map, p.x, p.y, p.z, limit);
+    const bool active = i < n;
+    const float4 p = active ? q[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const NNHit h = nn_query_warp(map, p.x, p.y, p.z, limit, active, wnn[threadIdx.x >> 5]);
+    if (!active) return;
     idx[i] = h.idx;
     d2[i] = h.idx >= 0 ? h.d2 : FLT_MAX;
 }

@@ -264,6 +264,174 @@ __device__ __forceinline__ NNHit nn_query(const MapView &m, float px, float py, 
     return h;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Warp-cooperative form.  Must be called by all 32 lanes of a warp (inactive lanes pass active =
+// false).  Each lane scans its own cell exactly like nn_query; the neighbour items that survive
+// the pruning mask are then published to a shared-memory queue and drained by ALL lanes, one
+// (owner, item) per lane per round, so the neighbour phase no longer runs with a handful of
+// lanes.  Results merge through 64-bit atomicMin on the packed (d2, index) key -- a minimum over
+// the same candidate set in any order -- so the outcome is identical to the sequential walk.
+// The position of the winner travels in a second key (d2, position); when an exact cross-cell
+// tie makes the two disagree (checked), the lane falls back to the sequential walk.
+// ---------------------------------------------------------------------------------------------------
+struct WarpNN {
+    float px[32], py[32], pz[32];
+    int cx[32], cy[32], cz[32];
+    float t_lo[3][32], t_hi[3][32];
+    uint4 own[32];
+    uint32_t flags[32];  // bit0 in_xl, bit1 in_xh, bit2 in_x0, bit3 near_left, bit4 sy > 0, bit5 sz > 0
+    unsigned long long key[32], pkey[32];
+    unsigned short queue[32 * 10];
+};
+
+__device__ __forceinline__ NNHit nn_query_warp(const MapView &m, float px, float py, float pz, float limit, bool active,
+                                               WarpNN &w)
+{
+    const int lane = threadIdx.x & 31;
+    NNHit h;
+    h.d2 = limit;
+    h.idx = -1;
+    h.pos = 0;
+    const unsigned long long none = (unsigned long long)__float_as_uint(limit) << 32;
+    unsigned long long best = none;
+    uint32_t pos = 0, mask = 0;
+    active = active && limit > 0.f && isfinite(px) && isfinite(py) && isfinite(pz);
+    CellBox b = {0, -1, 0, -1, 0, -1};
+    if (active) b = cell_box(m, px, py, pz, limit);
+    active = active && !(b.x0 > b.x1 || b.y0 > b.y1 || b.z0 > b.z1);
+    const int cx = cell_coord(px, m.ox, m.inv_h, m.nx), cy = cell_coord(py, m.oy, m.inv_h, m.ny),
+              cz = cell_coord(pz, m.oz, m.inv_h, m.nz);
+    const bool narrow = b.x0 >= cx - 1 && b.x1 <= cx + 1 && b.y0 >= cy - 1 && b.y1 <= cy + 1 && b.z0 >= cz - 1 &&
+                        b.z1 <= cz + 1;
+    if (active) NN_STAT(3, 1);
+    if (active && !narrow) {
+        NN_STAT(4, 1);
+        nn_walk_wide(m, b, px, py, pz, limit, best, pos);
+    }
+    float t_lo[3] = {0.f, 0.f, 0.f}, t_hi[3] = {0.f, 0.f, 0.f};
+    uint4 own = make_uint4(0, 0, 0, 0);
+    uint32_t flags = 0;
+    if (active && narrow) {
+        const float hcell = __frcp_rn(m.inv_h);
+        const float pk[3] = {px, py, pz}, ok[3] = {m.ox, m.oy, m.oz};
+        const int ck[3] = {cx, cy, cz};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {  // same thresholds as nn_query
+            const float lo = __fadd_rn(ok[k], __fmul_rn((float)ck[k], hcell));
+            const float hi = __fadd_rn(ok[k], __fmul_rn((float)(ck[k] + 1), hcell));
+            const float slack = __fmul_rn(4e-6f, fabsf(pk[k]) + fabsf(ok[k]) + __fmul_rn(fabsf((float)ck[k]) + 2.f, hcell));
+            const float rl = __fsub_rd(__fsub_rd(pk[k], lo), slack), rh = __fsub_rd(__fsub_rd(hi, pk[k]), slack);
+            t_lo[k] = rl > 0.f ? __fsub_rd(__fmul_rd(__fmul_rd(rl, rl), 0.999996f), 1e-30f) : 0.f;
+            t_hi[k] = rh > 0.f ? __fsub_rd(__fmul_rd(__fmul_rd(rh, rh), 0.999996f), 1e-30f) : 0.f;
+        }
+        const bool in_xl = b.x0 <= cx - 1, in_xh = b.x1 >= cx + 1, in_x0 = cx >= b.x0 && cx <= b.x1;
+        const float uy = __fmul_rn(__fsub_rn(py, m.oy), m.inv_h), uz = __fmul_rn(__fsub_rn(pz, m.oz), m.inv_h),
+                    ux = __fmul_rn(__fsub_rn(px, m.ox), m.inv_h);
+        const bool near_left = !((ux - floorf(ux)) > 0.5f);
+        const int sy = (uy - floorf(uy)) > 0.5f ? 1 : -1, sz = (uz - floorf(uz)) > 0.5f ? 1 : -1;
+        flags = (in_xl ? 1u : 0u) | (in_xh ? 2u : 0u) | (in_x0 ? 4u : 0u) | (near_left ? 8u : 0u) | (sy > 0 ? 16u : 0u) |
+                (sz > 0 ? 32u : 0u);
+        const bool own_ok = cy >= b.y0 && cy <= b.y1 && cz >= b.z0 && cz <= b.z1 && probe(m, cx, cy, cz, own);
+        if (own_ok && in_x0)
+            for (uint32_t j = own.y; j < own.z; j += 4) eval4(m, j, own.z, px, py, pz, best, pos);
+        const float bd = __uint_as_float((uint32_t)(best >> 32));
+        const bool xl = own_ok && in_xl && !(bd < t_lo[0]), xh = own_ok && in_xh && !(bd < t_hi[0]);
+        mask = ((near_left ? xl : xh) ? 1u : 0u) | ((near_left ? xh : xl) ? 2u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int dy = sy * ((int)((kRowY >> (2 * k)) & 3u) - 1), dz = sz * ((int)((kRowZ >> (2 * k)) & 3u) - 1);
+            const int ry = cy + dy, rz = cz + dz;
+            const bool out = ry < b.y0 || ry > b.y1 || rz < b.z0 || rz > b.z1 || (dy < 0 && bd < t_lo[1]) ||
+                             (dy > 0 && bd < t_hi[1]) || (dz < 0 && bd < t_lo[2]) || (dz > 0 && bd < t_hi[2]);
+            mask |= out ? 0u : (4u << k);
+        }
+    }
+    // ---- publish the lane's query and queue its items ----
+    w.px[lane] = px; w.py[lane] = py; w.pz[lane] = pz;
+    w.cx[lane] = cx; w.cy[lane] = cy; w.cz[lane] = cz;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { w.t_lo[k][lane] = t_lo[k]; w.t_hi[k][lane] = t_hi[k]; }
+    w.own[lane] = own;
+    w.flags[lane] = flags;
+    w.key[lane] = best;
+    w.pkey[lane] = best < none ? ((best & 0xFFFFFFFF00000000ull) | pos) : ~0ull;
+    const uint32_t cnt = __popc(mask);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    {
+        uint32_t at = incl - cnt, mm = mask;
+        while (mm) {
+            const int s = __ffs(mm) - 1;
+            mm &= mm - 1;
+            w.queue[at++] = (unsigned short)((lane << 4) | s);
+        }
+    }
+    __syncwarp();
+    // ---- drain: one (owner, item) per lane per round ----
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t i = base + lane;
+        if (i < total) {
+            const uint32_t it = w.queue[i];
+            const int o = it >> 4, s = it & 15;
+            const float opx = w.px[o], opy = w.py[o], opz = w.pz[o];
+            const uint32_t fl = w.flags[o];
+            unsigned long long lbest = *(volatile unsigned long long *)&w.key[o];
+            const unsigned long long snap = lbest;
+            const float bd = __uint_as_float((uint32_t)(lbest >> 32));
+            const bool xl = (fl & 1u) && !(bd < w.t_lo[0][o]), xh = (fl & 2u) && !(bd < w.t_hi[0][o]);
+            uint32_t j = 0, e = 0;
+            if (s < 2) {
+                const bool left = (s == 0) == ((fl & 8u) != 0);
+                if (left ? xl : xh) {
+                    const uint4 ow = w.own[o];
+                    j = left ? ow.x : ow.z;
+                    e = left ? ow.y : ow.w;
+                }
+            } else {
+                const int k = s - 2;
+                const int dy = ((fl & 16u) ? 1 : -1) * ((int)((kRowY >> (2 * k)) & 3u) - 1);
+                const int dz = ((fl & 32u) ? 1 : -1) * ((int)((kRowZ >> (2 * k)) & 3u) - 1);
+                const bool out = (dy < 0 && bd < w.t_lo[1][o]) || (dy > 0 && bd < w.t_hi[1][o]) ||
+                                 (dz < 0 && bd < w.t_lo[2][o]) || (dz > 0 && bd < w.t_hi[2][o]);
+                uint4 v;
+                if (!out && probe(m, w.cx[o], w.cy[o] + dy, w.cz[o] + dz, v)) {
+                    j = xl ? v.x : ((fl & 4u) ? v.y : v.z);
+                    e = xh ? v.w : ((fl & 4u) ? v.z : v.y);
+                }
+            }
+            uint32_t lpos = 0;
+            for (; j < e; j += 4) {
+                eval4(m, j, e, opx, opy, opz, lbest, lpos);
+                NN_STAT(6, 1);
+            }
+            if (lbest < snap) {
+                atomicMin(&w.key[o], lbest);
+                atomicMin(&w.pkey[o], (lbest & 0xFFFFFFFF00000000ull) | lpos);
+            }
+        }
+        __syncwarp();
+    }
+    best = w.key[lane];
+    const unsigned long long pk = w.pkey[lane];
+    __syncwarp();  // the scratch is reused by the next call
+    if (best < none) {
+        const int idx = (int)(uint32_t)(best & 0xFFFFFFFFull);
+        uint32_t p2 = (uint32_t)(pk & 0xFFFFFFFFull);
+        const bool consistent = (pk >> 32) == (best >> 32) && p2 < m.n_pts && __float_as_int(__ldg(&m.pts[p2]).w) == idx;
+        if (!consistent) return nn_query(m, px, py, pz, limit);  // exact cross-cell tie: sequential walk decides
+        NN_STAT(5, 1);
+        h.d2 = __uint_as_float((uint32_t)(best >> 32));
+        h.idx = idx;
+        h.pos = p2;
+    }
+    return h;
+}
+
 // reference applyTransformation (icp_point_to_point.cpp:103-105): ((T0*x + T1*y) + T2*z) + T3
 // with every product and sum rounded (the reference is built without FMA contraction)
 __device__ __forceinline__ float affine_row(float a, float b, float c, float d, float x, float y, float z)

@@ -228,6 +228,14 @@ class ICPPointToPoint:
                                             idx.ctypes.data, d2.ctypes.data))
         return idx, d2
 
+    def nearest_bench(self, queries, max_sqdist: float, reps: int = 10) -> float:
+        """Average device milliseconds of one search pass over ``queries`` (resident in HBM)."""
+        q = _cloud(queries)
+        ms = ctypes.c_float(0)
+        capi.check(capi.lib().ssf_nn_search_bench(self._h, q.ctypes.data, q.shape[0], q.strides[0], max_sqdist, reps,
+                                                  ctypes.byref(ms), None, None))
+        return float(ms.value)
+
     def align_batch(self, scans: list, inits) -> list[ICPResult]:
         """Register a list of scans against the target in one call (offline reprocessing)."""
         clouds = [_cloud(s) for s in scans]

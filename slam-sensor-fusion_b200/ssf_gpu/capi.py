@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libssf_gpu.so")
+LIB_PATH = os.environ.get("SSF_GPU_LIB") or os.path.join(os.path.dirname(_HERE), "csrc", "libssf_gpu.so")
 
 SSF_OK = 0
 MODE_REFERENCE, MODE_GN_P2P, MODE_GN_P2PLANE, MODE_O3D_P2P = 0, 1, 2, 3
@@ -16,7 +16,7 @@ EXPORTS = [
     "ssf_last_error", "ssf_version", "ssf_ctx_create", "ssf_ctx_destroy", "ssf_ctx_synchronize", "ssf_ctx_stream", "ssf_ctx_time_searches", "ssf_ctx_search_time",
     "ssf_icp_create", "ssf_icp_destroy", "ssf_icp_set_params", "ssf_icp_get_params", "ssf_icp_set_target",
     "ssf_icp_set_source", "ssf_icp_set_initial", "ssf_icp_align", "ssf_icp_get_correspondences", "ssf_icp_get_trace",
-    "ssf_icp_target_size", "ssf_icp_set_target_shard", "ssf_icp_set_allreduce", "ssf_nn_search", "ssf_voxel_downsample", "ssf_cloud_subsample", "ssf_cloud_remove_floor", "ssf_cloud_crop_radius", "ssf_bfa_pose_count", "ssf_bfa_align", "ssf_batch_create", "ssf_batch_destroy",
+    "ssf_icp_target_size", "ssf_icp_set_target_shard", "ssf_icp_set_allreduce", "ssf_nn_search", "ssf_nn_search_bench", "ssf_voxel_downsample", "ssf_cloud_subsample", "ssf_cloud_remove_floor", "ssf_cloud_crop_radius", "ssf_bfa_pose_count", "ssf_bfa_align", "ssf_batch_create", "ssf_batch_destroy",
     "ssf_batch_upload", "ssf_batch_upload_async", "ssf_batch_set_initial", "ssf_batch_run", "ssf_batch_results", "ssf_icp_align_batch",
     "ssf_kernel_launches", "ssf_nn_queries",
 ]
@@ -85,6 +85,7 @@ def lib() -> ctypes.CDLL:
     L.ssf_icp_set_target_shard.argtypes = [vp, vp, sz, sz, vp, sz, vp, vp]
     L.ssf_icp_set_allreduce.argtypes = [vp, vp, vp]
     L.ssf_nn_search.argtypes = [vp, vp, sz, sz, f32, vp, vp]
+    L.ssf_nn_search_bench.argtypes = [vp, vp, sz, sz, f32, i32, P(f32), vp, vp]
     L.ssf_voxel_downsample.argtypes = [vp, vp, sz, sz, f32, vp, P(sz), P(i32)]
     L.ssf_cloud_subsample.argtypes = [vp, vp, sz, sz, sz, vp, P(sz)]
     L.ssf_cloud_remove_floor.argtypes = [vp, vp, sz, sz, vp, P(sz)]
