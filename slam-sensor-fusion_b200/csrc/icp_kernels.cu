@@ -456,9 +456,22 @@ __device__ void strict_chains(const float4 *P, const float4 *Q, const int32_t *c
     for (uint32_t t = 0; t < n_tiles; ++t) {
         if (warp == 0) {
             if (lane < NCH) {
+                // the adds are one dependent chain (4 cycles each); keep the next 16 values in
+                // registers so the shared-memory loads never sit on the chain
                 const float *col = buf.v[t & 1][lane];
-#pragma unroll 8
-                for (int j = 0; j < kChainTile; ++j) acc = __fadd_rn(acc, col[j]);
+                float cur[16], nxt[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) cur[u] = col[u];
+                for (int j = 0; j < kChainTile; j += 16) {
+                    if (j + 16 < kChainTile) {
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) nxt[u] = col[j + 16 + u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) acc = __fadd_rn(acc, cur[u]);
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) cur[u] = nxt[u];
+                }
             }
         } else if (t + 1 < n_tiles) {
             fill(t + 1, (t + 1) & 1);
