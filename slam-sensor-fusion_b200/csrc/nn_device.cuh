@@ -37,6 +37,13 @@ static __device__ unsigned long long g_nn_stats[8];  // one copy per translation
 #define NN_STAT(i, v) ((void)0)
 #endif
 
+#ifdef SSF_BOUNDS
+// debug build only (make bounds): trap on any index outside its array
+#define SSF_CHECK(cond) do { if (!(cond)) { printf("SSF_CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); __trap(); } } while (0)
+#else
+#define SSF_CHECK(cond) ((void)0)
+#endif
+
 struct NNHit {
     float d2;      // best squared distance (== limit when nothing was found)
     int idx;       // original index of the best target point, -1 if none
@@ -78,8 +85,11 @@ __device__ __forceinline__ bool probe(const MapView &m, int cx, int cy, int cz, 
     NN_STAT(1, 1);
     while (true) {
         NN_STAT(2, 1);
+        SSF_CHECK(slot <= m.hmask);
         const unsigned long long t = __ldg(&m.hkeys[slot]);
         if (t == k) {
+            SSF_CHECK(m.hvals[slot].x <= m.hvals[slot].y && m.hvals[slot].y <= m.hvals[slot].z &&
+                      m.hvals[slot].z <= m.hvals[slot].w && m.hvals[slot].w <= m.n_pts);
             v = __ldg(&m.hvals[slot]);
             return true;
         }
@@ -100,6 +110,7 @@ __device__ __forceinline__ void eval4(const MapView &m, uint32_t j, uint32_t e, 
                                       unsigned long long &best, uint32_t &pos)
 {
     NN_STAT(0, 1);
+    SSF_CHECK(j < e && e <= m.n_pts);
     const uint32_t last = e - 1;
     const uint32_t j0 = j, j1 = min(j + 1, last), j2 = min(j + 2, last), j3 = min(j + 3, last);
     const float4 q0 = __ldg(&m.pts[j0]), q1 = __ldg(&m.pts[j1]), q2 = __ldg(&m.pts[j2]), q3 = __ldg(&m.pts[j3]);
@@ -368,6 +379,7 @@ __device__ __forceinline__ NNHit nn_query_warp(const MapView &m, float px, float
         while (mm) {
             const int s = __ffs(mm) - 1;
             mm &= mm - 1;
+            SSF_CHECK(at < 320);
             w.queue[at++] = (unsigned short)((lane << 4) | s);
         }
     }
