@@ -214,6 +214,9 @@ __device__ __forceinline__ NNHit nn_query(const MapView &m, float px, float py, 
         if (own_ok && in_x0)
             for (uint32_t j = own.y; j < own.z; j += 4) eval4(m, j, own.z, px, py, pz, best, pos);
         // 2. which of the ten neighbour items can still hold a better point?
+        // A neighbour block's squared distance is at least the SUM of its per-axis squared gaps
+        // (each t_* under-estimates one gap^2; the sum is rounded down), so diagonal rows and the
+        // x-cells of a row are pruned by the box bound, not axis by axis.
         float bd = __uint_as_float((uint32_t)(best >> 32));
         uint32_t mask = 0;
         {
@@ -223,8 +226,8 @@ __device__ __forceinline__ NNHit nn_query(const MapView &m, float px, float py, 
             for (int k = 0; k < 8; ++k) {
                 const int dy = sy * ((int)((kRowY >> (2 * k)) & 3u) - 1), dz = sz * ((int)((kRowZ >> (2 * k)) & 3u) - 1);
                 const int ry = cy + dy, rz = cz + dz;
-                const bool out = ry < b.y0 || ry > b.y1 || rz < b.z0 || rz > b.z1 || (dy < 0 && bd < t_lo[1]) ||
-                                 (dy > 0 && bd < t_hi[1]) || (dz < 0 && bd < t_lo[2]) || (dz > 0 && bd < t_hi[2]);
+                const float lb = __fadd_rd(dy < 0 ? t_lo[1] : (dy > 0 ? t_hi[1] : 0.f), dz < 0 ? t_lo[2] : (dz > 0 ? t_hi[2] : 0.f));
+                const bool out = ry < b.y0 || ry > b.y1 || rz < b.z0 || rz > b.z1 || bd < lb;
                 mask |= out ? 0u : (4u << k);
             }
         }
@@ -246,13 +249,13 @@ __device__ __forceinline__ NNHit nn_query(const MapView &m, float px, float py, 
                     } else {
                         const int k = s - 2;
                         const int dy = sy * ((int)((kRowY >> (2 * k)) & 3u) - 1), dz = sz * ((int)((kRowZ >> (2 * k)) & 3u) - 1);
-                        if ((dy < 0 && bd < t_lo[1]) || (dy > 0 && bd < t_hi[1]) || (dz < 0 && bd < t_lo[2]) ||
-                            (dz > 0 && bd < t_hi[2]))
-                            continue;
+                        const float lb = __fadd_rd(dy < 0 ? t_lo[1] : (dy > 0 ? t_hi[1] : 0.f), dz < 0 ? t_lo[2] : (dz > 0 ? t_hi[2] : 0.f));
+                        if (bd < lb) continue;
                         uint4 v;
                         if (!probe(m, cx, cy + dy, cz + dz, v)) continue;
-                        j = xl ? v.x : (in_x0 ? v.y : v.z);
-                        e = xh ? v.w : (in_x0 ? v.z : v.y);
+                        const bool rl = in_xl && !(bd < __fadd_rd(lb, t_lo[0])), rh = in_xh && !(bd < __fadd_rd(lb, t_hi[0]));
+                        j = rl ? v.x : (in_x0 ? v.y : v.z);
+                        e = rh ? v.w : (in_x0 ? v.z : v.y);
                     }
                     if (j < e) {
                         got = true;
@@ -352,8 +355,8 @@ __device__ __forceinline__ NNHit nn_query_warp(const MapView &m, float px, float
         for (int k = 0; k < 8; ++k) {
             const int dy = sy * ((int)((kRowY >> (2 * k)) & 3u) - 1), dz = sz * ((int)((kRowZ >> (2 * k)) & 3u) - 1);
             const int ry = cy + dy, rz = cz + dz;
-            const bool out = ry < b.y0 || ry > b.y1 || rz < b.z0 || rz > b.z1 || (dy < 0 && bd < t_lo[1]) ||
-                             (dy > 0 && bd < t_hi[1]) || (dz < 0 && bd < t_lo[2]) || (dz > 0 && bd < t_hi[2]);
+            const float lb = __fadd_rd(dy < 0 ? t_lo[1] : (dy > 0 ? t_hi[1] : 0.f), dz < 0 ? t_lo[2] : (dz > 0 ? t_hi[2] : 0.f));
+            const bool out = ry < b.y0 || ry > b.y1 || rz < b.z0 || rz > b.z1 || bd < lb;
             mask |= out ? 0u : (4u << k);
         }
     }
@@ -408,12 +411,14 @@ __device__ __forceinline__ NNHit nn_query_warp(const MapView &m, float px, float
                 const int k = s - 2;
                 const int dy = ((fl & 16u) ? 1 : -1) * ((int)((kRowY >> (2 * k)) & 3u) - 1);
                 const int dz = ((fl & 32u) ? 1 : -1) * ((int)((kRowZ >> (2 * k)) & 3u) - 1);
-                const bool out = (dy < 0 && bd < w.t_lo[1][o]) || (dy > 0 && bd < w.t_hi[1][o]) ||
-                                 (dz < 0 && bd < w.t_lo[2][o]) || (dz > 0 && bd < w.t_hi[2][o]);
+                const float lb = __fadd_rd(dy < 0 ? w.t_lo[1][o] : (dy > 0 ? w.t_hi[1][o] : 0.f),
+                                           dz < 0 ? w.t_lo[2][o] : (dz > 0 ? w.t_hi[2][o] : 0.f));
                 uint4 v;
-                if (!out && probe(m, w.cx[o], w.cy[o] + dy, w.cz[o] + dz, v)) {
-                    j = xl ? v.x : ((fl & 4u) ? v.y : v.z);
-                    e = xh ? v.w : ((fl & 4u) ? v.z : v.y);
+                if (!(bd < lb) && probe(m, w.cx[o], w.cy[o] + dy, w.cz[o] + dz, v)) {
+                    const bool rl = (fl & 1u) && !(bd < __fadd_rd(lb, w.t_lo[0][o]));
+                    const bool rh = (fl & 2u) && !(bd < __fadd_rd(lb, w.t_hi[0][o]));
+                    j = rl ? v.x : ((fl & 4u) ? v.y : v.z);
+                    e = rh ? v.w : ((fl & 4u) ? v.z : v.y);
                 }
             }
             uint32_t lpos = 0;
