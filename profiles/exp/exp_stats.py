@@ -1,4 +1,4 @@
-"""Search statistics (debug build libssf_gpu_stats.so): candidates / probes / trips per query."""
+"""Search statistics (debug build libssf_gpu_stats.so): eval4 calls / directory loads / rows per query."""
 import sys, os, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "slam-sensor-fusion_b200"))
@@ -26,6 +26,6 @@ for iters in (1, 10):
     b.run(); ctx.synchronize()
     L.ssf_debug_nn_stats(st, 1)
     q = st[3]
-    print(f"iters={iters}: queries {q}  cand/query {4*st[0]/q:.1f}  eval4/query {st[0]/q:.2f}  probes/query {st[1]/q:.2f} "
-          f"slots/probe {st[2]/max(1,st[1]):.2f}  wide {st[4]/q:.4f}  matched {st[5]/q:.3f}  trips/query {st[6]/q:.2f}")
+    print(f"iters={iters}: queries {q}  eval4/query {st[0]/q:.2f}  dir loads/query {st[1]/q:.2f}  rows/query {st[2]/q:.2f} "
+          f"runs/query {st[6]/q:.2f}  past-ring-1 {st[4]/q:.4f}  matched {st[5]/q:.3f}")
     b.close()

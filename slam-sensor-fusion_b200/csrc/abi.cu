@@ -71,7 +71,6 @@ struct ssf_icp {
     bool has_source = false;
     size_t n_source = 0;
     bool in_shard_call = false;
-    float shard_cell = 0.f;           // cell edge fixed by ssf_shard_info (all ranks must agree)
     AllreduceFn allreduce = nullptr;  // map sharding hook
     void *allreduce_user = nullptr;
     DevBuf<float4> q_dev;  // ssf_nn_search temporaries
@@ -225,19 +224,6 @@ static int check_params(const ssf_icp_params *p)
     return SSF_OK;
 }
 
-// cell edge for a rejection threshold thr (compared with SQUARED distances): one cell >= the
-// search radius so a query visits at most 3 cells per axis
-static float cell_size_for(float max_corr)
-{
-    const char *env = getenv("SSF_CELL_SIZE");
-    if (env && atof(env) > 0.0) return (float)atof(env);
-    float r = (max_corr > 0.f && std::isfinite(max_corr)) ? sqrtf(max_corr) : 1.0f;
-    float h = r * 1.01f;
-    if (h < 0.05f) h = 0.05f;
-    if (h > 4.0f) h = 4.0f;
-    return h;
-}
-
 // copy n points (stride) from the host into ctx->stage and pack them as float4 into dst
 static int upload_cloud(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, float4 *dst)
 {
@@ -318,8 +304,8 @@ extern "C" int ssf_icp_set_target(ssf_icp *icp, const float *xyz, size_t n, size
         SSF_CUDA(cudaStreamSynchronize(ctx->stream));  // stage buffer is reused
         SSF_TRY(upload_cloud(ctx, normals, n, normals_stride_bytes, m.raw_nrm.p));
     }
-    SSF_TRY(build_map_index(m, m.sharded ? icp->shard_cell : cell_size_for(icp->prm.max_correspondence_dist),
-                            ctx->scratch, ctx->stream));
+    // the cell edge is chosen from the cloud's own density (map_build.cu), not from the threshold
+    SSF_TRY(build_map_index(m, 0.f, ctx->scratch, ctx->stream));
     SSF_CUDA(cudaStreamSynchronize(ctx->stream));
     icp->has_target = true;
     return SSF_OK;
@@ -345,7 +331,7 @@ extern "C" int ssf_icp_set_target_shard(ssf_icp *icp, const float *xyz, size_t n
                                  icp->ctx->stream));
         SSF_CUDA(cudaStreamSynchronize(icp->ctx->stream));
     }
-    icp->shard_cell = info->cell_size;
+    m.shard_cell = info->cell_size;
     icp->in_shard_call = true;
     int rc = ssf_icp_set_target(icp, xyz, n, stride_bytes, normals, normals_stride_bytes);
     icp->in_shard_call = false;
@@ -358,18 +344,6 @@ extern "C" int ssf_icp_set_allreduce(ssf_icp *icp, ssf_allreduce_fn fn, void *us
     SSF_ARG(icp, "ssf_icp_set_allreduce: icp == NULL");
     icp->allreduce = fn;
     icp->allreduce_user = user;
-    return SSF_OK;
-}
-
-// re-index when the threshold moved far from the one the cells were sized for
-static int maybe_reindex(ssf_icp *icp)
-{
-    if (icp->map.sharded) return SSF_OK;  // the cell edge of a sharded map is part of the global grid
-    const float want = cell_size_for(icp->prm.max_correspondence_dist);
-    const float have = icp->map.cell_size;
-    if (have > 0.f && (want > 1.6f * have || want < 0.6f * have)) {
-        SSF_TRY(build_map_index(icp->map, want, icp->ctx->scratch, icp->ctx->stream));
-    }
     return SSF_OK;
 }
 
@@ -819,7 +793,6 @@ extern "C" int ssf_batch_run(ssf_batch *b)
     }
     ssf_ctx *ctx = icp->ctx;
     SSF_TRY(use_device(ctx));
-    SSF_TRY(maybe_reindex(icp));
     const ssf_icp_params &p = icp->prm;
     BatchBuffers &buf = b->buf;
     const int trace_len = p.mode == SSF_MODE_REFERENCE ? p.num_iterations : 0;

@@ -21,14 +21,13 @@ namespace ssf {
 
 __device__ __forceinline__ float nn_unbounded_d2(const MapView &m, float px, float py, float pz)
 {
+    if (m.n_pts == 0) return FLT_MAX;  // empty map
     const float h = __frcp_rn(m.inv_h);
-    float limit = __fmul_rn(h, h);
-    while (true) {
+    float limit = __fmul_rn(__fmul_rn(h, h), 4.0f);
+    while (true) {  // a non-empty map always answers once the limit passes the true distance
         const NNHit hit = nn_query(m, px, py, pz, limit);
         if (hit.idx >= 0) return hit.d2;
-        const CellBox b = cell_box(m, px, py, pz, limit);
-        const bool whole = b.x0 <= 0 && b.y0 <= 0 && b.z0 <= 0 && b.x1 >= m.nx - 1 && b.y1 >= m.ny - 1 && b.z1 >= m.nz - 1;
-        if (whole || !(limit < 1e30f)) return FLT_MAX;  // empty map
+        if (!(limit < 1e30f)) return FLT_MAX;
         limit = __fmul_rn(limit, 4.0f);
     }
 }

@@ -101,53 +101,40 @@ struct PinnedBuf {
 };
 
 // ---------------------------------------------------------------------------------------
-// Voxel-hash map index (built by map_build.cu, read by nn_search.cu).
+// Voxel-grid map index (built by map_build.cu, read by nn_device.cuh).
 //
-// The map cloud is sorted by cell key = morton2(cy, cz) * NX + (cx + 1): all cells of one
-// x-row are contiguous and ascending in x, rows follow a 2-D Morton curve over (y, z).
-// The hash table holds one entry per cell that is occupied or has an occupied x-neighbour;
-// its value is four offsets s0..s3 into the sorted cloud such that cell cx-1 = [s0,s1),
-// cx = [s1,s2), cx+1 = [s2,s3) -- one probe yields a contiguous run of up to three cells.
+// The map is binned into cubic cells of edge h (a few points per occupied cell; h does NOT
+// depend on the rejection threshold -- the search walks as many rings of rows as the current
+// best distance needs).  A ROW is the set of cells sharing (cy, cz); it is cut into BLOCKS of
+// 32 consecutive x cells.  The directory holds one 8-byte entry per (block, row):
+//     .x = occupancy mask of the 32 cells, .y = id of the block's first occupied cell
+// and is laid out so that the 16 rows of a 4x4 (y, z) tile at the same x block share one
+// 128-byte line:  index = (((cz>>2)*nty + (cy>>2))*nbx + bx)*16 + (cz&3)*4 + (cy&3).
+// The cloud is sorted by key = index*32 + (cx&31), so the occupied cells of a block -- and any
+// x run inside it -- are contiguous:  cells [a, b] of a block hold points
+//     [cell_start[.y + popc(mask & below(a))], cell_start[.y + popc(mask & upto(b))]).
+// One 8-byte load answers "is anything there" for up to 32 cells; no hashing, no probing.
 // ---------------------------------------------------------------------------------------
 struct MapView {
-    const float4 *pts;  // sorted; .w carries the ORIGINAL index (bit pattern of an int)
+    const float4 *pts;  // sorted by key; .w carries the ORIGINAL index (bit pattern of an int)
     const float4 *nrm;  // normals in sorted order, or nullptr
-    const unsigned long long *hkeys;
-    const uint4 *hvals;
-    uint32_t hmask;  // table size - 1 (power of two)
+    const uint2 *dir;   // directory, ntz*nty*nbx*16 entries
+    const uint32_t *cell_start;  // n_cells + 1 offsets into pts
     uint32_t n_pts;  // finite target points
     float ox, oy, oz, inv_h;
-    int nx, ny, nz;  // grid extent in cells; NX = nx + 2
-    int own_lo, own_hi;  // map sharding: this rank owns queries whose cell column cx is in [own_lo, own_hi)
+    float hq;        // (1 / inv_h) * (1 - 1e-6), rounded down: under-estimate of the cell edge
+    int nx, ny, nz;  // grid extent in cells
+    int nbx, nty;    // directory: x blocks per row, 4x4 tiles along y
+    // map sharding: this rank owns the queries whose shard column
+    // floor((x - shard_ox) * shard_inv_h) lies in [own_lo, own_hi)
+    float shard_ox, shard_inv_h;
+    int own_lo, own_hi;
 };
 
-constexpr unsigned long long kEmptyKey = ~0ull;
-
-__host__ __device__ inline uint32_t spread16(uint32_t v)
+__host__ __device__ inline uint32_t dir_index(int nbx, int nty, int bx, int cy, int cz)
 {
-    v &= 0xFFFFu;
-    v = (v | (v << 8)) & 0x00FF00FFu;
-    v = (v | (v << 4)) & 0x0F0F0F0Fu;
-    v = (v | (v << 2)) & 0x33333333u;
-    v = (v | (v << 1)) & 0x55555555u;
-    return v;
-}
-
-// cx in [-1, nx], cy in [0, ny), cz in [0, nz)
-__host__ __device__ inline unsigned long long cell_key(int cx, int cy, int cz, int nx)
-{
-    unsigned long long row = (unsigned long long)(spread16((uint32_t)cy) | (spread16((uint32_t)cz) << 1));
-    return row * (unsigned long long)(nx + 2) + (unsigned long long)(cx + 1);
-}
-
-__host__ __device__ inline uint32_t hash_key(unsigned long long k)
-{
-    uint32_t x = (uint32_t)k ^ ((uint32_t)(k >> 32) * 0x9E3779B1u);
-    x *= 0x85EBCA6Bu;
-    x ^= x >> 15;
-    x *= 0xC2B2AE35u;
-    x ^= x >> 13;
-    return x;
+    return ((((uint32_t)(cz >> 2) * (uint32_t)nty + (uint32_t)(cy >> 2)) * (uint32_t)nbx + (uint32_t)bx) << 4) |
+           (uint32_t)(((cz & 3) << 2) | (cy & 3));
 }
 
 #ifdef __CUDACC__

@@ -7,7 +7,9 @@
 
 namespace ssf {
 
-constexpr int kTile = 128;  // queries per block of the search kernels; scans are tile-aligned
+constexpr int kTile = 512;     // queries per block of the search kernels; scans are tile-aligned
+constexpr int kThreads = 128;  // threads of a fused search block
+constexpr int kQ = kTile / kThreads;  // queries per thread there
 constexpr int kAccum = 32;  // doubles per partial row
 
 // One scan of a batch (device memory).

@@ -110,91 +110,144 @@ enum AccumKind { ACC_GN_P2P = 0, ACC_GN_P2PLANE = 1, ACC_KABSCH = 2 };
 //   KABSCH: [0] K, [1..3] sum (p-c), [4..6] sum (q-c), [7..15] sum (p-c)(q-c)^T (row r, col c),
 //           [16] sum |p-q|^2, c = translation of the initial transform (pivot against cancellation)
 
+// ---- 1-D TMA bulk copy of a scan tile into shared memory --------------------------------------
+// One thread arms the mbarrier with the byte count and issues cp.async.bulk (SASS UBLKCP); the
+// copy engine moves the tile while the block loads the pose, and every thread then waits on the
+// barrier phase.  dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tile_load_issue(void *smem_dst, unsigned long long *bar, const void *gmem_src,
+                                                uint32_t bytes)
+{
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(gmem_src), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void tile_bar_init(unsigned long long *bar)
+{
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tile_bar_wait(unsigned long long *bar, uint32_t phase)
+{
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(b), "r"(phase)
+                     : "memory");
+    }
+}
+
+constexpr uint32_t kNoPos = 0xFFFFFFFFu;
+
+// A block owns one tile of kTile consecutive queries of one scan; every thread takes kQ of them
+// (rows t, t + kThreads, ...), first searching all of them, then accumulating their terms, so the
+// 32-value warp reduction is paid once per kQ queries.
 template <int KIND>
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(kThreads)
     search_accum_kernel(MapView map, const float4 *__restrict__ src, const uint32_t *__restrict__ tile_scan,
                         const ScanState *__restrict__ states, float limit, int32_t *__restrict__ corr,
                         double *__restrict__ partials)
 {
+    __shared__ __align__(128) float4 s_src[kTile];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ uint32_t s_pos[kTile];
     __shared__ float sT[16];
-    __shared__ double sred[kTile / 32][kAccum];
-    __shared__ WarpNN wnn[kTile / 32];
+    __shared__ double sred[kThreads / 32][kAccum];
     const uint32_t scan = tile_scan[blockIdx.x];
     const ScanState &z = states[scan];
     if (z.done) return;
     const uint32_t row0 = (blockIdx.x - z.tile_begin) * kTile;
     if (row0 >= z.n_pts) return;
+    const uint32_t n_here = min((uint32_t)kTile, z.n_pts - row0);
+    const size_t slot0 = (size_t)z.pt_begin + row0;
+    if (threadIdx.x == 0) tile_bar_init(&s_bar);
     if (threadIdx.x < 16) sT[threadIdx.x] = z.T[threadIdx.x];
     __syncthreads();
-    const uint32_t row = row0 + threadIdx.x;
-    const bool valid = row < z.n_pts;
+    if (threadIdx.x == 0) tile_load_issue(s_src, &s_bar, src + slot0, n_here * (uint32_t)sizeof(float4));
+    tile_bar_wait(&s_bar, 0);
+    // ---- K3: transform + exact NN + rejection ----
+    for (int k = 0; k < kQ; ++k) {
+        const uint32_t r = (uint32_t)k * kThreads + threadIdx.x;
+        if (r >= n_here) break;
+        const float4 s4 = s_src[r];
+        const float3 p = transform_point(sT, s4.x, s4.y, s4.z);
+        // map sharding: only the rank that owns the query's column searches it, so every
+        // correspondence is counted exactly once across ranks (the halo covers the radius)
+        const int col = cell_coord(p.x, map.shard_ox, map.shard_inv_h, 1 << 24);
+        const bool mine = col >= map.own_lo && col < map.own_hi;
+        int idx = -2;
+        uint32_t pos = kNoPos;
+        if (mine) {
+            const NNHit h = nn_query(map, p.x, p.y, p.z, limit);
+            idx = h.idx;
+            if (h.idx >= 0) pos = h.pos;
+        }
+        corr[slot0 + r] = idx;
+        s_pos[r] = pos;  // read back by this thread only
+    }
+    // ---- K4: residual / Jacobian terms of the matched queries ----
     double v[kAccum];
 #pragma unroll
     for (int i = 0; i < kAccum; ++i) v[i] = 0.0;
-    const size_t slot = (size_t)z.pt_begin + row;
-    float3 p = make_float3(0.f, 0.f, 0.f);
-    bool mine = false;
-    if (valid) {
-        const float4 s4 = src[slot];
-        p = transform_point(sT, s4.x, s4.y, s4.z);
-        // map sharding: only the rank that owns the query's cell column searches it, so every
-        // correspondence is counted exactly once across ranks (halo >= one cell on each side)
-        const int qcx = cell_coord(p.x, map.ox, map.inv_h, map.nx);
-        mine = qcx >= map.own_lo && qcx < map.own_hi;
-    }
-    NNHit h = nn_query_warp(map, p.x, p.y, p.z, limit, valid && mine, wnn[threadIdx.x >> 5]);
-    if (valid && !mine) h.idx = -2;
-    if (valid) {
-        corr[slot] = h.idx;
-        if (h.idx >= 0) {
-            const float4 q = __ldg(&map.pts[h.pos]);
-            if (KIND == ACC_KABSCH) {
-                const double cx = z.T_init[12], cy = z.T_init[13], cz = z.T_init[14];
-                const double a[3] = {(double)p.x - cx, (double)p.y - cy, (double)p.z - cz};
-                const double b[3] = {(double)q.x - cx, (double)q.y - cy, (double)q.z - cz};
-                v[0] = 1.0;
+    for (int k = 0; k < kQ; ++k) {
+        const uint32_t r = (uint32_t)k * kThreads + threadIdx.x;
+        if (r >= n_here) break;
+        const uint32_t pos = s_pos[r];
+        if (pos == kNoPos) continue;
+        const float4 s4 = s_src[r];
+        const float3 p = transform_point(sT, s4.x, s4.y, s4.z);
+        const float4 q = __ldg(&map.pts[pos]);
+        if (KIND == ACC_KABSCH) {
+            const double cx = z.T_init[12], cy = z.T_init[13], cz = z.T_init[14];
+            const double a[3] = {(double)p.x - cx, (double)p.y - cy, (double)p.z - cz};
+            const double b[3] = {(double)q.x - cx, (double)q.y - cy, (double)q.z - cz};
+            v[0] += 1.0;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    v[1 + k] = a[k];
-                    v[4 + k] = b[k];
-                }
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) v[7 + 3 * r + c] = a[r] * b[c];
-                const double ex = (double)p.x - q.x, ey = (double)p.y - q.y, ez = (double)p.z - q.z;
-                v[16] = ex * ex + ey * ey + ez * ez;
-            } else {
-                const double px = p.x, py = p.y, pz = p.z;
-                const double e[3] = {px - (double)q.x, py - (double)q.y, pz - (double)q.z};
-                if (KIND == ACC_GN_P2PLANE) {
-                    const float4 nf = __ldg(&map.nrm[h.pos]);
-                    const double n[3] = {nf.x, nf.y, nf.z};
-                    const double a[6] = {py * n[2] - pz * n[1], pz * n[0] - px * n[2], px * n[1] - py * n[0],
-                                         n[0], n[1], n[2]};
-                    const double r = n[0] * e[0] + n[1] * e[1] + n[2] * e[2];
-                    int t = 0;
-#pragma unroll
-                    for (int u = 0; u < 6; ++u)
-#pragma unroll
-                        for (int w = u; w < 6; ++w) v[t++] = a[u] * a[w];
-#pragma unroll
-                    for (int u = 0; u < 6; ++u) v[21 + u] = a[u] * r;
-                    v[27] = r * r;
-                } else {
-                    // J = [-[p]x | I]; J^T J = [[ -[p]x^T -[p]x , [p]x ], [ -[p]x , I ]]
-                    const double J[3][6] = {{0, pz, -py, 1, 0, 0}, {-pz, 0, px, 0, 1, 0}, {py, -px, 0, 0, 0, 1}};
-                    int t = 0;
-#pragma unroll
-                    for (int u = 0; u < 6; ++u)
-#pragma unroll
-                        for (int w = u; w < 6; ++w) v[t++] = J[0][u] * J[0][w] + J[1][u] * J[1][w] + J[2][u] * J[2][w];
-#pragma unroll
-                    for (int u = 0; u < 6; ++u) v[21 + u] = J[0][u] * e[0] + J[1][u] * e[1] + J[2][u] * e[2];
-                    v[27] = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
-                }
-                v[28] = 1.0;
+            for (int t = 0; t < 3; ++t) {
+                v[1 + t] += a[t];
+                v[4 + t] += b[t];
             }
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[7 + 3 * rr + c] += a[rr] * b[c];
+            const double ex = (double)p.x - q.x, ey = (double)p.y - q.y, ez = (double)p.z - q.z;
+            v[16] += ex * ex + ey * ey + ez * ez;
+        } else {
+            const double px = p.x, py = p.y, pz = p.z;
+            const double e[3] = {px - (double)q.x, py - (double)q.y, pz - (double)q.z};
+            if (KIND == ACC_GN_P2PLANE) {
+                const float4 nf = __ldg(&map.nrm[pos]);
+                const double n[3] = {nf.x, nf.y, nf.z};
+                const double a[6] = {py * n[2] - pz * n[1], pz * n[0] - px * n[2], px * n[1] - py * n[0],
+                                     n[0], n[1], n[2]};
+                const double rs = n[0] * e[0] + n[1] * e[1] + n[2] * e[2];
+                int t = 0;
+#pragma unroll
+                for (int u = 0; u < 6; ++u)
+#pragma unroll
+                    for (int w = u; w < 6; ++w) v[t++] += a[u] * a[w];
+#pragma unroll
+                for (int u = 0; u < 6; ++u) v[21 + u] += a[u] * rs;
+                v[27] += rs * rs;
+            } else {
+                // J = [-[p]x | I]; J^T J = [[ -[p]x^T -[p]x , [p]x ], [ -[p]x , I ]]
+                const double J[3][6] = {{0, pz, -py, 1, 0, 0}, {-pz, 0, px, 0, 1, 0}, {py, -px, 0, 0, 0, 1}};
+                int t = 0;
+#pragma unroll
+                for (int u = 0; u < 6; ++u)
+#pragma unroll
+                    for (int w = u; w < 6; ++w) v[t++] += J[0][u] * J[0][w] + J[1][u] * J[1][w] + J[2][u] * J[2][w];
+#pragma unroll
+                for (int u = 0; u < 6; ++u) v[21 + u] += J[0][u] * e[0] + J[1][u] * e[1] + J[2][u] * e[2];
+                v[27] += e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+            }
+            v[28] += 1.0;
         }
     }
     const double w = warp_transpose_reduce32(v);
@@ -204,7 +257,7 @@ __global__ void __launch_bounds__(kTile)
     if (threadIdx.x < kAccum) {
         double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < kTile / 32; ++k) s += sred[k][threadIdx.x];
+        for (int k = 0; k < kThreads / 32; ++k) s += sred[k][threadIdx.x];
         partials[(size_t)blockIdx.x * kAccum + threadIdx.x] = s;
     }
 }
@@ -325,7 +378,6 @@ __global__ void __launch_bounds__(kTile)
                       const ScanState *__restrict__ states, float limit, int first)
 {
     __shared__ float sT[16];
-    __shared__ WarpNN wnn[kTile / 32];
     const uint32_t scan = tile_scan[blockIdx.x];
     const ScanState &z = states[scan];
     if (z.done || (!first && !z.need_search)) return;
@@ -351,8 +403,8 @@ __global__ void __launch_bounds__(kTile)
             p = make_float3(p4.x, p4.y, p4.z);
         }
     }
-    const NNHit h = nn_query_warp(map, p.x, p.y, p.z, limit, active, wnn[threadIdx.x >> 5]);
     if (!active) return;
+    const NNHit h = nn_query(map, p.x, p.y, p.z, limit);
     corr[slot] = h.idx;
     if (h.idx >= 0) {
         float4 q = __ldg(&map.pts[h.pos]);
@@ -616,16 +668,14 @@ __global__ void __launch_bounds__(kRefThreads)
 // =========================================================================================
 // standalone search (parity / benchmark entry)
 // =========================================================================================
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(kThreads)
     nn_only_kernel(MapView map, const float4 *__restrict__ q, uint32_t n, float limit, int32_t *__restrict__ idx,
                    float *__restrict__ d2)
 {
-    __shared__ WarpNN wnn[kTile / 32];
-    const uint32_t i = blockIdx.x * kTile + threadIdx.x;
-    const bool active = i < n;
-    const float4 p = active ? q[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const NNHit h = nn_query_warp(map, p.x, p.y, p.z, limit, active, wnn[threadIdx.x >> 5]);
-    if (!active) return;
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = q[i];
+    const NNHit h = nn_query(map, p.x, p.y, p.z, limit);
     idx[i] = h.idx;
     d2[i] = h.idx >= 0 ? h.d2 : FLT_MAX;
 }
@@ -634,7 +684,8 @@ int nn_search_device(const MapView &map, const float4 *queries, size_t n, float 
                      cudaStream_t st)
 {
     if (n == 0) return SSF_OK;
-    nn_only_kernel<<<(unsigned)((n + kTile - 1) / kTile), kTile, 0, st>>>(map, queries, (uint32_t)n, limit, idx, d2);
+    nn_only_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, st>>>(map, queries, (uint32_t)n, limit, idx,
+                                                                                  d2);
     SSF_LAUNCHED();
     g_queries.fetch_add(n, std::memory_order_relaxed);
     return SSF_OK;
@@ -703,10 +754,10 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
         }
         for (int i = 0; i < cfg.num_iterations; ++i) {
             if (cfg.mode == SSF_MODE_GN_P2PLANE)
-                TIMED_SEARCH((search_accum_kernel<ACC_GN_P2PLANE><<<tiles, kTile, 0, st>>>(
+                TIMED_SEARCH((search_accum_kernel<ACC_GN_P2PLANE><<<tiles, kThreads, 0, st>>>(
                     map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p)));
             else
-                TIMED_SEARCH((search_accum_kernel<ACC_GN_P2P><<<tiles, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, S,
+                TIMED_SEARCH((search_accum_kernel<ACC_GN_P2P><<<tiles, kThreads, 0, st>>>(map, b.src.p, b.tile_scan.p, S,
                                                                                       limit, b.corr.p, b.partials.p)));
             g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
             SSF_TRY(reduce_sums(cfg, b, st));
@@ -715,7 +766,7 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
         }
     } else if (cfg.mode == SSF_MODE_O3D_P2P) {
         for (int i = 0; i <= cfg.num_iterations; ++i) {
-            TIMED_SEARCH((search_accum_kernel<ACC_KABSCH><<<tiles, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, S, limit,
+            TIMED_SEARCH((search_accum_kernel<ACC_KABSCH><<<tiles, kThreads, 0, st>>>(map, b.src.p, b.tile_scan.p, S, limit,
                                                                                   b.corr.p, b.partials.p)));
             g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
             SSF_TRY(reduce_sums(cfg, b, st));

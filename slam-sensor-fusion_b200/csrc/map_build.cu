@@ -1,25 +1,30 @@
-// map_build.cu -- K1: GPU voxel-hash build of the target map.
+// map_build.cu -- K1: GPU voxel-grid build of the target map.
 //
 // Replaces kdtree_.setInputCloud(target_cloud) at reference
 // localization/src/icp_point_to_point.cpp:54 (a FLANN KD-tree build on the CPU).
 //
-//   bbox -> cell key per point -> stable radix sort (key, original index) -> gather the
+//   bbox -> directory key per point -> stable radix sort (key, original index) -> gather the
 //   cloud into key order (float4, w = original index) -> unique cells + start offsets ->
-//   open-addressing hash of every cell that is occupied or x-adjacent to an occupied cell,
-//   value = offsets of the three cells {cx-1, cx, cx+1} (contiguous in the sorted cloud).
+//   directory fill (occupancy mask + first cell id per 32-cell block of a row).
 //
-// One-time cost per map (or per re-crop); algorithmic bytes 2*16*M + 8*n_cells.
+// The cell edge is chosen from the data: a first pass at a volumetric guess measures the
+// points per occupied cell, and the edge is shrunk (surface-like clouds) until a cell holds a
+// few points, within a memory budget for the dense directory.  The rejection threshold does
+// not enter: the search (nn_device.cuh) is exact for any radius at any cell edge.
+//
+// One-time cost per map (or per re-crop); algorithmic bytes 2*16*M + 8*n_dir per pass.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "map_index.cuh"
 
 namespace ssf {
 
-__global__ void __launch_bounds__(256) map_keys_kernel(const float4 *__restrict__ raw, uint32_t n, float ox, float oy,
-                                                       float oz, float inv_h, int nx, int ny, int nz,
-                                                       unsigned long long sentinel,
-                                                       unsigned long long *__restrict__ keys,
-                                                       uint32_t *__restrict__ vals)
+__global__ void __launch_bounds__(256)
+    map_keys_kernel(const float4 *__restrict__ raw, uint32_t n, float ox, float oy, float oz, float inv_h, int nx, int ny,
+                    int nz, int nbx, int nty, unsigned long long sentinel, unsigned long long *__restrict__ keys,
+                    uint32_t *__restrict__ vals)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -30,16 +35,24 @@ __global__ void __launch_bounds__(256) map_keys_kernel(const float4 *__restrict_
         cx = min(max(cx, 0), nx - 1);
         cy = min(max(cy, 0), ny - 1);
         cz = min(max(cz, 0), nz - 1);
-        k = cell_key(cx, cy, cz, nx);
+        k = ((unsigned long long)dir_index(nbx, nty, cx >> 5, cy, cz) << 5) | (unsigned long long)(cx & 31);
     }
     keys[i] = k;
     vals[i] = i;
 }
 
 __global__ void __launch_bounds__(256)
+    map_flags_kernel(const unsigned long long *__restrict__ keys, uint32_t n_finite, uint32_t *__restrict__ flags)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_finite) return;
+    flags[j] = (j == 0 || keys[j] != keys[j - 1]) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
     map_gather_kernel(const float4 *__restrict__ raw, const float4 *__restrict__ raw_nrm,
-                      const int32_t *__restrict__ global_index, const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t n_finite,
-                      float4 *__restrict__ pts, float4 *__restrict__ nrm, uint32_t *__restrict__ flags)
+                      const int32_t *__restrict__ global_index, const uint32_t *__restrict__ vals, uint32_t n_finite,
+                      float4 *__restrict__ pts, float4 *__restrict__ nrm)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_finite) return;
@@ -48,100 +61,26 @@ __global__ void __launch_bounds__(256)
     p.w = __int_as_float(global_index ? global_index[src] : (int)src);
     pts[j] = p;
     if (raw_nrm) nrm[j] = raw_nrm[src];
-    flags[j] = (j == 0 || keys[j] != keys[j - 1]) ? 1u : 0u;
 }
 
-// cell_id[j] = exclusive scan of flags (+flag - 1 = id of the cell point j belongs to)
+// cell c (= exclusive scan of the flags at its first point) starts at point j; the first cell of
+// a directory block records its id there, every cell sets its bit in the block's mask
 __global__ void __launch_bounds__(256)
     map_cells_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ flags,
-                     const uint32_t *__restrict__ scan, uint32_t n_finite, unsigned long long *__restrict__ cell_keys,
-                     uint32_t *__restrict__ cell_start, uint32_t n_cells)
+                     const uint32_t *__restrict__ scan, uint32_t n_finite, uint32_t *__restrict__ cell_start,
+                     uint32_t n_cells, uint2 *__restrict__ dir)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j == 0) cell_start[n_cells] = n_finite;
     if (j >= n_finite) return;
     if (flags[j]) {
         const uint32_t c = scan[j];
-        cell_keys[c] = keys[j];
         cell_start[c] = j;
+        const unsigned long long k = keys[j];
+        const uint32_t e = (uint32_t)(k >> 5);
+        atomicOr(&dir[e].x, 1u << (uint32_t)(k & 31));
+        if (j == 0 || (keys[j - 1] >> 5) != (k >> 5)) dir[e].y = c;
     }
-}
-
-// entries contributed by occupied cell c: itself, its left neighbour unless an earlier cell
-// already covers it, its right neighbour unless that cell is occupied
-__device__ __forceinline__ void cell_entries(const unsigned long long *cell_keys, uint32_t n_cells, uint32_t c,
-                                             bool &left, bool &right)
-{
-    const unsigned long long k = cell_keys[c];
-    left = (c == 0) || (cell_keys[c - 1] + 2 < k);
-    right = (c + 1 == n_cells) || (cell_keys[c + 1] > k + 1);
-}
-
-__global__ void __launch_bounds__(256)
-    map_count_entries_kernel(const unsigned long long *__restrict__ cell_keys, uint32_t n_cells, uint32_t *n_entries)
-{
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t cnt = 0;
-    if (c < n_cells) {
-        bool l, r;
-        cell_entries(cell_keys, n_cells, c, l, r);
-        cnt = 1u + (l ? 1u : 0u) + (r ? 1u : 0u);
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_entries, cnt);
-}
-
-__device__ __forceinline__ void hash_insert(unsigned long long *hkeys, uint32_t hmask, unsigned long long k)
-{
-    uint32_t slot = hash_key(k) & hmask;
-    while (true) {
-        unsigned long long old = atomicCAS(&hkeys[slot], kEmptyKey, k);
-        if (old == kEmptyKey || old == k) return;
-        slot = (slot + 1) & hmask;
-    }
-}
-
-__global__ void __launch_bounds__(256) map_insert_kernel(const unsigned long long *__restrict__ cell_keys,
-                                                         uint32_t n_cells, unsigned long long *hkeys, uint32_t hmask)
-{
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_cells) return;
-    bool l, r;
-    cell_entries(cell_keys, n_cells, c, l, r);
-    const unsigned long long k = cell_keys[c];
-    hash_insert(hkeys, hmask, k);
-    if (l) hash_insert(hkeys, hmask, k - 1);
-    if (r) hash_insert(hkeys, hmask, k + 1);
-}
-
-__global__ void __launch_bounds__(256)
-    map_fill_kernel(const unsigned long long *__restrict__ hkeys, uint4 *__restrict__ hvals, uint32_t table_size,
-                    const unsigned long long *__restrict__ cell_keys, const uint32_t *__restrict__ cell_start,
-                    uint32_t n_cells)
-{
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= table_size) return;
-    const unsigned long long k = hkeys[s];
-    if (k == kEmptyKey) return;
-    // first cell with key >= k - 1
-    uint32_t lo = 0, hi = n_cells;
-    const unsigned long long want = k ? k - 1 : 0;  // key 0 has no left neighbour
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (cell_keys[mid] < want) lo = mid + 1;
-        else hi = mid;
-    }
-    uint32_t c = lo;
-    uint4 v;
-    v.x = cell_start[c];
-    if (c < n_cells && cell_keys[c] == k - 1) ++c;
-    v.y = cell_start[c];
-    if (c < n_cells && cell_keys[c] == k) ++c;
-    v.z = cell_start[c];
-    if (c < n_cells && cell_keys[c] == k + 1) ++c;
-    v.w = cell_start[c];
-    hvals[s] = v;
 }
 
 static int bit_width_u64(unsigned long long v)
@@ -151,6 +90,44 @@ static int bit_width_u64(unsigned long long v)
     return b;
 }
 
+struct GridDims {
+    int nx, ny, nz, nbx, nty, ntz;
+    unsigned long long n_dir;
+};
+
+// same float expressions as cell_coord() on the device (no FMA possible: sub then mul)
+static bool grid_dims(const float *bb, const float *org, float cell, GridDims &g)
+{
+    const float inv_h = 1.0f / cell;
+    const float ux = (bb[3] - org[0]) * inv_h, uy = (bb[4] - org[1]) * inv_h, uz = (bb[5] - org[2]) * inv_h;
+    if (!(ux < 1048000.f) || !(uy < 1048000.f) || !(uz < 1048000.f)) return false;
+    g.nx = (int)floorf(ux) + 1; g.ny = (int)floorf(uy) + 1; g.nz = (int)floorf(uz) + 1;
+    g.nbx = (g.nx + 31) / 32; g.nty = (g.ny + 3) / 4; g.ntz = (g.nz + 3) / 4;
+    g.n_dir = (unsigned long long)g.ntz * g.nty * g.nbx * 16ull;
+    return true;
+}
+
+// keys -> sort -> flags -> scan; leaves the sorted (key, original index) pairs in m.keys/m.vals
+static int index_pass(MapIndex &m, const GridDims &g, float cell, const float *org, uint32_t n_finite, Scratch &s,
+                      cudaStream_t st, uint32_t *cnt_dev, uint32_t *n_cells_out)
+{
+    const size_t n = m.n_raw;
+    const unsigned long long sentinel = g.n_dir << 5;
+    const int key_bits = bit_width_u64(sentinel);
+    const unsigned blocks_n = (unsigned)((n + 255) / 256);
+    map_keys_kernel<<<blocks_n, 256, 0, st>>>(m.raw.p, (uint32_t)n, org[0], org[1], org[2], 1.0f / cell, g.nx, g.ny, g.nz,
+                                              g.nbx, g.nty, sentinel, m.keys.p, m.vals.p);
+    SSF_LAUNCHED();
+    SSF_TRY(radix_sort_pairs_u64(m.keys.p, m.vals.p, n, key_bits, s, st));
+    const unsigned blocks_f = (n_finite + 255) / 256;
+    map_flags_kernel<<<blocks_f, 256, 0, st>>>(m.keys.p, n_finite, m.flags.p);
+    SSF_LAUNCHED();
+    SSF_TRY(exclusive_scan_u32(m.flags.p, m.cell_id.p, n_finite, cnt_dev + 1, s, st));
+    SSF_CUDA(cudaMemcpyAsync(n_cells_out, cnt_dev + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SSF_CUDA(cudaStreamSynchronize(st));
+    return SSF_OK;
+}
+
 int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
 {
     const size_t n = m.n_raw;
@@ -158,16 +135,17 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
         set_error("target cloud too large for 31-bit indices (%zu)", n);
         return SSF_ERR_INVALID;
     }
-    if (!(cell_size > 0.f) || !std::isfinite(cell_size)) {
+    if (cell_size != cell_size || std::isinf(cell_size)) {
         set_error("invalid cell size %g", cell_size);
         return SSF_ERR_INVALID;
     }
     m.view = MapView{};
-    m.cell_size = cell_size;
-    m.n_cells = m.n_entries = m.table_size = 0;
+    m.cell_size = 0.f;
+    m.n_cells = m.n_dir = 0;
+    m.build_passes = 0;
     SSF_TRY(m.small.reserve(16));
     float *bbox_dev = m.small.p;
-    uint32_t *cnt_dev = reinterpret_cast<uint32_t *>(m.small.p + 8);  // [0] n_finite, [1] n_cells, [2] n_entries
+    uint32_t *cnt_dev = reinterpret_cast<uint32_t *>(m.small.p + 8);  // [0] n_finite, [1] n_cells
     SSF_TRY(bbox_finite(m.raw.p, n, bbox_dev, cnt_dev, st));
     float hb[6];
     uint32_t n_finite = 0;
@@ -180,90 +158,108 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
     v.n_pts = n_finite;
     v.own_lo = m.own_lo;
     v.own_hi = m.own_hi;
-    v.inv_h = 1.0f / cell_size;
-    if (n_finite == 0) {  // empty map: every search misses
+    v.shard_ox = m.sharded ? m.shard_origin[0] : 0.f;
+    v.shard_inv_h = m.sharded ? 1.0f / m.shard_cell : 1.f;
+    if (n_finite == 0) {  // empty map: every search misses (nn_query returns before touching the index)
         v.ox = v.oy = v.oz = 0.f;
+        v.inv_h = 1.f;
+        v.hq = 0.999999f;
         v.nx = v.ny = v.nz = 1;
-        SSF_TRY(m.hkeys.reserve(2));
-        SSF_TRY(m.hvals.reserve(2));
+        v.nbx = v.nty = 1;
+        SSF_TRY(m.dir.reserve(16));
+        SSF_TRY(m.cell_start.reserve(1));
         SSF_TRY(m.pts.reserve(1));
-        SSF_CUDA(cudaMemsetAsync(m.hkeys.p, 0xFF, 2 * sizeof(unsigned long long), st));
-        v.hkeys = m.hkeys.p; v.hvals = m.hvals.p; v.hmask = 1; v.pts = m.pts.p; v.nrm = nullptr;
-        m.table_size = 2;
+        SSF_CUDA(cudaMemsetAsync(m.dir.p, 0, 16 * sizeof(uint2), st));
+        v.dir = m.dir.p; v.cell_start = m.cell_start.p; v.pts = m.pts.p; v.nrm = nullptr;
+        m.n_dir = 16;
+        m.cell_size = 1.f;
         m.view = v;
         return SSF_OK;
     }
-    v.ox = hb[0]; v.oy = hb[1]; v.oz = hb[2];
-    if (m.sharded) {  // global grid: every rank uses the same origin so cell columns agree
-        if (m.shard_origin[0] > hb[0] || m.shard_origin[1] > hb[1] || m.shard_origin[2] > hb[2]) {
-            set_error("shard origin must not exceed the shard's own minimum");
-            return SSF_ERR_INVALID;
+    const float org[3] = {hb[0], hb[1], hb[2]};
+    const float ext[3] = {hb[3] - hb[0], hb[4] - hb[1], hb[5] - hb[2]};
+    const float ext_max = std::max(ext[0], std::max(ext[1], ext[2]));
+    // directory budget: at most 64 bytes of directory per point (>= 8 MB), and < 2 GB
+    const unsigned long long budget =
+        std::min<unsigned long long>(1ull << 28, std::max<unsigned long long>(1ull << 20, 8ull * n_finite));
+    // smallest usable edge: keeps every cell coordinate below 2^20 (float cell arithmetic) and
+    // the edge itself far from the float spacing of the coordinates
+    const float abs_max = std::max(std::max(fabsf(hb[0]), fabsf(hb[3])),
+                                   std::max(std::max(fabsf(hb[1]), fabsf(hb[4])), std::max(fabsf(hb[2]), fabsf(hb[5]))));
+    const float h_floor = std::max(std::max(ext_max / 1.0e6f, abs_max * 1.0e-5f), 1.0e-30f);
+    auto fit = [&](float h, GridDims &g) -> float {  // grow h until the grid is addressable and within budget
+        if (!(h > h_floor)) h = h_floor;
+        for (int it = 0; it < 400; ++it) {
+            if (grid_dims(hb, org, h, g) && g.n_dir <= budget) return h;
+            h *= 1.1f;
         }
-        v.ox = m.shard_origin[0]; v.oy = m.shard_origin[1]; v.oz = m.shard_origin[2];
-    }
-    // same float expression as cell_coord() on the device (no FMA possible: sub then mul)
-    const float ux = (hb[3] - v.ox) * v.inv_h, uy = (hb[4] - v.oy) * v.inv_h, uz = (hb[5] - v.oz) * v.inv_h;
-    if (!(ux < 1.0e6f) || !(uy < 65000.f) || !(uz < 65000.f)) {
-        set_error("map extent (%g x %g x %g cells of %g m) exceeds the voxel-hash key space", ux, uy, uz, cell_size);
-        return SSF_ERR_INVALID;
-    }
-    v.nx = (int)floorf(ux) + 1; v.ny = (int)floorf(uy) + 1; v.nz = (int)floorf(uz) + 1;
-    const int yz_bits = bit_width_u64((unsigned long long)((v.ny > v.nz ? v.ny : v.nz) - 1));
-    const unsigned long long sentinel = ((unsigned long long)1 << (2 * yz_bits)) * (unsigned long long)(v.nx + 2);
-    const int key_bits = bit_width_u64(sentinel);
+        return -1.f;
+    };
 
     SSF_TRY(m.keys.reserve(n));
     SSF_TRY(m.vals.reserve(n));
-    const unsigned blocks_n = (unsigned)((n + 255) / 256);
-    map_keys_kernel<<<blocks_n, 256, 0, st>>>(m.raw.p, (uint32_t)n, v.ox, v.oy, v.oz, v.inv_h, v.nx, v.ny, v.nz, sentinel,
-                                              m.keys.p, m.vals.p);
-    SSF_LAUNCHED();
-    SSF_TRY(radix_sort_pairs_u64(m.keys.p, m.vals.p, n, key_bits, s, st));
+    SSF_TRY(m.flags.reserve(n_finite));
+    SSF_TRY(m.cell_id.reserve(n_finite));
+
+    GridDims g{};
+    float h;
+    uint32_t n_cells = 0;
+    const char *env = getenv("SSF_CELL_SIZE");
+    if (env && atof(env) > 0.0) cell_size = (float)atof(env);
+    if (cell_size > 0.f) {
+        h = fit(cell_size, g);
+        if (h < 0.f) { set_error("map extent does not fit the directory at any cell size"); return SSF_ERR_INVALID; }
+        SSF_TRY(index_pass(m, g, h, org, n_finite, s, st, cnt_dev, &n_cells));
+        m.build_passes = 1;
+    } else {
+        // volumetric guess (4 points per cell if the cloud filled its box), then shrink while the
+        // occupied cells are crowded: for a surface-like cloud points/cell scales with h^2
+        const float eps = std::max(ext_max * 1.0e-3f, 1.0e-20f);
+        const double vol = (double)std::max(ext[0], eps) * std::max(ext[1], eps) * std::max(ext[2], eps);
+        h = ext_max > 0.f ? (float)cbrt(4.0 * vol / (double)n_finite) : 1.0f;
+        const float target = getenv("SSF_CELL_POINTS") ? (float)atof(getenv("SSF_CELL_POINTS")) : 3.0f;
+        for (int pass = 0; pass < 4; ++pass) {
+            h = fit(h, g);
+            if (h < 0.f) { set_error("map extent does not fit the directory at any cell size"); return SSF_ERR_INVALID; }
+            SSF_TRY(index_pass(m, g, h, org, n_finite, s, st, cnt_dev, &n_cells));
+            m.build_passes = pass + 1;
+            const float rho = (float)n_finite / (float)(n_cells ? n_cells : 1);
+            if (rho <= 2.0f * target || ext_max == 0.f) break;
+            float h_new = h * sqrtf(target / rho);
+            if (h_new < h / 16.f) h_new = h / 16.f;
+            GridDims g2{};
+            h_new = fit(h_new, g2);
+            if (h_new < 0.f || h_new > 0.9f * h) break;
+            h = h_new;
+        }
+    }
+    v.ox = org[0]; v.oy = org[1]; v.oz = org[2];
+    v.inv_h = 1.0f / h;
+    v.hq = nextafterf((1.0f / v.inv_h) * 0.999999f, 0.f);
+    v.nx = g.nx; v.ny = g.ny; v.nz = g.nz;
+    v.nbx = g.nbx; v.nty = g.nty;
 
     SSF_TRY(m.pts.reserve(n_finite));
     if (m.has_normals) SSF_TRY(m.nrm.reserve(n_finite));
-    SSF_TRY(m.flags.reserve(n_finite));
-    SSF_TRY(m.cell_id.reserve(n_finite));
+    SSF_TRY(m.cell_start.reserve((size_t)n_cells + 1));
+    SSF_TRY(m.dir.reserve((size_t)g.n_dir));
+    SSF_CUDA(cudaMemsetAsync(m.dir.p, 0, (size_t)g.n_dir * sizeof(uint2), st));
     const unsigned blocks_f = (n_finite + 255) / 256;
     map_gather_kernel<<<blocks_f, 256, 0, st>>>(m.raw.p, m.has_normals ? m.raw_nrm.p : nullptr,
-                                                m.has_global_index ? m.global_index.p : nullptr, m.keys.p, m.vals.p,
-                                                n_finite, m.pts.p, m.has_normals ? m.nrm.p : nullptr, m.flags.p);
+                                                m.has_global_index ? m.global_index.p : nullptr, m.vals.p, n_finite,
+                                                m.pts.p, m.has_normals ? m.nrm.p : nullptr);
     SSF_LAUNCHED();
-    SSF_TRY(exclusive_scan_u32(m.flags.p, m.cell_id.p, n_finite, cnt_dev + 1, s, st));
-    uint32_t n_cells = 0;
-    SSF_CUDA(cudaMemcpyAsync(&n_cells, cnt_dev + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    SSF_CUDA(cudaStreamSynchronize(st));
-    SSF_TRY(m.cell_keys.reserve(n_cells));
-    SSF_TRY(m.cell_start.reserve((size_t)n_cells + 1));
-    map_cells_kernel<<<blocks_f, 256, 0, st>>>(m.keys.p, m.flags.p, m.cell_id.p, n_finite, m.cell_keys.p, m.cell_start.p,
-                                               n_cells);
-    SSF_LAUNCHED();
-    SSF_CUDA(cudaMemsetAsync(cnt_dev + 2, 0, sizeof(uint32_t), st));
-    const unsigned blocks_c = (n_cells + 255) / 256;
-    map_count_entries_kernel<<<blocks_c, 256, 0, st>>>(m.cell_keys.p, n_cells, cnt_dev + 2);
-    SSF_LAUNCHED();
-    uint32_t n_entries = 0;
-    SSF_CUDA(cudaMemcpyAsync(&n_entries, cnt_dev + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    SSF_CUDA(cudaStreamSynchronize(st));
-    uint32_t table = 2;
-    while (table < 2u * n_entries && table < (1u << 31)) table <<= 1;
-    SSF_TRY(m.hkeys.reserve(table));
-    SSF_TRY(m.hvals.reserve(table));
-    SSF_CUDA(cudaMemsetAsync(m.hkeys.p, 0xFF, (size_t)table * sizeof(unsigned long long), st));
-    map_insert_kernel<<<blocks_c, 256, 0, st>>>(m.cell_keys.p, n_cells, m.hkeys.p, table - 1);
-    SSF_LAUNCHED();
-    map_fill_kernel<<<(table + 255) / 256, 256, 0, st>>>(m.hkeys.p, m.hvals.p, table, m.cell_keys.p, m.cell_start.p,
-                                                        n_cells);
+    map_cells_kernel<<<blocks_f, 256, 0, st>>>(m.keys.p, m.flags.p, m.cell_id.p, n_finite, m.cell_start.p, n_cells,
+                                               m.dir.p);
     SSF_LAUNCHED();
     v.pts = m.pts.p;
     v.nrm = m.has_normals ? m.nrm.p : nullptr;
-    v.hkeys = m.hkeys.p;
-    v.hvals = m.hvals.p;
-    v.hmask = table - 1;
+    v.dir = m.dir.p;
+    v.cell_start = m.cell_start.p;
     m.view = v;
     m.n_cells = n_cells;
-    m.n_entries = n_entries;
-    m.table_size = table;
+    m.n_dir = (uint32_t)g.n_dir;
+    m.cell_size = h;
     return SSF_OK;
 }
 

@@ -1,4 +1,4 @@
-// map_index.cuh -- owner of the HBM-resident voxel-hash map (see MapView in common.cuh).
+// map_index.cuh -- owner of the HBM-resident voxel-grid map (see MapView in common.cuh).
 #pragma once
 #include <climits>
 
@@ -7,33 +7,35 @@
 namespace ssf {
 
 struct MapIndex {
-    DevBuf<float4> raw;      // target cloud in ORIGINAL order (w unused); kept for re-indexing
+    DevBuf<float4> raw;      // target cloud in ORIGINAL order (w unused)
     DevBuf<float4> raw_nrm;  // normals in original order (optional)
     DevBuf<int32_t> global_index;  // map sharding: global index of every raw point (optional)
     bool has_global_index = false;
-    bool sharded = false;          // origin / ownership given by the caller (ssf_shard_info)
+    bool sharded = false;          // ownership columns given by the caller (ssf_shard_info)
     float shard_origin[3] = {0, 0, 0};
+    float shard_cell = 0.f;
     int own_lo = INT32_MIN, own_hi = INT32_MAX;
-    DevBuf<float4> pts;      // sorted by cell key, w = original index
+    DevBuf<float4> pts;      // sorted by directory key, w = original index
     DevBuf<float4> nrm;      // sorted normals
     DevBuf<unsigned long long> keys;
     DevBuf<uint32_t> vals;
     DevBuf<uint32_t> flags;
     DevBuf<uint32_t> cell_id;
-    DevBuf<unsigned long long> cell_keys;
     DevBuf<uint32_t> cell_start;
-    DevBuf<unsigned long long> hkeys;
-    DevBuf<uint4> hvals;
+    DevBuf<uint2> dir;
     DevBuf<float> small;  // bbox (6 floats) + counters
     MapView view{};
     size_t n_raw = 0;       // points given to set_target
     bool has_normals = false;
     float cell_size = 0.f;
-    uint32_t n_cells = 0, n_entries = 0, table_size = 0;
+    uint32_t n_cells = 0, n_dir = 0;
+    int build_passes = 0;   // sort passes the cell-size search needed
     float bbox[6] = {0, 0, 0, 0, 0, 0};
 };
 
 // raw (and raw_nrm when has_normals) must already hold n_raw points on the device.
+// cell_size > 0 fixes the cell edge; cell_size <= 0 picks it from the measured occupancy
+// (target: a few points per occupied cell).
 int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st);
 
 }  // namespace ssf
