@@ -125,6 +125,8 @@ struct MapView {
     float hq;        // (1 / inv_h) * (1 - 1e-6), rounded down: under-estimate of the cell edge
     int nx, ny, nz;  // grid extent in cells
     int nbx, nty;    // directory: x blocks per row, 4x4 tiles along y
+    float bmin[3], bmax[3];  // bounding box of the finite points
+    float cert_mu;           // margin of the search certificates (nn_device.cuh), a fraction of the cell edge
     // map sharding: this rank owns the queries whose shard column
     // floor((x - shard_ox) * shard_inv_h) lies in [own_lo, own_hi)
     float shard_ox, shard_inv_h;

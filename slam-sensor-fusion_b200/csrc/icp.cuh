@@ -33,7 +33,11 @@ struct BatchBuffers {
     DevBuf<float4> P;          // REFERENCE: transformed source, advanced in place
     DevBuf<float4> Q;          // REFERENCE: matched target point per row
     DevBuf<int32_t> corr;      // correspondence (original target index) or -1
+    DevBuf<float4> cert_p;     // search certificates: query position + radius (nn_device.cuh)
+    DevBuf<uint32_t> cert_pos; // ... and the neighbour's position in the sorted map
     DevBuf<uint32_t> tile_scan;
+    DevBuf<uint32_t> active;     // tiles that hold points (search kernel work list)
+    DevBuf<uint32_t> counters;   // [0] number of active tiles, [1 + i] tile fetch counter of search launch i
     DevBuf<double> partials;   // [tile][kAccum]
     DevBuf<double> sums;       // [scan][kAccum]: per-scan totals (all-reduced across ranks when sharded)
     DevBuf<ScanState> state;

@@ -142,123 +142,201 @@ __device__ __forceinline__ void tile_bar_wait(unsigned long long *bar, uint32_t 
     }
 }
 
-constexpr uint32_t kNoPos = 0xFFFFFFFFu;
+// list of the tiles that hold points (a scan's slots are sized for its RAW points; after the voxel
+// stage only the first ceil(n_pts / kTile) tiles of each scan are in use)
+__global__ void __launch_bounds__(128)
+    active_tiles_kernel(const ScanState *__restrict__ states, uint32_t n_scans, uint32_t *__restrict__ active,
+                        uint32_t *__restrict__ n_active)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scans) return;
+    const ScanState &z = states[s];
+    const uint32_t n = (z.n_pts + kTile - 1) / kTile;
+    if (n == 0) return;
+    const uint32_t base = atomicAdd(n_active, n);
+    for (uint32_t k = 0; k < n; ++k) active[base + k] = z.tile_begin + k;
+}
 
-// A block owns one tile of kTile consecutive queries of one scan; every thread takes kQ of them
-// (rows t, t + kThreads, ...), first searching all of them, then accumulating their terms, so the
-// 32-value warp reduction is paid once per kQ queries.
+// Persistent blocks fetch tiles (kTile consecutive queries of one scan) from a shared counter;
+// every thread takes kQ queries of a tile.
+//   V  transform; with use_cert, try to confirm last iteration's neighbour from its certificate
+//      (nn_verify) -- a handful of flops and one gather instead of a search;
+//   S  the queries that could not be confirmed, packed densely over the threads: full exact walk,
+//      new certificate;
+//   K4 residual / Jacobian terms of the matched queries, 32-value warp reduction paid once per kQ.
 template <int KIND>
 __global__ void __launch_bounds__(kThreads)
     search_accum_kernel(MapView map, const float4 *__restrict__ src, const uint32_t *__restrict__ tile_scan,
                         const ScanState *__restrict__ states, float limit, int32_t *__restrict__ corr,
-                        double *__restrict__ partials)
+                        double *__restrict__ partials, float4 *__restrict__ cert_p, uint32_t *__restrict__ cert_pos,
+                        int use_cert, const uint32_t *__restrict__ active, const uint32_t *__restrict__ n_active,
+                        uint32_t *__restrict__ fetch)
 {
-    __shared__ __align__(128) float4 s_src[kTile];
+    __shared__ __align__(128) float4 s_q[kTile];  // TMA destination; transformed in place, w = owned by this rank
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_pos[kTile];
+    __shared__ unsigned short s_queue[kTile];
+    __shared__ uint32_t s_nq, s_next;
     __shared__ float sT[16];
     __shared__ double sred[kThreads / 32][kAccum];
-    const uint32_t scan = tile_scan[blockIdx.x];
-    const ScanState &z = states[scan];
-    if (z.done) return;
-    const uint32_t row0 = (blockIdx.x - z.tile_begin) * kTile;
-    if (row0 >= z.n_pts) return;
-    const uint32_t n_here = min((uint32_t)kTile, z.n_pts - row0);
-    const size_t slot0 = (size_t)z.pt_begin + row0;
+    const uint32_t none_hi = __float_as_uint(limit);
+    const bool searchable = limit > 0.f && map.n_pts > 0;
+    const uint32_t n_tiles = *n_active;
     if (threadIdx.x == 0) tile_bar_init(&s_bar);
-    if (threadIdx.x < 16) sT[threadIdx.x] = z.T[threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x == 0) tile_load_issue(s_src, &s_bar, src + slot0, n_here * (uint32_t)sizeof(float4));
-    tile_bar_wait(&s_bar, 0);
-    // ---- K3: transform + exact NN + rejection ----
-    for (int k = 0; k < kQ; ++k) {
-        const uint32_t r = (uint32_t)k * kThreads + threadIdx.x;
-        if (r >= n_here) break;
-        const float4 s4 = s_src[r];
-        const float3 p = transform_point(sT, s4.x, s4.y, s4.z);
-        // map sharding: only the rank that owns the query's column searches it, so every
-        // correspondence is counted exactly once across ranks (the halo covers the radius)
-        const int col = cell_coord(p.x, map.shard_ox, map.shard_inv_h, 1 << 24);
-        const bool mine = col >= map.own_lo && col < map.own_hi;
-        int idx = -2;
-        uint32_t pos = kNoPos;
-        if (mine) {
-            const NNHit h = nn_query(map, p.x, p.y, p.z, limit);
-            idx = h.idx;
-            if (h.idx >= 0) pos = h.pos;
+    uint32_t phase = 0;
+    while (true) {
+        if (threadIdx.x == 0) {
+            s_next = atomicAdd(fetch, 1u);
+            s_nq = 0;
         }
-        corr[slot0 + r] = idx;
-        s_pos[r] = pos;  // read back by this thread only
-    }
-    // ---- K4: residual / Jacobian terms of the matched queries ----
-    double v[kAccum];
+        __syncthreads();
+        const uint32_t ti = s_next;
+        if (ti >= n_tiles) break;
+        const uint32_t tile = active[ti];
+        const uint32_t scan = tile_scan[tile];
+        const ScanState &z = states[scan];
+        const uint32_t row0 = (tile - z.tile_begin) * kTile;
+        if (z.done || row0 >= z.n_pts) {
+            __syncthreads();  // s_next is rewritten at the top
+            continue;
+        }
+        const uint32_t n_here = min((uint32_t)kTile, z.n_pts - row0);
+        const size_t slot0 = (size_t)z.pt_begin + row0;
+        if (threadIdx.x == 0) tile_load_issue(s_q, &s_bar, src + slot0, n_here * (uint32_t)sizeof(float4));
+        if (threadIdx.x < 16) sT[threadIdx.x] = z.T[threadIdx.x];
+        // certificates of this thread's queries: issue the loads before waiting for the tile
+        float4 cp4[kQ];
+        uint32_t cpos[kQ];
 #pragma unroll
-    for (int i = 0; i < kAccum; ++i) v[i] = 0.0;
-    for (int k = 0; k < kQ; ++k) {
-        const uint32_t r = (uint32_t)k * kThreads + threadIdx.x;
-        if (r >= n_here) break;
-        const uint32_t pos = s_pos[r];
-        if (pos == kNoPos) continue;
-        const float4 s4 = s_src[r];
-        const float3 p = transform_point(sT, s4.x, s4.y, s4.z);
-        const float4 q = __ldg(&map.pts[pos]);
-        if (KIND == ACC_KABSCH) {
-            const double cx = z.T_init[12], cy = z.T_init[13], cz = z.T_init[14];
-            const double a[3] = {(double)p.x - cx, (double)p.y - cy, (double)p.z - cz};
-            const double b[3] = {(double)q.x - cx, (double)q.y - cy, (double)q.z - cz};
-            v[0] += 1.0;
-#pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                v[1 + t] += a[t];
-                v[4 + t] += b[t];
+        for (int k = 0; k < kQ; ++k) {
+            const uint32_t r = (uint32_t)k * kThreads + threadIdx.x;
+            cp4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cpos[k] = kNoPos;
+            if (use_cert && r < n_here) {
+                cp4[k] = cert_p[slot0 + r];
+                cpos[k] = cert_pos[slot0 + r];
             }
+        }
+        __syncthreads();
+        tile_bar_wait(&s_bar, phase);
+        phase ^= 1u;
+        // ---- V ----
 #pragma unroll
-            for (int rr = 0; rr < 3; ++rr)
+        for (int k = 0; k < kQ; ++k) {
+            const uint32_t r = (uint32_t)k * kThreads + threadIdx.x;
+            if (r >= n_here) continue;
+            const float4 s4 = s_q[r];
+            const float3 p = transform_point(sT, s4.x, s4.y, s4.z);
+            // map sharding: only the rank that owns the query's column searches it, so every
+            // correspondence is counted exactly once across ranks (the halo covers the radius)
+            const int col = cell_coord(p.x, map.shard_ox, map.shard_inv_h, 1 << 24);
+            const bool mine = col >= map.own_lo && col < map.own_hi;
+            const bool ok = searchable && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+            s_q[r] = make_float4(p.x, p.y, p.z, mine ? 1.f : 0.f);
+            s_pos[r] = kNoPos;
+            if (!mine || !ok) {
+                corr[slot0 + r] = mine ? -1 : -2;
+                if (!use_cert || mine) cert_p[slot0 + r] = make_float4(0.f, 0.f, 0.f, 0.f);  // no certificate
+                continue;
+            }
+            unsigned long long key;
+            if (use_cert && nn_verify(map, cp4[k], cpos[k], p.x, p.y, p.z, limit, key)) {
+                const bool hit = (uint32_t)(key >> 32) < none_hi;
+                corr[slot0 + r] = hit ? (int)(uint32_t)key : -1;
+                if (hit) s_pos[r] = cpos[k];
+                continue;
+            }
+            s_queue[atomicAdd(&s_nq, 1u)] = (unsigned short)r;
+        }
+        __syncthreads();
+        // ---- S ----
+        const uint32_t nq = s_nq;
+        for (uint32_t i = threadIdx.x; i < nq; i += kThreads) {
+            const uint32_t r = s_queue[i];
+            const float4 p = s_q[r];
+            NNBest<true> B;
+            nn_walk<true>(map, p.x, p.y, p.z, limit, map.cert_mu, B);
+            const bool hit = (uint32_t)(B.key >> 32) < none_hi;
+            corr[slot0 + r] = hit ? (int)(uint32_t)B.key : -1;
+            if (hit) {
+                s_pos[r] = B.pos;
+                NN_STAT(5, 1);
+            }
+            cert_p[slot0 + r] = make_float4(p.x, p.y, p.z, cert_radius(B));
+            cert_pos[slot0 + r] = hit ? B.pos : kNoPos;
+        }
+        __syncthreads();
+        // ---- K4: residual / Jacobian terms of the matched queries ----
+        double v[kAccum];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) v[7 + 3 * rr + c] += a[rr] * b[c];
-            const double ex = (double)p.x - q.x, ey = (double)p.y - q.y, ez = (double)p.z - q.z;
-            v[16] += ex * ex + ey * ey + ez * ez;
-        } else {
-            const double px = p.x, py = p.y, pz = p.z;
-            const double e[3] = {px - (double)q.x, py - (double)q.y, pz - (double)q.z};
-            if (KIND == ACC_GN_P2PLANE) {
-                const float4 nf = __ldg(&map.nrm[pos]);
-                const double n[3] = {nf.x, nf.y, nf.z};
-                const double a[6] = {py * n[2] - pz * n[1], pz * n[0] - px * n[2], px * n[1] - py * n[0],
-                                     n[0], n[1], n[2]};
-                const double rs = n[0] * e[0] + n[1] * e[1] + n[2] * e[2];
-                int t = 0;
+        for (int i = 0; i < kAccum; ++i) v[i] = 0.0;
+        for (int k = 0; k < kQ; ++k) {
+            const uint32_t r = (uint32_t)k * kThreads + threadIdx.x;
+            if (r >= n_here) break;
+            const uint32_t pos = s_pos[r];
+            if (pos == kNoPos) continue;
+            const float4 p = s_q[r];
+            const float4 q = __ldg(&map.pts[pos]);
+            if (KIND == ACC_KABSCH) {
+                const double cx = z.T_init[12], cy = z.T_init[13], cz = z.T_init[14];
+                const double a[3] = {(double)p.x - cx, (double)p.y - cy, (double)p.z - cz};
+                const double b[3] = {(double)q.x - cx, (double)q.y - cy, (double)q.z - cz};
+                v[0] += 1.0;
 #pragma unroll
-                for (int u = 0; u < 6; ++u)
+                for (int t = 0; t < 3; ++t) {
+                    v[1 + t] += a[t];
+                    v[4 + t] += b[t];
+                }
 #pragma unroll
-                    for (int w = u; w < 6; ++w) v[t++] += a[u] * a[w];
+                for (int rr = 0; rr < 3; ++rr)
 #pragma unroll
-                for (int u = 0; u < 6; ++u) v[21 + u] += a[u] * rs;
-                v[27] += rs * rs;
+                    for (int c = 0; c < 3; ++c) v[7 + 3 * rr + c] += a[rr] * b[c];
+                const double ex = (double)p.x - q.x, ey = (double)p.y - q.y, ez = (double)p.z - q.z;
+                v[16] += ex * ex + ey * ey + ez * ez;
             } else {
-                // J = [-[p]x | I]; J^T J = [[ -[p]x^T -[p]x , [p]x ], [ -[p]x , I ]]
-                const double J[3][6] = {{0, pz, -py, 1, 0, 0}, {-pz, 0, px, 0, 1, 0}, {py, -px, 0, 0, 0, 1}};
-                int t = 0;
+                const double px = p.x, py = p.y, pz = p.z;
+                const double e[3] = {px - (double)q.x, py - (double)q.y, pz - (double)q.z};
+                if (KIND == ACC_GN_P2PLANE) {
+                    const float4 nf = __ldg(&map.nrm[pos]);
+                    const double n[3] = {nf.x, nf.y, nf.z};
+                    const double a[6] = {py * n[2] - pz * n[1], pz * n[0] - px * n[2], px * n[1] - py * n[0],
+                                         n[0], n[1], n[2]};
+                    const double rs = n[0] * e[0] + n[1] * e[1] + n[2] * e[2];
+                    int t = 0;
 #pragma unroll
-                for (int u = 0; u < 6; ++u)
+                    for (int u = 0; u < 6; ++u)
 #pragma unroll
-                    for (int w = u; w < 6; ++w) v[t++] += J[0][u] * J[0][w] + J[1][u] * J[1][w] + J[2][u] * J[2][w];
+                        for (int w = u; w < 6; ++w) v[t++] += a[u] * a[w];
 #pragma unroll
-                for (int u = 0; u < 6; ++u) v[21 + u] += J[0][u] * e[0] + J[1][u] * e[1] + J[2][u] * e[2];
-                v[27] += e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+                    for (int u = 0; u < 6; ++u) v[21 + u] += a[u] * rs;
+                    v[27] += rs * rs;
+                } else {
+                    // J = [-[p]x | I]; J^T J = [[ -[p]x^T -[p]x , [p]x ], [ -[p]x , I ]]
+                    const double J[3][6] = {{0, pz, -py, 1, 0, 0}, {-pz, 0, px, 0, 1, 0}, {py, -px, 0, 0, 0, 1}};
+                    int t = 0;
+#pragma unroll
+                    for (int u = 0; u < 6; ++u)
+#pragma unroll
+                        for (int w = u; w < 6; ++w)
+                            v[t++] += J[0][u] * J[0][w] + J[1][u] * J[1][w] + J[2][u] * J[2][w];
+#pragma unroll
+                    for (int u = 0; u < 6; ++u) v[21 + u] += J[0][u] * e[0] + J[1][u] * e[1] + J[2][u] * e[2];
+                    v[27] += e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+                }
+                v[28] += 1.0;
             }
-            v[28] += 1.0;
         }
-    }
-    const double w = warp_transpose_reduce32(v);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    sred[warp][lane] = w;
-    __syncthreads();
-    if (threadIdx.x < kAccum) {
-        double s = 0.0;
+        const double w = warp_transpose_reduce32(v);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        sred[warp][lane] = w;
+        __syncthreads();
+        if (threadIdx.x < kAccum) {
+            double sum = 0.0;
 #pragma unroll
-        for (int k = 0; k < kThreads / 32; ++k) s += sred[k][threadIdx.x];
-        partials[(size_t)blockIdx.x * kAccum + threadIdx.x] = s;
+            for (int k = 0; k < kThreads / 32; ++k) sum += sred[k][threadIdx.x];
+            partials[(size_t)tile * kAccum + threadIdx.x] = sum;
+        }
+        // (the barrier at the top of the loop orders these reads before the next tile's writes)
     }
 }
 
@@ -747,6 +825,24 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
         SSF_LAUNCHED();
         return SSF_OK;
     }
+    unsigned grid = 1;
+    if (cfg.mode != SSF_MODE_REFERENCE) {
+        // persistent search blocks: counters[0] = number of active tiles, counters[1 + i] = fetch
+        // counter of launch i
+        static int n_sm = 0;
+        if (n_sm == 0) {
+            int dev = 0;
+            SSF_CUDA(cudaGetDevice(&dev));
+            SSF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        }
+        grid = (unsigned)n_sm * 8u;
+        if (grid > tiles) grid = tiles;
+        SSF_TRY(b.active.reserve(tiles));
+        SSF_TRY(b.counters.reserve((size_t)cfg.num_iterations + 3));
+        SSF_CUDA(cudaMemsetAsync(b.counters.p, 0, ((size_t)cfg.num_iterations + 3) * sizeof(uint32_t), st));
+        active_tiles_kernel<<<(scans + 127) / 128, 128, 0, st>>>(S, scans, b.active.p, b.counters.p);
+        SSF_LAUNCHED();
+    }
     if (cfg.mode == SSF_MODE_GN_P2P || cfg.mode == SSF_MODE_GN_P2PLANE) {
         if (cfg.mode == SSF_MODE_GN_P2PLANE && !map.nrm) {
             set_error("SSF_MODE_GN_P2PLANE needs target normals (ssf_icp_set_target normals == NULL)");
@@ -754,11 +850,13 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
         }
         for (int i = 0; i < cfg.num_iterations; ++i) {
             if (cfg.mode == SSF_MODE_GN_P2PLANE)
-                TIMED_SEARCH((search_accum_kernel<ACC_GN_P2PLANE><<<tiles, kThreads, 0, st>>>(
-                    map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p)));
+                TIMED_SEARCH((search_accum_kernel<ACC_GN_P2PLANE><<<grid, kThreads, 0, st>>>(
+                    map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p, i > 0,
+                    b.active.p, b.counters.p, b.counters.p + 1 + i)));
             else
-                TIMED_SEARCH((search_accum_kernel<ACC_GN_P2P><<<tiles, kThreads, 0, st>>>(map, b.src.p, b.tile_scan.p, S,
-                                                                                      limit, b.corr.p, b.partials.p)));
+                TIMED_SEARCH((search_accum_kernel<ACC_GN_P2P><<<grid, kThreads, 0, st>>>(
+                    map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p, i > 0,
+                    b.active.p, b.counters.p, b.counters.p + 1 + i)));
             g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
             SSF_TRY(reduce_sums(cfg, b, st));
             solve_gn_kernel<<<scans, 32, 0, st>>>(S, b.sums.p, i, cfg.acc_err, cfg.eps);
@@ -766,8 +864,9 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
         }
     } else if (cfg.mode == SSF_MODE_O3D_P2P) {
         for (int i = 0; i <= cfg.num_iterations; ++i) {
-            TIMED_SEARCH((search_accum_kernel<ACC_KABSCH><<<tiles, kThreads, 0, st>>>(map, b.src.p, b.tile_scan.p, S, limit,
-                                                                                  b.corr.p, b.partials.p)));
+            TIMED_SEARCH((search_accum_kernel<ACC_KABSCH><<<grid, kThreads, 0, st>>>(
+                map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p, i > 0,
+                b.active.p, b.counters.p, b.counters.p + 1 + i)));
             g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
             SSF_TRY(reduce_sums(cfg, b, st));
             solve_o3d_kernel<<<scans, 32, 0, st>>>(S, b.sums.p, i, cfg.num_iterations);

@@ -238,6 +238,8 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
     v.hq = nextafterf((1.0f / v.inv_h) * 0.999999f, 0.f);
     v.nx = g.nx; v.ny = g.ny; v.nz = g.nz;
     v.nbx = g.nbx; v.nty = g.nty;
+    for (int k = 0; k < 3; ++k) { v.bmin[k] = hb[k]; v.bmax[k] = hb[3 + k]; }
+    v.cert_mu = (getenv("SSF_CERT_MU") ? (float)atof(getenv("SSF_CERT_MU")) : 0.1f) * h;
 
     SSF_TRY(m.pts.reserve(n_finite));
     if (m.has_normals) SSF_TRY(m.nrm.reserve(n_finite));

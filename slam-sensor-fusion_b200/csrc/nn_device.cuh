@@ -81,28 +81,58 @@ __device__ __forceinline__ AxisGap axis_gap(float v, float o, float inv_h, float
 // squared gap, shrunk: a lower bound of what the float d2 of any point behind the gap can be
 __device__ __forceinline__ float gap_sq(float g) { return fmaxf(__fsub_rd(__fmul_rd(__fmul_rd(g, g), kShrink), 1e-30f), 0.f); }
 
-__device__ __forceinline__ unsigned long long cand_key(const float4 &q, float px, float py, float pz)
+// ---- running result of one walk ------------------------------------------------------------------
+// key = (d2 bits << 32) | original index of the best candidate so far (or the `none` sentinel).
+// CERT walks additionally keep what a later search needs to be SKIPPED (see nn_verify):
+//   b2   second-smallest d2 among the candidates evaluated (every point is evaluated at most once)
+//   bdm  the pruning bound, (sqrt(best d2) + mu)^2 instead of best d2: rows and cells are only
+//        skipped when they lie farther than the best distance PLUS the margin mu, so at the end
+//        every point that was never looked at is known to be farther than sqrt(d2 best) + mu.
+template <bool CERT>
+struct NNBest {
+    unsigned long long key;
+    uint32_t pos;
+    float b2, bdm, mu;
+    __device__ __forceinline__ float bd() const { return __uint_as_float((uint32_t)(key >> 32)); }
+    // bound to prune with
+    __device__ __forceinline__ float prune() const { return CERT ? bdm : bd(); }
+    __device__ __forceinline__ void refresh()
+    {
+        if (CERT) {  // (s + mu)^2 with s >= sqrt(bd), everything rounded up
+            const float r = __fadd_ru(__fsqrt_ru(bd()), mu);
+            bdm = __fmul_ru(r, r);
+        }
+    }
+};
+
+template <bool CERT>
+__device__ __forceinline__ void cand_update(NNBest<CERT> &B, const float4 &q, uint32_t j, bool valid, float px,
+                                            float py, float pz)
 {
     const float dx = __fsub_rn(px, q.x), dy = __fsub_rn(py, q.y), dz = __fsub_rn(pz, q.z);
     const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-    return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(q.w);
+    const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(q.w);
+    if (CERT) {  // padding slots (valid == false) must not pose as a second point at the same distance
+        const float dv = valid ? d2 : FLT_MAX;
+        B.b2 = fminf(B.b2, fmaxf(dv, B.bd()));
+    }
+    if (k < B.key) { B.key = k; B.pos = j; }
 }
 
 // four candidates of run [j, e) per call; indices past the end re-read the last one (harmless)
+template <bool CERT>
 __device__ __forceinline__ void eval4(const MapView &m, uint32_t j, uint32_t e, float px, float py, float pz,
-                                      unsigned long long &best, uint32_t &pos)
+                                      NNBest<CERT> &B)
 {
     NN_STAT(0, 1);
     SSF_CHECK(j < e && e <= m.n_pts);
     const uint32_t last = e - 1;
     const uint32_t j0 = j, j1 = min(j + 1, last), j2 = min(j + 2, last), j3 = min(j + 3, last);
     const float4 q0 = __ldg(&m.pts[j0]), q1 = __ldg(&m.pts[j1]), q2 = __ldg(&m.pts[j2]), q3 = __ldg(&m.pts[j3]);
-    const unsigned long long k0 = cand_key(q0, px, py, pz), k1 = cand_key(q1, px, py, pz),
-                             k2 = cand_key(q2, px, py, pz), k3 = cand_key(q3, px, py, pz);
-    if (k0 < best) { best = k0; pos = j0; }
-    if (k1 < best) { best = k1; pos = j1; }
-    if (k2 < best) { best = k2; pos = j2; }
-    if (k3 < best) { best = k3; pos = j3; }
+    cand_update(B, q0, j0, true, px, py, pz);
+    cand_update(B, q1, j1, j + 1 <= last, px, py, pz);
+    cand_update(B, q2, j2, j + 2 <= last, px, py, pz);
+    cand_update(B, q3, j3, j + 3 <= last, px, py, pz);
 }
 
 struct NNQuery {
@@ -113,8 +143,9 @@ struct NNQuery {
 };
 
 // all points of cells [xa, xb] of row (ry, rz); 0 <= xa, xb < nx, row inside the grid
+template <bool CERT>
 __device__ __forceinline__ void scan_cells(const MapView &m, const NNQuery &q, int xa, int xb, int ry, int rz,
-                                           unsigned long long &best, uint32_t &pos)
+                                           NNBest<CERT> &B)
 {
     if (xa > xb) return;
     for (int bx = xa >> 5; bx <= (xb >> 5); ++bx) {
@@ -129,18 +160,19 @@ __device__ __forceinline__ void scan_cells(const MapView &m, const NNQuery &q, i
         NN_STAT(6, 1);
         uint32_t j = __ldg(&m.cell_start[i0]);
         const uint32_t e = __ldg(&m.cell_start[i1]);
-        for (; j < e; j += 4) eval4(m, j, e, q.px, q.py, q.pz, best, pos);
+        for (; j < e; j += 4) eval4(m, j, e, q.px, q.py, q.pz, B);
+        B.refresh();
     }
 }
 
 // one row whose points are all at least sqrt(g) away in (y, z): keep the x cells the best
 // distance still reaches.  own: cells cx-1..cx+1 of this row were already scanned.
+template <bool CERT>
 __device__ __forceinline__ void visit_row(const MapView &m, const NNQuery &q, int ry, int rz, float g, bool own,
-                                          unsigned long long &best, uint32_t &pos)
+                                          NNBest<CERT> &B)
 {
     NN_STAT(2, 1);
-    const float bd = __uint_as_float((uint32_t)(best >> 32));
-    const float rem = __fsub_ru(__fmul_ru(bd, kGrow), g);  // real dx^2 of any useful point is <= rem
+    const float rem = __fsub_ru(__fmul_ru(B.prune(), kGrow), g);  // real dx^2 of any useful point is <= rem
     int xa, xb;
     if (rem < q.xlim2) {
         xa = q.cx - (rem >= q.xdn2 ? 1 : 0);
@@ -153,16 +185,23 @@ __device__ __forceinline__ void visit_row(const MapView &m, const NNQuery &q, in
     xa = max(xa, 0);
     xb = min(xb, m.nx - 1);
     if (own) {
-        scan_cells(m, q, xa, min(xb, q.cx - 2), ry, rz, best, pos);
-        scan_cells(m, q, max(xa, q.cx + 2), xb, ry, rz, best, pos);
+        scan_cells(m, q, xa, min(xb, q.cx - 2), ry, rz, B);
+        scan_cells(m, q, max(xa, q.cx + 2), xb, ry, rz, B);
     } else {
-        scan_cells(m, q, xa, xb, ry, rz, best, pos);
+        scan_cells(m, q, xa, xb, ry, rz, B);
     }
 }
 
+__device__ __forceinline__ float ring_gap(const AxisGap &a, int d, float hq)
+{
+    return d == 0 ? 0.f
+                  : (d > 0 ? __fadd_rd(a.up, __fmul_rd((float)(d - 1), hq)) : __fadd_rd(a.dn, __fmul_rd((float)(-d - 1), hq)));
+}
+
 // rings 2, 3, ... (rows farther than the eight around the own row): rare for matched queries
+template <bool CERT>
 static __device__ __noinline__ void nn_far_rings(const MapView &m, const NNQuery &q, const AxisGap ay, const AxisGap az,
-                                                 unsigned long long &best, uint32_t &pos)
+                                                 NNBest<CERT> &B)
 {
     for (int rho = 2;; ++rho) {
         const float e = __fmul_rd((float)(rho - 1), m.hq);
@@ -174,7 +213,7 @@ static __device__ __noinline__ void nn_far_rings(const MapView &m, const NNQuery
         if (y_dn) mn = fminf(mn, __fadd_rd(ay.dn, e));
         if (z_up) mn = fminf(mn, __fadd_rd(az.up, e));
         if (z_dn) mn = fminf(mn, __fadd_rd(az.dn, e));
-        if (__uint_as_float((uint32_t)(best >> 32)) < gap_sq(mn)) return;  // later rings are farther still
+        if (B.prune() < gap_sq(mn)) return;  // later rings are farther still
         const int n_side = 2 * rho + 1;
         for (int t = 0; t < 8 * rho; ++t) {
             int dy, dz;
@@ -182,21 +221,15 @@ static __device__ __noinline__ void nn_far_rings(const MapView &m, const NNQuery
                 dz = t < n_side ? -rho : rho;
                 dy = (t < n_side ? t : t - n_side) - rho;
             } else {  // its two sides: dy = -rho, +rho, |dz| < rho
-                const int s = t - 2 * n_side;
-                dy = (s & 1) ? rho : -rho;
-                dz = (s >> 1) - (rho - 1);
+                const int u = t - 2 * n_side;
+                dy = (u & 1) ? rho : -rho;
+                dz = (u >> 1) - (rho - 1);
             }
             const int ry = q.cy + dy, rz = q.cz + dz;
             if (ry < 0 || ry >= m.ny || rz < 0 || rz >= m.nz) continue;
-            const float gy = dy == 0 ? 0.f
-                                     : (dy > 0 ? __fadd_rd(ay.up, __fmul_rd((float)(dy - 1), m.hq))
-                                               : __fadd_rd(ay.dn, __fmul_rd((float)(-dy - 1), m.hq)));
-            const float gz = dz == 0 ? 0.f
-                                     : (dz > 0 ? __fadd_rd(az.up, __fmul_rd((float)(dz - 1), m.hq))
-                                               : __fadd_rd(az.dn, __fmul_rd((float)(-dz - 1), m.hq)));
-            const float g = __fadd_rd(gap_sq(gy), gap_sq(gz));
-            if (__uint_as_float((uint32_t)(best >> 32)) < g) continue;
-            visit_row(m, q, ry, rz, g, false, best, pos);
+            const float g = __fadd_rd(gap_sq(ring_gap(ay, dy, m.hq)), gap_sq(ring_gap(az, dz, m.hq)));
+            if (B.prune() < g) continue;
+            visit_row(m, q, ry, rz, g, false, B);
         }
     }
 }
@@ -212,18 +245,26 @@ constexpr uint32_t pack8(int a0, int a1, int a2, int a3, int a4, int a5, int a6,
 constexpr uint32_t kRowY = pack8(1, 0, 1, -1, 0, 1, -1, -1);
 constexpr uint32_t kRowZ = pack8(0, 1, 1, 0, -1, -1, 1, -1);
 
-// limit: accept only d2 < limit (strict), like the reference's threshold test
-__device__ __forceinline__ NNHit nn_query(const MapView &m, float px, float py, float pz, float limit)
+// The complete walk.  limit: accept only d2 < limit (strict), like the reference's threshold test.
+// On return B.key < (bits(limit) << 32) iff a point was found.
+template <bool CERT>
+__device__ __forceinline__ void nn_walk(const MapView &m, float px, float py, float pz, float limit, float mu,
+                                        NNBest<CERT> &B)
 {
-    NNHit h;
-    h.d2 = limit;
-    h.idx = -1;
-    h.pos = 0;
-    if (!(limit > 0.f) || m.n_pts == 0 || !isfinite(px) || !isfinite(py) || !isfinite(pz)) return h;
+    B.key = (unsigned long long)__float_as_uint(limit) << 32;
+    B.pos = 0;
+    B.b2 = FLT_MAX;
+    B.mu = mu;
+    B.bdm = limit;
+    B.refresh();
     NN_STAT(3, 1);
-    const unsigned long long none = (unsigned long long)__float_as_uint(limit) << 32;
-    unsigned long long best = none;
-    uint32_t pos = 0;
+    {   // farther from the map's bounding box than the (inflated) limit: nothing to look at
+        const float ex = fmaxf(fmaxf(__fsub_rd(m.bmin[0], px), __fsub_rd(px, m.bmax[0])), 0.f);
+        const float ey = fmaxf(fmaxf(__fsub_rd(m.bmin[1], py), __fsub_rd(py, m.bmax[1])), 0.f);
+        const float ez = fmaxf(fmaxf(__fsub_rd(m.bmin[2], pz), __fsub_rd(pz, m.bmax[2])), 0.f);
+        const float out2 = __fmul_rd(__fadd_rd(__fadd_rd(__fmul_rd(ex, ex), __fmul_rd(ey, ey)), __fmul_rd(ez, ez)), kShrink);
+        if (B.prune() < out2) return;
+    }
     const AxisGap ax = axis_gap(px, m.ox, m.inv_h, m.hq, m.nx), ay = axis_gap(py, m.oy, m.inv_h, m.hq, m.ny),
                   az = axis_gap(pz, m.oz, m.inv_h, m.hq, m.nz);
     NNQuery q;
@@ -234,18 +275,16 @@ __device__ __forceinline__ NNHit nn_query(const MapView &m, float px, float py, 
     q.xlim2 = gap_sq(__fadd_rd(fminf(ax.dn, ax.up), m.hq));
     // own row: seed with the cells cx-1..cx+1, then whatever else of the row is still in reach
     if (q.cy >= 0 && q.cy < m.ny && q.cz >= 0 && q.cz < m.nz) {
-        scan_cells(m, q, max(q.cx - 1, 0), min(q.cx + 1, m.nx - 1), q.cy, q.cz, best, pos);
-        if (!(__fmul_ru(__uint_as_float((uint32_t)(best >> 32)), kGrow) < q.xlim2))
-            visit_row(m, q, q.cy, q.cz, 0.f, true, best, pos);
+        scan_cells(m, q, max(q.cx - 1, 0), min(q.cx + 1, m.nx - 1), q.cy, q.cz, B);
+        if (!(__fmul_ru(B.prune(), kGrow) < q.xlim2)) visit_row(m, q, q.cy, q.cz, 0.f, true, B);
     }
     // ring 1: which of the eight rows can still hold a better point?
-    const bool y_up_near = ay.up <= ay.dn, z_up_near = az.up <= az.dn;
-    const int sy = y_up_near ? 1 : -1, sz = z_up_near ? 1 : -1;
+    const int sy = ay.up <= ay.dn ? 1 : -1, sz = az.up <= az.dn ? 1 : -1;
     const float yn2 = gap_sq(fminf(ay.up, ay.dn)), yf2 = gap_sq(fmaxf(ay.up, ay.dn));
     const float zn2 = gap_sq(fminf(az.up, az.dn)), zf2 = gap_sq(fmaxf(az.up, az.dn));
     uint32_t mask = 0;
     {
-        const float bd = __uint_as_float((uint32_t)(best >> 32));
+        const float bd = B.prune();
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int my = (int)((kRowY >> (2 * k)) & 3u) - 1, mz = (int)((kRowZ >> (2 * k)) & 3u) - 1;
@@ -260,26 +299,78 @@ __device__ __forceinline__ NNHit nn_query(const MapView &m, float px, float py, 
         mask &= mask - 1;
         const int my = (int)((kRowY >> (2 * k)) & 3u) - 1, mz = (int)((kRowZ >> (2 * k)) & 3u) - 1;
         const float g = __fadd_rd(my > 0 ? yn2 : (my < 0 ? yf2 : 0.f), mz > 0 ? zn2 : (mz < 0 ? zf2 : 0.f));
-        if (__uint_as_float((uint32_t)(best >> 32)) < g) continue;
-        visit_row(m, q, q.cy + sy * my, q.cz + sz * mz, g, false, best, pos);
+        if (B.prune() < g) continue;
+        visit_row(m, q, q.cy + sy * my, q.cz + sz * mz, g, false, B);
     }
-    // farther rings only while the best distance reaches past ring 1
-    {
-        const float bd = __uint_as_float((uint32_t)(best >> 32));
-        const float reach = fminf(fminf(__fadd_rd(ay.up, m.hq), __fadd_rd(ay.dn, m.hq)),
-                                  fminf(__fadd_rd(az.up, m.hq), __fadd_rd(az.dn, m.hq)));
-        if (!(bd < gap_sq(reach))) {
-            NN_STAT(4, 1);
-            nn_far_rings(m, q, ay, az, best, pos);
-        }
+    // farther rings only while the bound reaches past ring 1
+    const float reach = fminf(fminf(__fadd_rd(ay.up, m.hq), __fadd_rd(ay.dn, m.hq)),
+                              fminf(__fadd_rd(az.up, m.hq), __fadd_rd(az.dn, m.hq)));
+    if (!(B.prune() < gap_sq(reach))) {
+        NN_STAT(4, 1);
+        nn_far_rings(m, q, ay, az, B);
     }
-    if (best < none) {
+}
+
+__device__ __forceinline__ NNHit nn_query(const MapView &m, float px, float py, float pz, float limit)
+{
+    NNHit h;
+    h.d2 = limit;
+    h.idx = -1;
+    h.pos = 0;
+    if (!(limit > 0.f) || m.n_pts == 0 || !isfinite(px) || !isfinite(py) || !isfinite(pz)) return h;
+    NNBest<false> B;
+    nn_walk<false>(m, px, py, pz, limit, 0.f, B);
+    if ((uint32_t)(B.key >> 32) < __float_as_uint(limit)) {
         NN_STAT(5, 1);
-        h.d2 = __uint_as_float((uint32_t)(best >> 32));
-        h.idx = (int)(uint32_t)(best & 0xFFFFFFFFull);
-        h.pos = pos;
+        h.d2 = B.bd();
+        h.idx = (int)(uint32_t)(B.key & 0xFFFFFFFFull);
+        h.pos = B.pos;
     }
     return h;
+}
+
+// ---- certificates: skipping the search when the query has barely moved ---------------------------
+// A CERT walk at query position p leaves, besides the result, a radius L such that EVERY map point
+// other than the reported neighbour lies farther than L from p (real distances):
+//   * evaluated points: their float d2 >= b2, i.e. real distance >= sqrt(b2 * (1 - 4e-7));
+//   * points never looked at: farther than sqrt(d2 best) + mu (see NNBest).
+// If the same source point is searched again at p' (next iteration, pose moved a little) and
+//       d2(p', neighbour) < limit   and   d2(p', neighbour) < (L - |p' - p|)^2 * (1 - 2e-6),
+// the neighbour is still the strict minimum, so the exact search would return the same index and
+// the d2 evaluated here -- bit for bit -- and is skipped.  For a query without a neighbour the
+// same L bounds ALL points: it stays unmatched while (L - |p' - p|)^2 * (1 - 2e-6) >= limit.
+constexpr uint32_t kNoPos = 0xFFFFFFFFu;
+
+// L of a finished CERT walk (rounded down)
+__device__ __forceinline__ float cert_radius(const NNBest<true> &B)
+{
+    const float s2 = __fmul_rd(__fsqrt_rd(__fmul_rd(B.b2, 0.999999f)), 0.999999f);
+    const float s1 = __fadd_rd(__fsqrt_rd(B.bd()), B.mu);  // bd() == limit when nothing was found
+    return fminf(s1, s2);
+}
+
+// cert = (p.xyz, L), pos = neighbour position or kNoPos.  Returns true when the old result stands;
+// then key = packed (d2, index) of the neighbour at the new position (or the none sentinel).
+__device__ __forceinline__ bool nn_verify(const MapView &m, const float4 cert, uint32_t pos, float px, float py, float pz,
+                                          float limit, unsigned long long &key)
+{
+    if (!(cert.w > 0.f)) return false;
+    const float mx = __fsub_rn(px, cert.x), my = __fsub_rn(py, cert.y), mz = __fsub_rn(pz, cert.z);
+    const float mv2 = __fadd_ru(__fadd_ru(__fmul_ru(mx, mx), __fmul_ru(my, my)), __fmul_ru(mz, mz));
+    const float mv = __fadd_ru(__fmul_ru(__fsqrt_ru(mv2), 1.000001f), 1e-18f);  // >= |p' - p|
+    const float rest = __fsub_rd(cert.w, mv);
+    if (!(rest > 0.f)) return false;
+    const float thr = __fmul_rd(__fmul_rd(rest, rest), kShrink);  // every OTHER point has float d2 > thr
+    const unsigned long long none = (unsigned long long)__float_as_uint(limit) << 32;
+    if (pos == kNoPos) {
+        key = none;
+        return thr >= limit;
+    }
+    const float4 q = __ldg(&m.pts[pos]);
+    const float dx = __fsub_rn(px, q.x), dy = __fsub_rn(py, q.y), dz = __fsub_rn(pz, q.z);
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(q.w);
+    return d2 < limit && d2 < thr;
 }
 
 // reference applyTransformation (icp_point_to_point.cpp:103-105): ((T0*x + T1*y) + T2*z) + T3
