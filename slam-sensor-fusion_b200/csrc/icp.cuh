@@ -22,6 +22,8 @@ struct ScanState {
     float pend_error;  // REFERENCE: error of the pass that decided to re-search
     int iterations, done, converged, aborted, n_searches, k_last, need_search, have_step;
     double fitness, rmse;  // O3D
+    float last_step;       // size of the last pose update (metres; rotations weighted by a 30 m lever arm)
+    float pad_;
     uint32_t pt_begin;     // first slot in the packed arrays (multiple of kTile)
     uint32_t n_pts;        // source points (after optional voxel downsample)
     uint32_t tile_begin, tile_cap;

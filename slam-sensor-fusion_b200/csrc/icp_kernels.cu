@@ -61,6 +61,7 @@ __global__ void init_states_kernel(ScanState *st, const float *T_init, uint32_t 
     z.have_step = 0;
     z.fitness = 0.0;
     z.rmse = 0.0;
+    z.last_step = 3.0e38f;
     for (int i = 0; i < trace_len; ++i) {
         trace_err[(size_t)s * trace_len + i] = nanf("");
         trace_search[(size_t)s * trace_len + i] = 0;
@@ -175,8 +176,10 @@ __global__ void __launch_bounds__(kThreads)
     __shared__ __align__(128) float4 s_q[kTile];  // TMA destination; transformed in place, w = owned by this rank
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_pos[kTile];
-    __shared__ unsigned short s_queue[kTile];
-    __shared__ uint32_t s_nq, s_next;
+    __shared__ unsigned short s_queue[kTile], s_far[kTile];
+    __shared__ unsigned long long s_key[kTile];
+    __shared__ float s_b2[kTile];
+    __shared__ uint32_t s_nq, s_nfar, s_next;
     __shared__ float sT[16];
     __shared__ double sred[kThreads / 32][kAccum];
     const uint32_t none_hi = __float_as_uint(limit);
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(kThreads)
         if (threadIdx.x == 0) {
             s_next = atomicAdd(fetch, 1u);
             s_nq = 0;
+            s_nfar = 0;
         }
         __syncthreads();
         const uint32_t ti = s_next;
@@ -202,6 +206,9 @@ __global__ void __launch_bounds__(kThreads)
         }
         const uint32_t n_here = min((uint32_t)kTile, z.n_pts - row0);
         const size_t slot0 = (size_t)z.pt_begin + row0;
+        // a certificate only pays off if the next pose update is small: write them once the last
+        // update was below a few margins (the updates shrink fast)
+        const bool make_cert = z.last_step < 4.0f * map.cert_mu;
         if (threadIdx.x == 0) tile_load_issue(s_q, &s_bar, src + slot0, n_here * (uint32_t)sizeof(float4));
         if (threadIdx.x < 16) sT[threadIdx.x] = z.T[threadIdx.x];
         // certificates of this thread's queries: issue the loads before waiting for the tile
@@ -249,21 +256,66 @@ __global__ void __launch_bounds__(kThreads)
             s_queue[atomicAdd(&s_nq, 1u)] = (unsigned short)r;
         }
         __syncthreads();
-        // ---- S ----
+        // ---- S: near part of the walk for every queued query; the few that must go on to rings 2..
+        // are queued again and finished afterwards, packed densely, so that a warp is not held up
+        // by the lanes that drew a far query ----
         const uint32_t nq = s_nq;
         for (uint32_t i = threadIdx.x; i < nq; i += kThreads) {
             const uint32_t r = s_queue[i];
             const float4 p = s_q[r];
-            NNBest<true> B;
-            nn_walk<true>(map, p.x, p.y, p.z, limit, map.cert_mu, B);
-            const bool hit = (uint32_t)(B.key >> 32) < none_hi;
-            corr[slot0 + r] = hit ? (int)(uint32_t)B.key : -1;
-            if (hit) {
-                s_pos[r] = B.pos;
-                NN_STAT(5, 1);
+            unsigned long long key;
+            uint32_t pos;
+            float b2 = 0.f;
+            bool far;
+            if (make_cert) {
+                NNBest<true> B;
+                far = nn_walk_near<true>(map, p.x, p.y, p.z, limit, map.cert_mu, B);
+                key = B.key; pos = B.pos; b2 = B.b2;
+            } else {
+                NNBest<false> B;
+                far = nn_walk_near<false>(map, p.x, p.y, p.z, limit, 0.f, B);
+                key = B.key; pos = B.pos;
             }
-            cert_p[slot0 + r] = make_float4(p.x, p.y, p.z, cert_radius(B));
-            cert_pos[slot0 + r] = hit ? B.pos : kNoPos;
+            s_key[r] = key;
+            s_pos[r] = pos;
+            s_b2[r] = b2;
+            if (far) s_far[atomicAdd(&s_nfar, 1u)] = (unsigned short)r;
+        }
+        __syncthreads();
+        const uint32_t nfar = s_nfar;
+        for (uint32_t i = threadIdx.x; i < nfar; i += kThreads) {
+            const uint32_t r = s_far[i];
+            const float4 p = s_q[r];
+            if (make_cert) {
+                NNBest<true> B;
+                B.key = s_key[r]; B.pos = s_pos[r]; B.b2 = s_b2[r]; B.mu = map.cert_mu;
+                B.refresh();
+                nn_walk_far<true>(map, p.x, p.y, p.z, B);
+                s_key[r] = B.key; s_pos[r] = B.pos; s_b2[r] = B.b2;
+            } else {
+                NNBest<false> B;
+                B.key = s_key[r]; B.pos = s_pos[r];
+                nn_walk_far<false>(map, p.x, p.y, p.z, B);
+                s_key[r] = B.key; s_pos[r] = B.pos;
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nq; i += kThreads) {
+            const uint32_t r = s_queue[i];
+            const float4 p = s_q[r];
+            const unsigned long long key = s_key[r];
+            const bool hit = (uint32_t)(key >> 32) < none_hi;
+            corr[slot0 + r] = hit ? (int)(uint32_t)key : -1;
+            float radius = 0.f;
+            if (make_cert) {
+                NNBest<true> B;
+                B.key = key; B.b2 = s_b2[r]; B.mu = map.cert_mu;
+                radius = cert_radius(B);
+            }
+            cert_p[slot0 + r] = make_float4(p.x, p.y, p.z, radius);
+            cert_pos[slot0 + r] = hit ? s_pos[r] : kNoPos;
+            if (!hit) s_pos[r] = kNoPos;
+            else NN_STAT(5, 1);
         }
         __syncthreads();
         // ---- K4: residual / Jacobian terms of the matched queries ----
@@ -400,6 +452,8 @@ __global__ void __launch_bounds__(32) solve_gn_kernel(ScanState *states, const d
     z.iterations += 1;
     double mx = 0.0;
     for (int u = 0; u < 6; ++u) mx = fmax(mx, fabs(x[u]));
+    z.last_step = (float)fmax(fmax(fabs(x[3]), fmax(fabs(x[4]), fabs(x[5]))),
+                              30.0 * fmax(fabs(x[0]), fmax(fabs(x[1]), fabs(x[2]))));
     if (mx < (double)eps) { z.converged = 1; z.done = 1; }
 }
 
@@ -438,6 +492,15 @@ __global__ void __launch_bounds__(32) solve_o3d_kernel(ScanState *states, const 
         for (int cc = 0; cc < 3; ++cc) H[cc * 3 + r] = sv[7 + 3 * r + cc] - (double)K * ma[r] * mb[cc];
     double Ts[16];
     kabsch_from_moments_d(sp, sq, H, Ts);
+    {   // step applied to a point 30 m from the pivot: |Ts * y - y| with y = pivot + (30, 30, 30) / sqrt(3)
+        double mv = 0.0;
+        for (int r = 0; r < 3; ++r) {
+            double acc = Ts[12 + r];
+            for (int cc = 0; cc < 3; ++cc) acc += (Ts[cc * 4 + r] - (r == cc ? 1.0 : 0.0)) * (c[cc] + 17.32);
+            mv = fmax(mv, fabs(acc));
+        }
+        z.last_step = (float)mv;
+    }
     compose_round(Ts, z.T);
     z.iterations += 1;
 }

@@ -217,7 +217,7 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
         const float eps = std::max(ext_max * 1.0e-3f, 1.0e-20f);
         const double vol = (double)std::max(ext[0], eps) * std::max(ext[1], eps) * std::max(ext[2], eps);
         h = ext_max > 0.f ? (float)cbrt(4.0 * vol / (double)n_finite) : 1.0f;
-        const float target = getenv("SSF_CELL_POINTS") ? (float)atof(getenv("SSF_CELL_POINTS")) : 3.0f;
+        const float target = getenv("SSF_CELL_POINTS") ? (float)atof(getenv("SSF_CELL_POINTS")) : 4.5f;
         for (int pass = 0; pass < 4; ++pass) {
             h = fit(h, g);
             if (h < 0.f) { set_error("map extent does not fit the directory at any cell size"); return SSF_ERR_INVALID; }

@@ -57,6 +57,21 @@ struct NNHit {
 constexpr float kShrink = 0.999998f;  // (1 - 2e-6): applied to squared gaps
 constexpr float kGrow = 1.000002f;    // (1 + 2e-6): applied to the best distance
 
+// one-instruction square root (MUFU, relative error <= 2^-23) pushed to a guaranteed upper / lower
+// bound; the absolute term covers flushed subnormals
+__device__ __forceinline__ float sqrt_up(float x)
+{
+    float s;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(x));
+    return __fadd_ru(__fmul_ru(s, 1.0000005f), 1e-18f);
+}
+__device__ __forceinline__ float sqrt_dn(float x)
+{
+    float s;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(x));
+    return fmaxf(__fsub_rd(__fmul_rd(s, 0.9999995f), 1e-18f), 0.f);
+}
+
 // cell coordinate of v plus under-estimates (metres) of the distance from v to the cells
 // c - 1 (dn) and c + 1 (up)
 struct AxisGap {
@@ -99,7 +114,7 @@ struct NNBest {
     __device__ __forceinline__ void refresh()
     {
         if (CERT) {  // (s + mu)^2 with s >= sqrt(bd), everything rounded up
-            const float r = __fadd_ru(__fsqrt_ru(bd()), mu);
+            const float r = __fadd_ru(sqrt_up(bd()), mu);
             bdm = __fmul_ru(r, r);
         }
     }
@@ -178,7 +193,7 @@ __device__ __forceinline__ void visit_row(const MapView &m, const NNQuery &q, in
         xa = q.cx - (rem >= q.xdn2 ? 1 : 0);
         xb = q.cx + (rem >= q.xup2 ? 1 : 0);
     } else {
-        const float rx = __fadd_ru(__fsqrt_ru(fmaxf(rem, 0.f)), 1e-18f);
+        const float rx = sqrt_up(fmaxf(rem, 0.f));
         xa = cell_coord(__fsub_rd(q.px, rx), m.ox, m.inv_h, m.nx);
         xb = cell_coord(__fadd_ru(q.px, rx), m.ox, m.inv_h, m.nx);
     }
@@ -245,11 +260,13 @@ constexpr uint32_t pack8(int a0, int a1, int a2, int a3, int a4, int a5, int a6,
 constexpr uint32_t kRowY = pack8(1, 0, 1, -1, 0, 1, -1, -1);
 constexpr uint32_t kRowZ = pack8(0, 1, 1, 0, -1, -1, 1, -1);
 
-// The complete walk.  limit: accept only d2 < limit (strict), like the reference's threshold test.
-// On return B.key < (bits(limit) << 32) iff a point was found.
+// limit: accept only d2 < limit (strict), like the reference's threshold test.  After the walk
+// B.key < (bits(limit) << 32) iff a point was found.
+// Near part: own row and ring 1.  Returns true when rings 2.. are still within reach of the bound
+// (then nn_walk_far must follow, possibly later and in another thread: B carries all the state).
 template <bool CERT>
-__device__ __forceinline__ void nn_walk(const MapView &m, float px, float py, float pz, float limit, float mu,
-                                        NNBest<CERT> &B)
+__device__ __forceinline__ bool nn_walk_near(const MapView &m, float px, float py, float pz, float limit, float mu,
+                                             NNBest<CERT> &B)
 {
     B.key = (unsigned long long)__float_as_uint(limit) << 32;
     B.pos = 0;
@@ -263,7 +280,7 @@ __device__ __forceinline__ void nn_walk(const MapView &m, float px, float py, fl
         const float ey = fmaxf(fmaxf(__fsub_rd(m.bmin[1], py), __fsub_rd(py, m.bmax[1])), 0.f);
         const float ez = fmaxf(fmaxf(__fsub_rd(m.bmin[2], pz), __fsub_rd(pz, m.bmax[2])), 0.f);
         const float out2 = __fmul_rd(__fadd_rd(__fadd_rd(__fmul_rd(ex, ex), __fmul_rd(ey, ey)), __fmul_rd(ez, ez)), kShrink);
-        if (B.prune() < out2) return;
+        if (B.prune() < out2) return false;
     }
     const AxisGap ax = axis_gap(px, m.ox, m.inv_h, m.hq, m.nx), ay = axis_gap(py, m.oy, m.inv_h, m.hq, m.ny),
                   az = axis_gap(pz, m.oz, m.inv_h, m.hq, m.nz);
@@ -307,8 +324,32 @@ __device__ __forceinline__ void nn_walk(const MapView &m, float px, float py, fl
                               fminf(__fadd_rd(az.up, m.hq), __fadd_rd(az.dn, m.hq)));
     if (!(B.prune() < gap_sq(reach))) {
         NN_STAT(4, 1);
-        nn_far_rings(m, q, ay, az, B);
+        return true;
     }
+    return false;
+}
+
+// Far part: rings 2, 3, ... until the bound is met.
+template <bool CERT>
+__device__ __forceinline__ void nn_walk_far(const MapView &m, float px, float py, float pz, NNBest<CERT> &B)
+{
+    const AxisGap ax = axis_gap(px, m.ox, m.inv_h, m.hq, m.nx), ay = axis_gap(py, m.oy, m.inv_h, m.hq, m.ny),
+                  az = axis_gap(pz, m.oz, m.inv_h, m.hq, m.nz);
+    NNQuery q;
+    q.px = px; q.py = py; q.pz = pz;
+    q.cx = ax.c; q.cy = ay.c; q.cz = az.c;
+    q.xdn2 = gap_sq(ax.dn);
+    q.xup2 = gap_sq(ax.up);
+    q.xlim2 = gap_sq(__fadd_rd(fminf(ax.dn, ax.up), m.hq));
+    nn_far_rings(m, q, ay, az, B);
+}
+
+// The complete walk in one thread.
+template <bool CERT>
+__device__ __forceinline__ void nn_walk(const MapView &m, float px, float py, float pz, float limit, float mu,
+                                        NNBest<CERT> &B)
+{
+    if (nn_walk_near(m, px, py, pz, limit, mu, B)) nn_walk_far(m, px, py, pz, B);
 }
 
 __device__ __forceinline__ NNHit nn_query(const MapView &m, float px, float py, float pz, float limit)
@@ -344,8 +385,8 @@ constexpr uint32_t kNoPos = 0xFFFFFFFFu;
 // L of a finished CERT walk (rounded down)
 __device__ __forceinline__ float cert_radius(const NNBest<true> &B)
 {
-    const float s2 = __fmul_rd(__fsqrt_rd(__fmul_rd(B.b2, 0.999999f)), 0.999999f);
-    const float s1 = __fadd_rd(__fsqrt_rd(B.bd()), B.mu);  // bd() == limit when nothing was found
+    const float s2 = __fmul_rd(sqrt_dn(__fmul_rd(B.b2, 0.999999f)), 0.999999f);
+    const float s1 = __fadd_rd(sqrt_dn(B.bd()), B.mu);  // bd() == limit when nothing was found
     return fminf(s1, s2);
 }
 
@@ -357,7 +398,7 @@ __device__ __forceinline__ bool nn_verify(const MapView &m, const float4 cert, u
     if (!(cert.w > 0.f)) return false;
     const float mx = __fsub_rn(px, cert.x), my = __fsub_rn(py, cert.y), mz = __fsub_rn(pz, cert.z);
     const float mv2 = __fadd_ru(__fadd_ru(__fmul_ru(mx, mx), __fmul_ru(my, my)), __fmul_ru(mz, mz));
-    const float mv = __fadd_ru(__fmul_ru(__fsqrt_ru(mv2), 1.000001f), 1e-18f);  // >= |p' - p|
+    const float mv = __fmul_ru(sqrt_up(mv2), 1.000001f);  // >= |p' - p|
     const float rest = __fsub_rd(cert.w, mv);
     if (!(rest > 0.f)) return false;
     const float thr = __fmul_rd(__fmul_rd(rest, rest), kShrink);  // every OTHER point has float d2 > thr
