@@ -634,7 +634,7 @@ extern "C" int ssf_batch_create(ssf_icp *icp, size_t max_scans, size_t max_total
 {
     SSF_ARG(icp && out, "ssf_batch_create: NULL argument");
     SSF_ARG(max_scans >= 1 && max_scans < (1u << 24), "ssf_batch_create: max_scans out of range");
-    SSF_ARG(max_total_points + max_scans * kTile < ((size_t)1 << 31), "ssf_batch_create: too many points");
+    SSF_ARG(max_total_points + max_scans * kSlotAlign < ((size_t)1 << 31), "ssf_batch_create: too many points");
     *out = nullptr;
     SSF_TRY(use_device(icp->ctx));
     ssf_batch *b = new (std::nothrow) ssf_batch;
@@ -642,7 +642,7 @@ extern "C" int ssf_batch_create(ssf_icp *icp, size_t max_scans, size_t max_total
     b->icp = icp;
     b->max_scans = max_scans;
     b->max_points = max_total_points;
-    const size_t slots = max_total_points + max_scans * kTile;  // tile alignment padding
+    const size_t slots = max_total_points + max_scans * kSlotAlign;  // alignment padding
     const size_t tiles = slots / kTile + 1;
     int rc = SSF_OK;
     auto chk = [&](int r) { if (rc == SSF_OK) rc = r; };
@@ -707,7 +707,7 @@ static int batch_upload_impl(ssf_batch *b, const float *xyz, const size_t *n_pts
     uint32_t max_n = 0;
     for (size_t s = 0; s < n_scans; ++s) {
         const uint32_t n = (uint32_t)n_pts[s];
-        const uint32_t cap = (n + kTile - 1) / kTile;
+        const uint32_t cap = (n + kSlotAlign - 1) / kSlotAlign * (kSlotAlign / kTile);  // search tiles, whole sort tiles
         b->meta_host[5 * s + 0] = (uint32_t)raw;
         b->meta_host[5 * s + 1] = n;
         b->meta_host[5 * s + 2] = (uint32_t)(tile * kTile);

@@ -172,6 +172,11 @@ int exclusive_scan_u32(const uint32_t *in, uint32_t *out, size_t n, uint32_t *to
 // Stable LSD radix sort of (key, val) pairs on the low `bits` bits of the keys.  Sorted data
 // ends up in keys/vals (ping-pong through scratch).
 int radix_sort_pairs_u64(unsigned long long *keys, uint32_t *vals, size_t n, int bits, Scratch &s, cudaStream_t st);
+// Segmented form: n a multiple of kSortTileSize; seg_of_tile[t] = (first sort tile of t's segment, tiles in it).
+// Every segment is sorted on its own (all 32 key bits), in place.
+constexpr int kSortTileSize = 2048;
+int seg_radix_sort_pairs_u32(uint32_t *keys, uint32_t *vals, size_t n, const uint2 *seg_of_tile, Scratch &s,
+                             cudaStream_t st);
 // bbox[0..2] = min xyz, bbox[3..5] = max xyz over finite points (device array of 6 floats);
 // n_finite (device) = number of finite points.
 int bbox_finite(const float4 *pts, size_t n, float *bbox_dev, uint32_t *n_finite_dev, cudaStream_t st);

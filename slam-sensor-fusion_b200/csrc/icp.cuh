@@ -11,6 +11,8 @@ constexpr int kTile = 512;     // queries per block of the search kernels; scans
 constexpr int kThreads = 128;  // threads of a fused search block
 constexpr int kQ = kTile / kThreads;  // queries per thread there
 constexpr int kAccum = 32;  // doubles per partial row
+constexpr int kSlotAlign = kSortTileSize;  // a scan's slot range is a whole number of sort tiles
+static_assert(kSlotAlign % kTile == 0, "slot alignment must be a multiple of the search tile");
 
 // One scan of a batch (device memory).
 struct ScanState {
@@ -48,8 +50,9 @@ struct BatchBuffers {
     DevBuf<int32_t> trace_search;  // [scan][num_iterations]
     // voxel-downsample stage
     DevBuf<float4> raw;            // raw scans when source_voxel_leaf > 0
-    DevBuf<unsigned long long> vkeys;
+    DevBuf<uint32_t> vkeys;
     DevBuf<uint32_t> vvals;
+    DevBuf<uint2> vseg;            // per sort tile: (first tile of its scan, tiles in it)
     DevBuf<uint32_t> vflags, vscan;
     DevBuf<float> vbox;            // per scan: min xyz, max xyz (ordered ints during reduce)
     DevBuf<int32_t> vgrid;         // per scan: minb[3], divb[3], refused, pad

@@ -132,6 +132,7 @@ int exclusive_scan_u32(const uint32_t *in, uint32_t *out, size_t n, uint32_t *to
 constexpr int kSortThreads = 256;
 constexpr int kSortItems = 8;  // rounds per warp
 constexpr int kSortTile = kSortThreads * kSortItems;
+static_assert(kSortTile == kSortTileSize, "common.cuh announces the sort tile size");
 
 __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const unsigned long long *__restrict__ keys, size_t n,
                                                                  int shift, uint32_t *__restrict__ ghist,
@@ -236,6 +237,107 @@ int radix_sort_pairs_u64(unsigned long long *keys, uint32_t *vals, size_t n, int
     if (kin != keys) {
         SSF_CUDA(cudaMemcpyAsync(keys, kin, n * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
         SSF_CUDA(cudaMemcpyAsync(vals, vin, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    return SSF_OK;
+}
+
+// =========================================================================================
+// Segmented stable LSD radix sort of (u32 key, u32 value) pairs, 8-bit digits, 4 passes.
+// The array is a sequence of segments, each a whole number of sort tiles; seg[t] = (first tile
+// of t's segment, tiles in it).  The digit counts are laid out [segment][digit][tile in segment],
+// so ONE global exclusive scan yields, for every (tile, digit), the output position that keeps
+// each segment in its own slot range and orders it by digit, then tile, then rank -- i.e. an
+// independent stable sort per segment, all segments in the same launches.
+// =========================================================================================
+__global__ void __launch_bounds__(kSortThreads)
+    seg_hist_kernel(const uint32_t *__restrict__ keys, int shift, const uint2 *__restrict__ seg,
+                    uint32_t *__restrict__ ghist)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t base = (size_t)blockIdx.x * kSortTile;
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i)
+        atomicAdd(&h[(keys[base + (size_t)i * kSortThreads + threadIdx.x] >> shift) & 255u], 1u);
+    __syncthreads();
+    const uint2 sg = seg[blockIdx.x];
+    ghist[(size_t)256 * sg.x + (size_t)threadIdx.x * sg.y + (blockIdx.x - sg.x)] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+    seg_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                       uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int shift,
+                       const uint2 *__restrict__ seg, const uint32_t *__restrict__ ghist_scanned)
+{
+    __shared__ uint32_t wh[kSortThreads / 32][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (kSortThreads / 32) * 256; i += kSortThreads) (&wh[0][0])[i] = 0;
+    __syncthreads();
+    const size_t wbase = (size_t)blockIdx.x * kSortTile + (size_t)warp * (32 * kSortItems);
+    uint32_t k[kSortItems], v[kSortItems], rank[kSortItems];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const size_t idx = wbase + (size_t)r * 32 + lane;
+        k[r] = keys_in[idx];
+        v[r] = vals_in[idx];
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t digit = (k[r] >> shift) & 255u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        const uint32_t prev = wh[warp][digit];
+        __syncwarp();
+        if ((peers & lt_mask) == 0) wh[warp][digit] = prev + __popc(peers);
+        __syncwarp();
+        rank[r] = prev + __popc(peers & lt_mask);
+    }
+    __syncthreads();
+    {
+        // thread d owns digit d: turn per-warp counts into global output offsets
+        const uint2 sg = seg[blockIdx.x];
+        const int d = threadIdx.x;
+        uint32_t run = ghist_scanned[(size_t)256 * sg.x + (size_t)d * sg.y + (blockIdx.x - sg.x)];
+#pragma unroll
+        for (int w = 0; w < kSortThreads / 32; ++w) {
+            const uint32_t c = wh[w][d];
+            wh[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t pos = wh[warp][(k[r] >> shift) & 255u] + rank[r];
+        keys_out[pos] = k[r];
+        vals_out[pos] = v[r];
+    }
+}
+
+int seg_radix_sort_pairs_u32(uint32_t *keys, uint32_t *vals, size_t n, const uint2 *seg_of_tile, Scratch &s,
+                             cudaStream_t st)
+{
+    if (n == 0) return SSF_OK;
+    if (n % kSortTile != 0 || n >= (size_t)1 << 32) {
+        set_error("seg_radix_sort_pairs_u32: n must be a multiple of %d and below 2^32", kSortTile);
+        return SSF_ERR_INVALID;
+    }
+    const uint32_t n_tiles = (uint32_t)(n / kSortTile);
+    SSF_TRY(s.hist.reserve((size_t)256 * n_tiles));
+    SSF_TRY(s.keys_alt.reserve(n / 2 + 1));
+    SSF_TRY(s.vals_alt.reserve(n));
+    uint32_t *kin = keys, *kout = reinterpret_cast<uint32_t *>(s.keys_alt.p);
+    uint32_t *vin = vals, *vout = s.vals_alt.p;
+    for (int p = 0; p < 4; ++p) {  // an even number of passes: the result ends up in keys / vals
+        const int shift = 8 * p;
+        seg_hist_kernel<<<n_tiles, kSortThreads, 0, st>>>(kin, shift, seg_of_tile, s.hist.p);
+        SSF_LAUNCHED();
+        SSF_TRY(exclusive_scan_u32(s.hist.p, s.hist.p, (size_t)256 * n_tiles, nullptr, s, st));
+        seg_scatter_kernel<<<n_tiles, kSortThreads, 0, st>>>(kin, vin, kout, vout, shift, seg_of_tile, s.hist.p);
+        SSF_LAUNCHED();
+        uint32_t *tk = kin; kin = kout; kout = tk;
+        uint32_t *tv = vin; vin = vout; vout = tv;
     }
     return SSF_OK;
 }

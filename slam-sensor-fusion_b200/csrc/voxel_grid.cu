@@ -138,7 +138,7 @@ int voxel_downsample_device(VoxelWork &w, size_t n, float leaf, Scratch &s, cuda
 namespace ssf {
 
 // vbox per scan: 6 ordered ints (min xyz, max xyz), [6] finite count, [7] pad
-__global__ void vb_init_kernel(int *vbox, uint32_t *n_out, uint32_t *first_run, uint32_t n_scans)
+__global__ void vb_init_kernel(int *vbox, uint32_t n_scans)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_scans) return;
@@ -148,8 +148,6 @@ __global__ void vb_init_kernel(int *vbox, uint32_t *n_out, uint32_t *first_run, 
     }
     vbox[8 * s + 6] = 0;
     vbox[8 * s + 7] = 0;
-    n_out[s] = 0;
-    first_run[s] = 0xFFFFFFFFu;
 }
 
 __global__ void __launch_bounds__(kTile)
@@ -223,88 +221,79 @@ __global__ void vb_grid_kernel(const int *__restrict__ vbox, int32_t *__restrict
     if (d64[0] * d64[1] * d64[2] > (long long)INT32_MAX) g[6] = 1;  // PCL refuses: output = input
 }
 
-__global__ void __launch_bounds__(kTile)
-    vb_keys_kernel(const float4 *__restrict__ raw, const uint32_t *__restrict__ tile_scan,
-                   const uint32_t *__restrict__ meta, const int32_t *__restrict__ vgrid, float inv, uint32_t n_scans,
-                   unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals)
+// per sort tile: (first sort tile of its scan, sort tiles of that scan)
+__global__ void vb_seg_kernel(const uint32_t *__restrict__ tile_scan, const uint32_t *__restrict__ meta,
+                              uint32_t n_sort_tiles, uint2 *__restrict__ seg)
 {
-    const uint32_t s = tile_scan[blockIdx.x];
-    const uint32_t n = meta[5 * s + 1], pt_begin = meta[5 * s + 2], tile_begin = meta[5 * s + 3];
-    const uint32_t row = (blockIdx.x - tile_begin) * kTile + threadIdx.x;
-    const size_t slot = (size_t)blockIdx.x * kTile + threadIdx.x;  // == pt_begin + row
-    unsigned long long k = (unsigned long long)n_scans << 32;      // dropped / padding: sorts last
+    constexpr uint32_t kPer = kSlotAlign / kTile;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_sort_tiles) return;
+    const uint32_t s = tile_scan[t * kPer];
+    seg[t] = make_uint2(meta[5 * s + 3] / kPer, meta[5 * s + 4] / kPer);
+}
+
+constexpr uint32_t kDeadKey = 0xFFFFFFFFu;  // padding / dropped points: sort to the end of their scan
+
+__global__ void __launch_bounds__(256)
+    vb_keys_kernel(const float4 *__restrict__ raw, const uint32_t *__restrict__ tile_scan,
+                   const uint32_t *__restrict__ meta, const int32_t *__restrict__ vgrid, float inv,
+                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t n_slots)
+{
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= n_slots) return;
+    const uint32_t s = tile_scan[slot / kTile];
+    const uint32_t n = meta[5 * s + 1], pt_begin = meta[5 * s + 2];
+    const uint32_t row = slot - pt_begin;
+    uint32_t k = kDeadKey;
     if (row < n) {
         const int32_t *g = vgrid + 8 * s;
-        const float4 p = raw[(size_t)pt_begin + row];
+        const float4 p = raw[slot];
         if (g[6]) {
-            k = ((unsigned long long)s << 32) | row;  // refused: every point is its own voxel
+            k = row;  // refused: every point is its own voxel
         } else if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
             const int i0 = (int)__fsub_rn(floorf(__fmul_rn(p.x, inv)), (float)g[0]);
             const int i1 = (int)__fsub_rn(floorf(__fmul_rn(p.y, inv)), (float)g[1]);
             const int i2 = (int)__fsub_rn(floorf(__fmul_rn(p.z, inv)), (float)g[2]);
-            k = ((unsigned long long)s << 32) | (uint32_t)(i0 + i1 * g[3] + i2 * g[3] * g[4]);
+            k = (uint32_t)(i0 + i1 * g[3] + i2 * g[3] * g[4]);  // < 2^31 (PCL's overflow guard)
         }
     }
     keys[slot] = k;
-    vals[slot] = (uint32_t)slot;
+    vals[slot] = slot;
 }
 
+// flags[j] = 1 on the first element of every voxel run; flags[n_slots] = 0 (so the exclusive
+// scan also yields the total)
 __global__ void __launch_bounds__(256)
-    vb_flags_kernel(const unsigned long long *__restrict__ keys, uint32_t n_slots, uint32_t n_scans,
-                    uint32_t *__restrict__ flags)
+    vb_flags_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ tile_scan,
+                    const uint32_t *__restrict__ meta, uint32_t n_slots, uint32_t *__restrict__ flags)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_slots) return;
-    const unsigned long long k = keys[j];
-    const bool live = (uint32_t)(k >> 32) < n_scans;
-    flags[j] = (live && (j == 0 || keys[j - 1] != k)) ? 1u : 0u;
-}
-
-// first_run[s] = id of the first run (voxel) of scan s: written by the one element where the
-// scan id changes in the sorted order -- no contended atomics
-__global__ void __launch_bounds__(256)
-    vb_runs_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ flags,
-                   const uint32_t *__restrict__ scan, uint32_t n_slots, uint32_t n_scans, uint32_t *first_run,
-                   uint32_t *total_runs)
-{
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_slots) return;
-    const uint32_t s = (uint32_t)(keys[j] >> 32);
-    const uint32_t sp = j ? (uint32_t)(keys[j - 1] >> 32) : 0xFFFFFFFFu;
-    if (s != sp) {
-        if (s < n_scans) first_run[s] = scan[j];
-        else *total_runs = scan[j];  // first dropped / padding element: every live run lies before it
+    if (j > n_slots) return;
+    uint32_t f = 0;
+    if (j < n_slots) {
+        const uint32_t k = keys[j];
+        if (k != kDeadKey) {
+            const uint32_t s = tile_scan[j / kTile];
+            f = (j == meta[5 * s + 2] || keys[j - 1] != k) ? 1u : 0u;
+        }
     }
-    if (j == n_slots - 1 && s < n_scans) *total_runs = scan[j] + flags[j];
-}
-
-// n_out[s] = first_run[next non-empty scan] - first_run[s]
-__global__ void vb_nout_kernel(const uint32_t *__restrict__ first_run, const uint32_t *__restrict__ total_runs,
-                               uint32_t n_scans, uint32_t *__restrict__ n_out)
-{
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_scans) return;
-    const uint32_t f = first_run[s];
-    if (f == 0xFFFFFFFFu) { n_out[s] = 0; return; }
-    uint32_t nxt = *total_runs;
-    for (uint32_t t = s + 1; t < n_scans; ++t)
-        if (first_run[t] != 0xFFFFFFFFu) { nxt = first_run[t]; break; }
-    n_out[s] = nxt - f;
+    flags[j] = f;
 }
 
 __global__ void __launch_bounds__(128)
-    vb_centroid_kernel(const float4 *__restrict__ raw, const unsigned long long *__restrict__ keys,
+    vb_centroid_kernel(const float4 *__restrict__ raw, const uint32_t *__restrict__ keys,
                        const uint32_t *__restrict__ vals, const uint32_t *__restrict__ flags,
-                       const uint32_t *__restrict__ scan, uint32_t n_slots, const uint32_t *__restrict__ meta,
-                       const uint32_t *__restrict__ first_run, float4 *__restrict__ src)
+                       const uint32_t *__restrict__ scan, uint32_t n_slots, const uint32_t *__restrict__ tile_scan,
+                       const uint32_t *__restrict__ meta, float4 *__restrict__ src)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_slots || !flags[j]) return;
-    const unsigned long long k = keys[j];
-    const uint32_t s = (uint32_t)(k >> 32);
+    const uint32_t k = keys[j];
+    const uint32_t s = tile_scan[j / kTile];
+    const uint32_t pt_begin = meta[5 * s + 2], seg_end = pt_begin + meta[5 * s + 4] * kTile;
     float cx = 0.f, cy = 0.f, cz = 0.f;
     uint32_t e = j;
-    while (e < n_slots && keys[e] == k) {
+    while (e < seg_end && keys[e] == k) {
         const float4 p = raw[vals[e]];
         cx = __fadd_rn(cx, p.x);
         cy = __fadd_rn(cy, p.y);
@@ -312,14 +301,18 @@ __global__ void __launch_bounds__(128)
         ++e;
     }
     const float cnt = (float)(e - j);
-    const uint32_t out = meta[5 * s + 2] + (scan[j] - first_run[s]);
+    const uint32_t out = pt_begin + (scan[j] - scan[pt_begin]);
     src[out] = make_float4(__fdiv_rn(cx, cnt), __fdiv_rn(cy, cnt), __fdiv_rn(cz, cnt), 1.0f);
 }
 
-__global__ void vb_counts_kernel(ScanState *st, const uint32_t *__restrict__ n_out, uint32_t n_scans)
+// centroids of scan s = voxel runs that start inside its slot range
+__global__ void vb_counts_kernel(ScanState *st, const uint32_t *__restrict__ scan, const uint32_t *__restrict__ meta,
+                                 uint32_t n_scans, int have_runs)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < n_scans) st[s].n_pts = n_out[s];
+    if (s >= n_scans) return;
+    const uint32_t pt_begin = meta[5 * s + 2], seg_end = pt_begin + meta[5 * s + 4] * kTile;
+    st[s].n_pts = have_runs ? scan[seg_end] - scan[pt_begin] : 0u;
 }
 
 int voxel_downsample_batch(BatchBuffers &b, const uint32_t *meta_dev, float leaf, Scratch &s, cudaStream_t st)
@@ -328,43 +321,36 @@ int voxel_downsample_batch(BatchBuffers &b, const uint32_t *meta_dev, float leaf
     if (n_scans == 0) return SSF_OK;
     SSF_TRY(b.vbox.reserve((size_t)8 * n_scans));
     SSF_TRY(b.vgrid.reserve((size_t)8 * n_scans));
-    SSF_TRY(b.vflags.reserve((size_t)n_slots + 2 * n_scans + 4));
+    SSF_TRY(b.vflags.reserve((size_t)n_slots + 1));
     SSF_TRY(b.vscan.reserve((size_t)n_slots + 1));
     SSF_TRY(b.vkeys.reserve((size_t)n_slots + 1));
     SSF_TRY(b.vvals.reserve((size_t)n_slots + 1));
     int *vbox = reinterpret_cast<int *>(b.vbox.p);
-    uint32_t *n_out = b.vflags.p + n_slots, *first_run = n_out + n_scans, *total_runs = first_run + n_scans;
     const float inv = 1.0f / leaf;
     const unsigned sb = (n_scans + 127) / 128;
-    vb_init_kernel<<<sb, 128, 0, st>>>(vbox, n_out, first_run, n_scans);
+    vb_init_kernel<<<sb, 128, 0, st>>>(vbox, n_scans);
     SSF_LAUNCHED();
     if (tiles > 0) {
+        const uint32_t n_sort_tiles = n_slots / kSlotAlign;
+        SSF_TRY(b.vseg.reserve(n_sort_tiles));
         vb_bbox_kernel<<<tiles, kTile, 0, st>>>(b.raw.p, b.tile_scan.p, meta_dev, vbox);
         SSF_LAUNCHED();
-    }
-    vb_grid_kernel<<<sb, 128, 0, st>>>(vbox, b.vgrid.p, n_scans, inv);
-    SSF_LAUNCHED();
-    if (tiles > 0) {
-        vb_keys_kernel<<<tiles, kTile, 0, st>>>(b.raw.p, b.tile_scan.p, meta_dev, b.vgrid.p, inv, n_scans, b.vkeys.p,
-                                                b.vvals.p);
+        vb_grid_kernel<<<sb, 128, 0, st>>>(vbox, b.vgrid.p, n_scans, inv);
         SSF_LAUNCHED();
-        int scan_bits = 0;
-        while ((1u << scan_bits) <= n_scans) ++scan_bits;
-        SSF_TRY(radix_sort_pairs_u64(b.vkeys.p, b.vvals.p, n_slots, 32 + scan_bits, s, st));
-        const unsigned fb = (n_slots + 255) / 256;
-        vb_flags_kernel<<<fb, 256, 0, st>>>(b.vkeys.p, n_slots, n_scans, b.vflags.p);
+        vb_seg_kernel<<<(n_sort_tiles + 127) / 128, 128, 0, st>>>(b.tile_scan.p, meta_dev, n_sort_tiles, b.vseg.p);
         SSF_LAUNCHED();
-        SSF_TRY(exclusive_scan_u32(b.vflags.p, b.vscan.p, n_slots, nullptr, s, st));
-        SSF_CUDA(cudaMemsetAsync(total_runs, 0, sizeof(uint32_t), st));
-        vb_runs_kernel<<<fb, 256, 0, st>>>(b.vkeys.p, b.vflags.p, b.vscan.p, n_slots, n_scans, first_run, total_runs);
+        const unsigned fb = (n_slots + 256) / 256;  // n_slots + 1 elements
+        vb_keys_kernel<<<fb, 256, 0, st>>>(b.raw.p, b.tile_scan.p, meta_dev, b.vgrid.p, inv, b.vkeys.p, b.vvals.p, n_slots);
         SSF_LAUNCHED();
-        vb_nout_kernel<<<sb, 128, 0, st>>>(first_run, total_runs, n_scans, n_out);
+        SSF_TRY(seg_radix_sort_pairs_u32(b.vkeys.p, b.vvals.p, n_slots, b.vseg.p, s, st));
+        vb_flags_kernel<<<fb, 256, 0, st>>>(b.vkeys.p, b.tile_scan.p, meta_dev, n_slots, b.vflags.p);
         SSF_LAUNCHED();
+        SSF_TRY(exclusive_scan_u32(b.vflags.p, b.vscan.p, (size_t)n_slots + 1, nullptr, s, st));
         vb_centroid_kernel<<<(n_slots + 127) / 128, 128, 0, st>>>(b.raw.p, b.vkeys.p, b.vvals.p, b.vflags.p, b.vscan.p,
-                                                                 n_slots, meta_dev, first_run, b.src.p);
+                                                                 n_slots, b.tile_scan.p, meta_dev, b.src.p);
         SSF_LAUNCHED();
     }
-    vb_counts_kernel<<<sb, 128, 0, st>>>(b.state.p, n_out, n_scans);
+    vb_counts_kernel<<<sb, 128, 0, st>>>(b.state.p, b.vscan.p, meta_dev, n_scans, tiles > 0 ? 1 : 0);
     SSF_LAUNCHED();
     return SSF_OK;
 }
