@@ -175,8 +175,12 @@ int radix_sort_pairs_u64(unsigned long long *keys, uint32_t *vals, size_t n, int
 // Segmented form: n a multiple of kSortTileSize; seg_of_tile[t] = (first sort tile of t's segment, tiles in it).
 // Every segment is sorted on its own (all 32 key bits), in place.
 constexpr int kSortTileSize = 2048;
-int seg_radix_sort_pairs_u32(uint32_t *keys, uint32_t *vals, size_t n, const uint2 *seg_of_tile, Scratch &s,
-                             cudaStream_t st);
+// segs[i] = (first sort tile, tiles, base offset of the segment's slot range, unused), n_segs segments.
+int seg_radix_sort_pairs_u32(uint32_t *keys, uint32_t *vals, size_t n, const uint2 *seg_of_tile, const uint4 *segs,
+                             uint32_t n_segs, Scratch &s, cudaStream_t st);
+// in-place exclusive scan of per-tile counts (entries_per_tile per sort tile), every segment on its
+// own and starting at its base offset
+int seg_scan_u32(uint32_t *counts, const uint4 *segs, uint32_t n_segs, uint32_t entries_per_tile, cudaStream_t st);
 // bbox[0..2] = min xyz, bbox[3..5] = max xyz over finite points (device array of 6 floats);
 // n_finite (device) = number of finite points.
 int bbox_finite(const float4 *pts, size_t n, float *bbox_dev, uint32_t *n_finite_dev, cudaStream_t st);

@@ -53,6 +53,9 @@ struct BatchBuffers {
     DevBuf<uint32_t> vkeys;
     DevBuf<uint32_t> vvals;
     DevBuf<uint2> vseg;            // per sort tile: (first tile of its scan, tiles in it)
+    DevBuf<uint4> vsegs;           // per scan: (first sort tile, sort tiles, 0, 0): run ids restart per scan
+    DevBuf<uint4> vsegs_sort;      // per scan: (first sort tile, sort tiles, first slot, 0)
+    DevBuf<uint32_t> vruns;        // per sort tile: voxel runs starting in it, then their exclusive scan
     DevBuf<uint32_t> vflags, vscan;
     DevBuf<float> vbox;            // per scan: min xyz, max xyz (ordered ints during reduce)
     DevBuf<int32_t> vgrid;         // per scan: minb[3], divb[3], refused, pad

@@ -315,8 +315,45 @@ __global__ void __launch_bounds__(kSortThreads)
     }
 }
 
-int seg_radix_sort_pairs_u32(uint32_t *keys, uint32_t *vals, size_t n, const uint2 *seg_of_tile, Scratch &s,
-                             cudaStream_t st)
+// in-place exclusive scan of every segment's [digit][tile] counts, starting at the segment's base
+// offset (a segment keeps its slot range): one block per segment, 4096 counts per trip
+__global__ void __launch_bounds__(kScanThreads)
+    seg_scan_kernel(uint32_t *__restrict__ ghist, const uint4 *__restrict__ segs, uint32_t entries_per_tile)
+{
+    __shared__ uint32_t s_total;
+    const uint4 sg = segs[blockIdx.x];  // first tile, tiles, base offset
+    uint32_t *h = ghist + (size_t)entries_per_tile * sg.x;
+    const uint32_t n = entries_per_tile * sg.y;
+    uint32_t carry = sg.z;
+    for (uint32_t off = 0; off < n; off += kScanTile) {
+        const uint32_t base = off + threadIdx.x * kScanItems;
+        uint32_t v[kScanItems], sum = 0;
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            v[i] = base + i < n ? h[base + i] : 0u;
+            sum += v[i];
+        }
+        uint32_t prefix = block_excl_scan_256(sum, &s_total) + carry;
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            if (base + i < n) h[base + i] = prefix;
+            prefix += v[i];
+        }
+        carry += s_total;
+        __syncthreads();
+    }
+}
+
+int seg_scan_u32(uint32_t *counts, const uint4 *segs, uint32_t n_segs, uint32_t entries_per_tile, cudaStream_t st)
+{
+    if (n_segs == 0) return SSF_OK;
+    seg_scan_kernel<<<n_segs, kScanThreads, 0, st>>>(counts, segs, entries_per_tile);
+    SSF_LAUNCHED();
+    return SSF_OK;
+}
+
+int seg_radix_sort_pairs_u32(uint32_t *keys, uint32_t *vals, size_t n, const uint2 *seg_of_tile, const uint4 *segs,
+                             uint32_t n_segs, Scratch &s, cudaStream_t st)
 {
     if (n == 0) return SSF_OK;
     if (n % kSortTile != 0 || n >= (size_t)1 << 32) {
@@ -333,7 +370,7 @@ int seg_radix_sort_pairs_u32(uint32_t *keys, uint32_t *vals, size_t n, const uin
         const int shift = 8 * p;
         seg_hist_kernel<<<n_tiles, kSortThreads, 0, st>>>(kin, shift, seg_of_tile, s.hist.p);
         SSF_LAUNCHED();
-        SSF_TRY(exclusive_scan_u32(s.hist.p, s.hist.p, (size_t)256 * n_tiles, nullptr, s, st));
+        SSF_TRY(seg_scan_u32(s.hist.p, segs, n_segs, 256, st));
         seg_scatter_kernel<<<n_tiles, kSortThreads, 0, st>>>(kin, vin, kout, vout, shift, seg_of_tile, s.hist.p);
         SSF_LAUNCHED();
         uint32_t *tk = kin; kin = kout; kout = tk;

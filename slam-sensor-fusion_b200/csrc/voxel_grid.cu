@@ -261,96 +261,183 @@ __global__ void __launch_bounds__(256)
     vals[slot] = slot;
 }
 
-// flags[j] = 1 on the first element of every voxel run; flags[n_slots] = 0 (so the exclusive
-// scan also yields the total)
-__global__ void __launch_bounds__(256)
-    vb_flags_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ tile_scan,
-                    const uint32_t *__restrict__ meta, uint32_t n_slots, uint32_t *__restrict__ flags)
+__global__ void vb_segs_kernel(const uint32_t *__restrict__ meta, uint32_t n_scans, uint4 *__restrict__ segs)
 {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j > n_slots) return;
-    uint32_t f = 0;
-    if (j < n_slots) {
-        const uint32_t k = keys[j];
+    constexpr uint32_t kPer = kSlotAlign / kTile;
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scans) return;
+    segs[s] = make_uint4(meta[5 * s + 3] / kPer, meta[5 * s + 4] / kPer, 0u, 0u);  // run ids restart at 0 per scan
+}
+
+__global__ void vb_sortsegs_kernel(const uint32_t *__restrict__ meta, uint32_t n_scans, uint4 *__restrict__ segs)
+{
+    constexpr uint32_t kPer = kSlotAlign / kTile;
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scans) return;
+    segs[s] = make_uint4(meta[5 * s + 3] / kPer, meta[5 * s + 4] / kPer, meta[5 * s + 2], 0u);  // sorted in place
+}
+
+// is sorted element j (key k) the first of its voxel run?
+__device__ __forceinline__ bool run_head(const uint32_t *__restrict__ keys, uint32_t j, uint32_t k, uint32_t seg_begin)
+{
+    return k != kDeadKey && (j == seg_begin || keys[j - 1] != k);
+}
+
+// voxel runs that start in each sort tile
+__global__ void __launch_bounds__(256)
+    vb_runcount_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ tile_scan,
+                       const uint32_t *__restrict__ meta, uint32_t *__restrict__ tile_runs)
+{
+    __shared__ uint32_t s_cnt[8];
+    const uint32_t base = blockIdx.x * kSlotAlign;
+    const uint32_t seg_begin = meta[5 * tile_scan[base / kTile] + 2];
+    uint32_t c = 0;
+    for (uint32_t l = threadIdx.x; l < (uint32_t)kSlotAlign; l += 256) {
+        const uint32_t j = base + l;
+        c += run_head(keys, j, keys[j], seg_begin) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; ++w) t += s_cnt[w];
+        tile_runs[blockIdx.x] = t;
+    }
+}
+
+// Centroids of the runs that start in one sort tile.  The tile's points are gathered into shared
+// memory by all threads (independent loads), then each run head adds its run IN ORDER -- the same
+// float chain as a sequential CPU loop -- continuing in global memory if the run crosses the tile end.
+__global__ void __launch_bounds__(256)
+    vb_centroid_kernel(const float4 *__restrict__ raw, const uint32_t *__restrict__ keys,
+                       const uint32_t *__restrict__ vals, const uint32_t *__restrict__ tile_base,
+                       const uint32_t *__restrict__ tile_scan, const uint32_t *__restrict__ meta,
+                       float4 *__restrict__ src)
+{
+    constexpr int kPerThread = kSlotAlign / 256;
+    __shared__ uint32_t s_key[kSlotAlign];
+    __shared__ float s_x[kSlotAlign], s_y[kSlotAlign], s_z[kSlotAlign];
+    __shared__ uint32_t s_warp[8];
+    const uint32_t base = blockIdx.x * kSlotAlign;
+    const uint32_t s = tile_scan[base / kTile];
+    const uint32_t seg_begin = meta[5 * s + 2], seg_end = seg_begin + meta[5 * s + 4] * kTile;
+    for (uint32_t l = threadIdx.x; l < (uint32_t)kSlotAlign; l += 256) {
+        const uint32_t k = keys[base + l];
+        s_key[l] = k;
         if (k != kDeadKey) {
-            const uint32_t s = tile_scan[j / kTile];
-            f = (j == meta[5 * s + 2] || keys[j - 1] != k) ? 1u : 0u;
+            const float4 p = raw[vals[base + l]];
+            s_x[l] = p.x; s_y[l] = p.y; s_z[l] = p.z;
         }
     }
-    flags[j] = f;
-}
-
-__global__ void __launch_bounds__(128)
-    vb_centroid_kernel(const float4 *__restrict__ raw, const uint32_t *__restrict__ keys,
-                       const uint32_t *__restrict__ vals, const uint32_t *__restrict__ flags,
-                       const uint32_t *__restrict__ scan, uint32_t n_slots, const uint32_t *__restrict__ tile_scan,
-                       const uint32_t *__restrict__ meta, float4 *__restrict__ src)
-{
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_slots || !flags[j]) return;
-    const uint32_t k = keys[j];
-    const uint32_t s = tile_scan[j / kTile];
-    const uint32_t pt_begin = meta[5 * s + 2], seg_end = pt_begin + meta[5 * s + 4] * kTile;
-    float cx = 0.f, cy = 0.f, cz = 0.f;
-    uint32_t e = j;
-    while (e < seg_end && keys[e] == k) {
-        const float4 p = raw[vals[e]];
-        cx = __fadd_rn(cx, p.x);
-        cy = __fadd_rn(cy, p.y);
-        cz = __fadd_rn(cz, p.z);
-        ++e;
+    __syncthreads();
+    // thread t owns the consecutive elements [t * kPerThread, (t + 1) * kPerThread): local run ids
+    const uint32_t l0 = threadIdx.x * kPerThread;
+    uint32_t heads = 0, cnt = 0;
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+        const uint32_t l = l0 + i, k = s_key[l];
+        const bool h = k != kDeadKey && (base + l == seg_begin || (l ? s_key[l - 1] : keys[base - 1]) != k);
+        heads |= h ? (1u << i) : 0u;
+        cnt += h ? 1u : 0u;
     }
-    const float cnt = (float)(e - j);
-    const uint32_t out = pt_begin + (scan[j] - scan[pt_begin]);
-    src[out] = make_float4(__fdiv_rn(cx, cnt), __fdiv_rn(cy, cnt), __fdiv_rn(cz, cnt), 1.0f);
+    uint32_t incl = cnt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t rank = incl - cnt + tile_base[blockIdx.x];
+    for (int w = 0; w < warp; ++w) rank += s_warp[w];
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+        if (!(heads & (1u << i))) continue;
+        uint32_t l = l0 + i;
+        const uint32_t k = s_key[l];
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        uint32_t n = 0;
+        for (; l < (uint32_t)kSlotAlign && s_key[l] == k; ++l, ++n) {
+            cx = __fadd_rn(cx, s_x[l]);
+            cy = __fadd_rn(cy, s_y[l]);
+            cz = __fadd_rn(cz, s_z[l]);
+        }
+        if (l == (uint32_t)kSlotAlign) {  // the run goes on in the next tile(s) of the same scan
+            for (uint32_t e = base + kSlotAlign; e < seg_end && keys[e] == k; ++e, ++n) {
+                const float4 p = raw[vals[e]];
+                cx = __fadd_rn(cx, p.x);
+                cy = __fadd_rn(cy, p.y);
+                cz = __fadd_rn(cz, p.z);
+            }
+        }
+        const float fn = (float)n;
+        src[seg_begin + rank] = make_float4(__fdiv_rn(cx, fn), __fdiv_rn(cy, fn), __fdiv_rn(cz, fn), 1.0f);
+        ++rank;
+    }
 }
 
-// centroids of scan s = voxel runs that start inside its slot range
-__global__ void vb_counts_kernel(ScanState *st, const uint32_t *__restrict__ scan, const uint32_t *__restrict__ meta,
+// centroids of scan s = runs that start in its tiles: last tile's base + count
+__global__ void vb_counts_kernel(ScanState *st, const uint32_t *__restrict__ tile_base,
+                                 const uint32_t *__restrict__ tile_runs, const uint4 *__restrict__ segs,
                                  uint32_t n_scans, int have_runs)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_scans) return;
-    const uint32_t pt_begin = meta[5 * s + 2], seg_end = pt_begin + meta[5 * s + 4] * kTile;
-    st[s].n_pts = have_runs ? scan[seg_end] - scan[pt_begin] : 0u;
+    uint32_t n = 0;
+    if (have_runs && segs[s].y > 0) {
+        const uint32_t last = segs[s].x + segs[s].y - 1;
+        n = tile_base[last] + tile_runs[last];
+    }
+    st[s].n_pts = n;
 }
 
 int voxel_downsample_batch(BatchBuffers &b, const uint32_t *meta_dev, float leaf, Scratch &s, cudaStream_t st)
 {
     const uint32_t n_scans = (uint32_t)b.n_scans, n_slots = (uint32_t)b.n_slots, tiles = (uint32_t)b.n_tiles;
     if (n_scans == 0) return SSF_OK;
+    const uint32_t n_sort_tiles = n_slots / kSlotAlign;
     SSF_TRY(b.vbox.reserve((size_t)8 * n_scans));
     SSF_TRY(b.vgrid.reserve((size_t)8 * n_scans));
-    SSF_TRY(b.vflags.reserve((size_t)n_slots + 1));
-    SSF_TRY(b.vscan.reserve((size_t)n_slots + 1));
     SSF_TRY(b.vkeys.reserve((size_t)n_slots + 1));
     SSF_TRY(b.vvals.reserve((size_t)n_slots + 1));
+    SSF_TRY(b.vseg.reserve((size_t)n_sort_tiles + 1));
+    SSF_TRY(b.vsegs.reserve(n_scans));
+    SSF_TRY(b.vruns.reserve((size_t)2 * n_sort_tiles + 2));
     int *vbox = reinterpret_cast<int *>(b.vbox.p);
+    uint32_t *tile_runs = b.vruns.p, *tile_base = b.vruns.p + n_sort_tiles + 1;
     const float inv = 1.0f / leaf;
     const unsigned sb = (n_scans + 127) / 128;
     vb_init_kernel<<<sb, 128, 0, st>>>(vbox, n_scans);
     SSF_LAUNCHED();
+    vb_segs_kernel<<<sb, 128, 0, st>>>(meta_dev, n_scans, b.vsegs.p);
+    SSF_LAUNCHED();
     if (tiles > 0) {
-        const uint32_t n_sort_tiles = n_slots / kSlotAlign;
-        SSF_TRY(b.vseg.reserve(n_sort_tiles));
         vb_bbox_kernel<<<tiles, kTile, 0, st>>>(b.raw.p, b.tile_scan.p, meta_dev, vbox);
         SSF_LAUNCHED();
         vb_grid_kernel<<<sb, 128, 0, st>>>(vbox, b.vgrid.p, n_scans, inv);
         SSF_LAUNCHED();
         vb_seg_kernel<<<(n_sort_tiles + 127) / 128, 128, 0, st>>>(b.tile_scan.p, meta_dev, n_sort_tiles, b.vseg.p);
         SSF_LAUNCHED();
-        const unsigned fb = (n_slots + 256) / 256;  // n_slots + 1 elements
-        vb_keys_kernel<<<fb, 256, 0, st>>>(b.raw.p, b.tile_scan.p, meta_dev, b.vgrid.p, inv, b.vkeys.p, b.vvals.p, n_slots);
+        vb_keys_kernel<<<(n_slots + 255) / 256, 256, 0, st>>>(b.raw.p, b.tile_scan.p, meta_dev, b.vgrid.p, inv, b.vkeys.p,
+                                                            b.vvals.p, n_slots);
         SSF_LAUNCHED();
-        SSF_TRY(seg_radix_sort_pairs_u32(b.vkeys.p, b.vvals.p, n_slots, b.vseg.p, s, st));
-        vb_flags_kernel<<<fb, 256, 0, st>>>(b.vkeys.p, b.tile_scan.p, meta_dev, n_slots, b.vflags.p);
+        // the sort's own segment table carries each scan's first SLOT as base offset
+        SSF_TRY(b.vsegs_sort.reserve(n_scans));
+        vb_sortsegs_kernel<<<sb, 128, 0, st>>>(meta_dev, n_scans, b.vsegs_sort.p);
         SSF_LAUNCHED();
-        SSF_TRY(exclusive_scan_u32(b.vflags.p, b.vscan.p, (size_t)n_slots + 1, nullptr, s, st));
-        vb_centroid_kernel<<<(n_slots + 127) / 128, 128, 0, st>>>(b.raw.p, b.vkeys.p, b.vvals.p, b.vflags.p, b.vscan.p,
-                                                                 n_slots, b.tile_scan.p, meta_dev, b.src.p);
+        SSF_TRY(seg_radix_sort_pairs_u32(b.vkeys.p, b.vvals.p, n_slots, b.vseg.p, b.vsegs_sort.p, n_scans, s, st));
+        vb_runcount_kernel<<<n_sort_tiles, 256, 0, st>>>(b.vkeys.p, b.tile_scan.p, meta_dev, tile_runs);
+        SSF_LAUNCHED();
+        SSF_CUDA(cudaMemcpyAsync(tile_base, tile_runs, (size_t)n_sort_tiles * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        SSF_TRY(seg_scan_u32(tile_base, b.vsegs.p, n_scans, 1, st));
+        vb_centroid_kernel<<<n_sort_tiles, 256, 0, st>>>(b.raw.p, b.vkeys.p, b.vvals.p, tile_base, b.tile_scan.p, meta_dev,
+                                                        b.src.p);
         SSF_LAUNCHED();
     }
-    vb_counts_kernel<<<sb, 128, 0, st>>>(b.state.p, b.vscan.p, meta_dev, n_scans, tiles > 0 ? 1 : 0);
+    vb_counts_kernel<<<sb, 128, 0, st>>>(b.state.p, tile_base, tile_runs, b.vsegs.p, n_scans, tiles > 0 ? 1 : 0);
     SSF_LAUNCHED();
     return SSF_OK;
 }
