@@ -47,18 +47,22 @@ struct ssf_batch {
     ssf_icp *icp = nullptr;
     BatchBuffers buf;
     size_t max_scans = 0, max_points = 0;
-    DevBuf<float> T_init_dev;
+    PinnedBuf<float> T_init_pinned;  // initial transforms: pinned host memory the device reads directly (see set_initial)
     DevBuf<uint32_t> meta_dev;  // per scan: raw_begin, n_raw, pt_begin, tile_begin, tile_cap
     std::vector<uint32_t> meta_host;
+    PinnedBuf<uint32_t> meta_pinned;     // what the device copy reads (pageable sources make cudaMemcpyAsync synchronise)
+    PinnedBuf<ssf_icp_result> res_pinned;
     std::vector<uint32_t> n_raw;
     size_t total_points = 0;
     bool uploaded = false, initial_set = false, ran = false;
+    bool ever_ran = false;  // ran_ev has been recorded at least once
     bool uploaded_raw = false;  // scans went to buf.raw (voxel stage in front of the loop)
     float last_ms = 0.f;
     // copies run on their own stream so the upload of one batch overlaps the alignment of another
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t uploaded_ev = nullptr, ran_ev = nullptr, ev0 = nullptr, ev1 = nullptr;
     DevBuf<unsigned char> stage;  // raw bytes of the caller's scans before packing
+    cudaEvent_t dbg[4] = {nullptr, nullptr, nullptr, nullptr};  // SSF_DEBUG_TIMING: H2D begin/end, pack end
 };
 
 struct ssf_icp {
@@ -655,7 +659,7 @@ extern "C" int ssf_batch_create(ssf_icp *icp, size_t max_scans, size_t max_total
     chk(b->buf.state.reserve(max_scans));
     chk(b->buf.sums.reserve(max_scans * kAccum));
     chk(b->buf.results.reserve(max_scans));
-    chk(b->T_init_dev.reserve(max_scans * 16));
+    chk(b->T_init_pinned.reserve(max_scans * 16));
     chk(b->meta_dev.reserve(max_scans * 5));
     if (rc == SSF_OK && (cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
                          cudaEventCreateWithFlags(&b->uploaded_ev, cudaEventDisableTiming) != cudaSuccess ||
@@ -722,13 +726,20 @@ static int batch_upload_impl(ssf_batch *b, const float *xyz, const size_t *n_pts
     b->buf.n_tiles = tile;
     b->buf.n_slots = tile * kTile;
     b->total_points = total;
-    // meta_host is pageable: cudaMemcpyAsync returns once it has been staged, so it may be reused
-    SSF_CUDA(cudaMemcpyAsync(b->meta_dev.p, b->meta_host.data(), b->meta_host.size() * sizeof(uint32_t),
+    // pinned copy of the table: a pageable source would make the "async" copy synchronise the stream
+    SSF_TRY(b->meta_pinned.reserve(b->meta_host.size()));
+    if (b->uploaded) SSF_CUDA(cudaEventSynchronize(b->uploaded_ev));  // the previous upload may still read it
+    memcpy(b->meta_pinned.p, b->meta_host.data(), b->meta_host.size() * sizeof(uint32_t));
+    SSF_CUDA(cudaMemcpyAsync(b->meta_dev.p, b->meta_pinned.p, b->meta_host.size() * sizeof(uint32_t),
                              cudaMemcpyHostToDevice, cs));
     if (total > 0) {
         const size_t bytes = (total - 1) * stride_bytes + 12;
         SSF_TRY(b->stage.reserve(bytes));
+        static const bool dbg = getenv("SSF_DEBUG_TIMING") != nullptr;
+        if (dbg && !b->dbg[0]) for (auto &e : b->dbg) cudaEventCreate(&e);
+        if (dbg) cudaEventRecord(b->dbg[0], cs);
         SSF_CUDA(cudaMemcpyAsync(b->stage.p, xyz, bytes, cudaMemcpyHostToDevice, cs));
+        if (dbg) cudaEventRecord(b->dbg[1], cs);
         unsigned bx = (max_n + 255) / 256;
         if (bx > 64) bx = 64;
         if (bx == 0) bx = 1;
@@ -743,6 +754,7 @@ static int batch_upload_impl(ssf_batch *b, const float *xyz, const size_t *n_pts
     b->uploaded_raw = b->icp->prm.source_voxel_leaf > 0.f;
     layout_kernel<<<(unsigned)n_scans, 128, 0, cs>>>(b->buf.state.p, b->meta_dev.p, (uint32_t)n_scans, b->buf.tile_scan.p);
     SSF_LAUNCHED();
+    if (b->dbg[2]) cudaEventRecord(b->dbg[2], cs);
     SSF_CUDA(cudaEventRecord(b->uploaded_ev, cs));
     if (wait) SSF_CUDA(cudaStreamSynchronize(cs));  // the caller's buffer is free again
     b->uploaded = true;
@@ -772,11 +784,12 @@ extern "C" int ssf_batch_set_initial(ssf_batch *b, const float *T_colmajor)
     }
     ssf_ctx *ctx = b->icp->ctx;
     SSF_TRY(use_device(ctx));
-    if (b->ran) SSF_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ran_ev, 0));
-    // small (64 B per scan): staged by the runtime when pageable, so the caller's array is free on return
-    SSF_CUDA(cudaMemcpyAsync(b->T_init_dev.p, T_colmajor, b->buf.n_scans * 16 * sizeof(float), cudaMemcpyHostToDevice,
-                             b->copy_stream));
-    SSF_CUDA(cudaEventRecord(b->uploaded_ev, b->copy_stream));
+    // 64 B per scan.  NOT a copy-engine transfer: a small H2D copy queued here would sit behind the
+    // other batch's large scan upload on the copy engine and hold this batch's alignment back for
+    // the whole of it.  The transforms go to pinned host memory instead, which init_states_kernel
+    // reads directly (zero-copy, a few KB).
+    if (b->ever_ran) SSF_CUDA(cudaEventSynchronize(b->ran_ev));  // a previous alignment may still read them
+    memcpy(b->T_init_pinned.p, T_colmajor, b->buf.n_scans * 16 * sizeof(float));
     b->initial_set = true;
     return SSF_OK;
 }
@@ -813,7 +826,7 @@ extern "C" int ssf_batch_run(ssf_batch *b)
     SSF_CUDA(cudaEventRecord(b->ev0, ctx->stream));
     if (p.source_voxel_leaf > 0.f && b->total_points > 0)
         SSF_TRY(voxel_downsample_batch(buf, b->meta_dev.p, p.source_voxel_leaf, ctx->scratch, ctx->stream));
-    SSF_TRY(init_states(buf, b->T_init_dev.p, ctx->stream));
+    SSF_TRY(init_states(buf, b->T_init_pinned.p, ctx->stream));
     IcpConfig cfg{p.max_correspondence_dist, p.num_iterations, p.acceptable_mean_error, p.transformation_epsilon,
                   p.mode, p.reduce};
     if (icp->map.sharded) {
@@ -824,6 +837,7 @@ extern "C" int ssf_batch_run(ssf_batch *b)
     SSF_CUDA(cudaEventRecord(b->ev1, ctx->stream));
     SSF_CUDA(cudaEventRecord(b->ran_ev, ctx->stream));
     b->ran = true;
+    b->ever_ran = true;
     return SSF_OK;
 }
 
@@ -840,15 +854,26 @@ extern "C" int ssf_batch_results(ssf_batch *b, ssf_icp_result *out, size_t n_sca
     // D2H on the batch's copy stream: waits for THIS batch's alignment only, so another batch may
     // keep the compute stream busy meanwhile
     SSF_CUDA(cudaStreamWaitEvent(b->copy_stream, b->ran_ev, 0));
-    SSF_CUDA(cudaMemcpyAsync(out, b->buf.results.p, n_scans * sizeof(ssf_icp_result), cudaMemcpyDeviceToHost,
+    SSF_TRY(b->res_pinned.reserve(n_scans ? n_scans : 1));
+    SSF_CUDA(cudaMemcpyAsync(b->res_pinned.p, b->buf.results.p, n_scans * sizeof(ssf_icp_result), cudaMemcpyDeviceToHost,
                              b->copy_stream));
     SSF_CUDA(cudaStreamSynchronize(b->copy_stream));
+    memcpy(out, b->res_pinned.p, n_scans * sizeof(ssf_icp_result));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) != cudaSuccess) {
         cudaGetLastError();
         ms = 0.f;
     }
     b->last_ms = ms;
+    if (b->dbg[2]) {  // timeline relative to the start of this batch's H2D copy
+        float t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+        cudaEventElapsedTime(&t1, b->dbg[0], b->dbg[1]);
+        cudaEventElapsedTime(&t2, b->dbg[0], b->dbg[2]);
+        cudaEventElapsedTime(&t3, b->dbg[0], b->ev0);
+        cudaEventElapsedTime(&t4, b->dbg[0], b->ev1);
+        fprintf(stderr, "[ssf timing] batch %p: H2D end %.3f  pack end %.3f  run begin %.3f  run end %.3f ms\n", (void *)b, t1,
+                t2, t3, t4);
+    }
     for (size_t s = 0; s < n_scans; ++s) out[s].device_ms = ms;
     return SSF_OK;
 }

@@ -143,6 +143,12 @@ __device__ __forceinline__ void tile_bar_wait(unsigned long long *bar, uint32_t 
     }
 }
 
+__global__ void zero_u32_kernel(uint32_t *p, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0;
+}
+
 // list of the tiles that hold points (a scan's slots are sized for its RAW points; after the voxel
 // stage only the first ceil(n_pts / kTile) tiles of each scan are in use)
 __global__ void __launch_bounds__(128)
@@ -902,7 +908,11 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
         if (grid > tiles) grid = tiles;
         SSF_TRY(b.active.reserve(tiles));
         SSF_TRY(b.counters.reserve((size_t)cfg.num_iterations + 3));
-        SSF_CUDA(cudaMemsetAsync(b.counters.p, 0, ((size_t)cfg.num_iterations + 3) * sizeof(uint32_t), st));
+        // (zeroed by a kernel: memsets and copies on the compute stream can queue behind the other
+        // batch's H2D copy on a copy engine and stall the pipeline)
+        zero_u32_kernel<<<(unsigned)((cfg.num_iterations + 3 + 255) / 256), 256, 0, st>>>(b.counters.p,
+                                                                                          (uint32_t)cfg.num_iterations + 3);
+        SSF_LAUNCHED();
         active_tiles_kernel<<<(scans + 127) / 128, 128, 0, st>>>(S, scans, b.active.p, b.counters.p);
         SSF_LAUNCHED();
     }

@@ -286,7 +286,8 @@ __device__ __forceinline__ bool run_head(const uint32_t *__restrict__ keys, uint
 // voxel runs that start in each sort tile
 __global__ void __launch_bounds__(256)
     vb_runcount_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ tile_scan,
-                       const uint32_t *__restrict__ meta, uint32_t *__restrict__ tile_runs)
+                       const uint32_t *__restrict__ meta, uint32_t *__restrict__ tile_runs,
+                       uint32_t *__restrict__ tile_base)
 {
     __shared__ uint32_t s_cnt[8];
     const uint32_t base = blockIdx.x * kSlotAlign;
@@ -304,6 +305,7 @@ __global__ void __launch_bounds__(256)
         uint32_t t = 0;
         for (int w = 0; w < 8; ++w) t += s_cnt[w];
         tile_runs[blockIdx.x] = t;
+        tile_base[blockIdx.x] = t;  // scanned in place afterwards (no copy-engine work on the compute stream)
     }
 }
 
@@ -429,9 +431,8 @@ int voxel_downsample_batch(BatchBuffers &b, const uint32_t *meta_dev, float leaf
         vb_sortsegs_kernel<<<sb, 128, 0, st>>>(meta_dev, n_scans, b.vsegs_sort.p);
         SSF_LAUNCHED();
         SSF_TRY(seg_radix_sort_pairs_u32(b.vkeys.p, b.vvals.p, n_slots, b.vseg.p, b.vsegs_sort.p, n_scans, s, st));
-        vb_runcount_kernel<<<n_sort_tiles, 256, 0, st>>>(b.vkeys.p, b.tile_scan.p, meta_dev, tile_runs);
+        vb_runcount_kernel<<<n_sort_tiles, 256, 0, st>>>(b.vkeys.p, b.tile_scan.p, meta_dev, tile_runs, tile_base);
         SSF_LAUNCHED();
-        SSF_CUDA(cudaMemcpyAsync(tile_base, tile_runs, (size_t)n_sort_tiles * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         SSF_TRY(seg_scan_u32(tile_base, b.vsegs.p, n_scans, 1, st));
         vb_centroid_kernel<<<n_sort_tiles, 256, 0, st>>>(b.raw.p, b.vkeys.p, b.vvals.p, tile_base, b.tile_scan.p, meta_dev,
                                                         b.src.p);
