@@ -8,12 +8,13 @@
 // scans that are done.
 //
 //   search_accum_kernel<GN|KABSCH>  transform + exact NN + rejection + per-block partial sums
-//   solve_gn_kernel / solve_o3d_kernel   ordered sum of the partial rows + 6x6 Cholesky or
+//   rowsum_solve_kernel (rowsum_kernel + solve_kernel when map-sharded)   ordered sum of the partial rows + 6x6 Cholesky or
 //                                         3x3 SVD + pose update + stop rules
 //   ref_search_kernel / ref_reduce_kernel / ref_step_kernel   the reference's own state
 //                                         machine, STRICT (sequential float chains) or FAST
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 
 #include "icp.cuh"
 #include "nn_device.cuh"
@@ -421,15 +422,9 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const ScanState *__restrict
     }
 }
 
-__global__ void __launch_bounds__(32) solve_gn_kernel(ScanState *states, const double *__restrict__ sums, int pass,
-                                                      float acc_err, float eps)
+// one thread: normal equations -> Cholesky -> pose update -> stop rules (sv = the scan's kAccum totals)
+__device__ void gn_solve(ScanState &z, const double *sv, int pass, float acc_err, float eps)
 {
-    __shared__ double sv[kAccum];
-    ScanState &z = states[blockIdx.x];
-    if (z.done) return;
-    sv[threadIdx.x] = sums[(size_t)blockIdx.x * kAccum + threadIdx.x];
-    __syncwarp();
-    if (threadIdx.x != 0) return;
     const long long K = (long long)(sv[28] + 0.5);
     z.n_searches += 1;
     z.k_last = (int)K;
@@ -463,15 +458,8 @@ __global__ void __launch_bounds__(32) solve_gn_kernel(ScanState *states, const d
     if (mx < (double)eps) { z.converged = 1; z.done = 1; }
 }
 
-__global__ void __launch_bounds__(32) solve_o3d_kernel(ScanState *states, const double *__restrict__ sums,
-                                                       int pass, int max_iteration)
+__device__ void o3d_solve(ScanState &z, const double *sv, int pass, int max_iteration)
 {
-    __shared__ double sv[kAccum];
-    ScanState &z = states[blockIdx.x];
-    if (z.done) return;
-    sv[threadIdx.x] = sums[(size_t)blockIdx.x * kAccum + threadIdx.x];
-    __syncwarp();
-    if (threadIdx.x != 0) return;
     const long long K = (long long)(sv[0] + 0.5);
     z.n_searches += 1;
     z.k_last = (int)K;
@@ -509,6 +497,47 @@ __global__ void __launch_bounds__(32) solve_o3d_kernel(ScanState *states, const 
     }
     compose_round(Ts, z.T);
     z.iterations += 1;
+}
+
+// the sums arrive from outside (map sharding: all-reduced across ranks)
+__global__ void __launch_bounds__(32) solve_kernel(ScanState *states, const double *__restrict__ sums, int pass,
+                                                   int o3d, float acc_err, float eps, int max_iteration)
+{
+    __shared__ double sv[kAccum];
+    ScanState &z = states[blockIdx.x];
+    if (z.done) return;
+    sv[threadIdx.x] = sums[(size_t)blockIdx.x * kAccum + threadIdx.x];
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+    if (o3d) o3d_solve(z, sv, pass, max_iteration);
+    else gn_solve(z, sv, pass, acc_err, eps);
+}
+
+// single GPU: ordered sum of the scan's partial rows and the solve in one launch
+__global__ void __launch_bounds__(256)
+    rowsum_solve_kernel(ScanState *states, const double *__restrict__ partials, double *__restrict__ sums, int pass,
+                        int o3d, float acc_err, float eps, int max_iteration)
+{
+    __shared__ double sw[8][kAccum];
+    __shared__ double sv[kAccum];
+    ScanState &z = states[blockIdx.x];
+    if (z.done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double s = 0.0;
+    const uint32_t n_tiles = (z.n_pts + kTile - 1) / kTile;
+    for (uint32_t t = warp; t < n_tiles; t += 8) s += partials[(size_t)(z.tile_begin + t) * kAccum + lane];
+    sw[warp][lane] = s;
+    __syncthreads();
+    if (warp != 0) return;
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += sw[w][lane];
+    sums[(size_t)blockIdx.x * kAccum + lane] = tot;
+    sv[lane] = tot;
+    __syncwarp();
+    if (lane != 0) return;
+    if (o3d) o3d_solve(z, sv, pass, max_iteration);
+    else gn_solve(z, sv, pass, acc_err, eps);
 }
 
 // =========================================================================================
@@ -860,18 +889,26 @@ int SearchTimer::end(cudaStream_t st)
     return SSF_OK;
 }
 
-// per-scan totals of the partial rows; summed across ranks through the caller's hook when the map
-// is sharded (one small all-reduce per iteration: n_scans x 32 doubles)
-static int reduce_sums(const IcpConfig &cfg, BatchBuffers &b, cudaStream_t st)
+// per-scan totals of the partial rows and the solve.  Map sharding: the totals are summed across
+// ranks through the caller's hook (one small all-reduce per iteration: n_scans x 32 doubles) between
+// the two; otherwise both run in one launch.
+static int reduce_and_solve(const IcpConfig &cfg, BatchBuffers &b, int pass, int o3d, cudaStream_t st)
 {
+    if (!cfg.allreduce) {
+        rowsum_solve_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, b.sums.p, pass, o3d,
+                                                                 cfg.acc_err, cfg.eps, cfg.num_iterations);
+        SSF_LAUNCHED();
+        return SSF_OK;
+    }
     rowsum_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, b.sums.p);
     SSF_LAUNCHED();
-    if (cfg.allreduce) {
-        if (cfg.allreduce(cfg.allreduce_user, b.sums.p, b.n_scans * kAccum, (void *)st) != 0) {
-            set_error("all-reduce hook failed");
-            return SSF_ERR_COMM;
-        }
+    if (cfg.allreduce(cfg.allreduce_user, b.sums.p, b.n_scans * kAccum, (void *)st) != 0) {
+        set_error("all-reduce hook failed");
+        return SSF_ERR_COMM;
     }
+    solve_kernel<<<(unsigned)b.n_scans, 32, 0, st>>>(b.state.p, b.sums.p, pass, o3d, cfg.acc_err, cfg.eps,
+                                                     cfg.num_iterations);
+    SSF_LAUNCHED();
     return SSF_OK;
 }
 
@@ -895,6 +932,10 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
         return SSF_OK;
     }
     unsigned grid = 1;
+    // SSF_NO_CERT=1 turns the search certificates off (every query walks every iteration): the
+    // results must not change by a single bit (tests/test_gpu_parity.py::test_certificates_change_nothing)
+    const char *nc = getenv("SSF_NO_CERT");
+    const bool certs = !(nc && atoi(nc) != 0);
     if (cfg.mode != SSF_MODE_REFERENCE) {
         // persistent search blocks: counters[0] = number of active tiles, counters[1 + i] = fetch
         // counter of launch i
@@ -924,26 +965,22 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
         for (int i = 0; i < cfg.num_iterations; ++i) {
             if (cfg.mode == SSF_MODE_GN_P2PLANE)
                 TIMED_SEARCH((search_accum_kernel<ACC_GN_P2PLANE><<<grid, kThreads, 0, st>>>(
-                    map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p, i > 0,
+                    map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p, certs && i > 0,
                     b.active.p, b.counters.p, b.counters.p + 1 + i)));
             else
                 TIMED_SEARCH((search_accum_kernel<ACC_GN_P2P><<<grid, kThreads, 0, st>>>(
-                    map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p, i > 0,
+                    map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p, certs && i > 0,
                     b.active.p, b.counters.p, b.counters.p + 1 + i)));
             g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
-            SSF_TRY(reduce_sums(cfg, b, st));
-            solve_gn_kernel<<<scans, 32, 0, st>>>(S, b.sums.p, i, cfg.acc_err, cfg.eps);
-            SSF_LAUNCHED();
+            SSF_TRY(reduce_and_solve(cfg, b, i, 0, st));
         }
     } else if (cfg.mode == SSF_MODE_O3D_P2P) {
         for (int i = 0; i <= cfg.num_iterations; ++i) {
             TIMED_SEARCH((search_accum_kernel<ACC_KABSCH><<<grid, kThreads, 0, st>>>(
-                map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p, i > 0,
+                map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p, certs && i > 0,
                 b.active.p, b.counters.p, b.counters.p + 1 + i)));
             g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
-            SSF_TRY(reduce_sums(cfg, b, st));
-            solve_o3d_kernel<<<scans, 32, 0, st>>>(S, b.sums.p, i, cfg.num_iterations);
-            SSF_LAUNCHED();
+            SSF_TRY(reduce_and_solve(cfg, b, i, 1, st));
         }
     } else if (cfg.mode == SSF_MODE_REFERENCE) {
         if (map.own_lo != INT32_MIN || map.own_hi != INT32_MAX) {

@@ -224,6 +224,38 @@ def test_batch_matches_single(gpu, ora, small_world):
             assert (r1.iterations, r1.n_searches, r1.k_final) == (rb.iterations, rb.n_searches, rb.k_final)
 
 
+@pytest.mark.parametrize("mode", ["p2p", "p2plane", "o3d"])
+def test_certificates_change_nothing(gpu, c1_world, small_world, mode, monkeypatch):
+    """Search certificates (a query that barely moved keeps its neighbour without a walk) are an
+    exactness-preserving shortcut: with them switched off every pose, error, count and
+    correspondence must be bit-identical."""
+    from ssf_gpu import synth
+    for w, iters in ((small_world, 10), (c1_world, 30)):
+        scans, inits = [w["scan"]], [w["T0"]]
+        for k in range(3):
+            T = synth.street_pose(5 + 11 * k, half=w["half"])
+            scans.append(synth.make_scan(T, beams=16, azimuths=512, scan_id=70 + k, max_range=60.0))
+            inits.append(synth.perturb_pose(T, 70 + k))
+        out = []
+        for no_cert in ("0", "1"):
+            monkeypatch.setenv("SSF_NO_CERT", no_cert)
+            m = {"p2p": gpu.MODE_GN_P2P, "p2plane": gpu.MODE_GN_P2PLANE, "o3d": gpu.MODE_O3D_P2P}[mode]
+            icp = gpu.ICPPointToPoint(0.5, iters, 0.0, 0.0, mode=m)
+            icp.setTargetPointCloud(w["map"], w["normals"])
+            res = icp.align_batch(scans, inits)
+            icp.setSourcePointCloud(scans[0])
+            icp.setInitialTransformation(inits[0])
+            r1 = icp.calculateAlignment()
+            out.append((res, r1, icp.correspondences().copy()))
+        (ra, sa, ca), (rb, sb, cb) = out
+        assert np.array_equal(ca, cb)
+        for x, y in list(zip(ra, rb)) + [(sa, sb)]:
+            assert np.array_equal(x.transformation.view(np.uint32), y.transformation.view(np.uint32))
+            assert (x.iterations, x.n_searches, x.k_final, x.has_converged) == (y.iterations, y.n_searches, y.k_final,
+                                                                                y.has_converged)
+            assert np.float32(x.error).view(np.uint32) == np.float32(y.error).view(np.uint32)
+
+
 def test_golden_fixture(gpu):
     """CUDA path against the committed golden vectors (tests/golden/c1_mini.npz)."""
     import os
