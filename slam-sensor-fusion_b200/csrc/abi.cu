@@ -655,6 +655,7 @@ extern "C" int ssf_batch_create(ssf_icp *icp, size_t max_scans, size_t max_total
     chk(b->buf.cert_p.reserve(slots));
     chk(b->buf.cert_pos.reserve(slots));
     chk(b->buf.tile_scan.reserve(tiles));
+    b->buf.max_tiles = tiles;
     chk(b->buf.partials.reserve(tiles * kAccum));
     chk(b->buf.state.reserve(max_scans));
     chk(b->buf.sums.reserve(max_scans * kAccum));
@@ -826,14 +827,13 @@ extern "C" int ssf_batch_run(ssf_batch *b)
     SSF_CUDA(cudaEventRecord(b->ev0, ctx->stream));
     if (p.source_voxel_leaf > 0.f && b->total_points > 0)
         SSF_TRY(voxel_downsample_batch(buf, b->meta_dev.p, p.source_voxel_leaf, ctx->scratch, ctx->stream));
-    SSF_TRY(init_states(buf, b->T_init_pinned.p, ctx->stream));
     IcpConfig cfg{p.max_correspondence_dist, p.num_iterations, p.acceptable_mean_error, p.transformation_epsilon,
                   p.mode, p.reduce};
     if (icp->map.sharded) {
         cfg.allreduce = icp->allreduce;
         cfg.allreduce_user = icp->allreduce_user;
     }
-    SSF_TRY(run_batch(icp->map.view, cfg, buf, ctx->stream, &ctx->timer));
+    SSF_TRY(run_batch(icp->map.view, cfg, buf, b->T_init_pinned.p, ctx->stream, &ctx->timer));
     SSF_CUDA(cudaEventRecord(b->ev1, ctx->stream));
     SSF_CUDA(cudaEventRecord(b->ran_ev, ctx->stream));
     b->ran = true;

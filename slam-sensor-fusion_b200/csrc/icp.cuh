@@ -60,6 +60,15 @@ struct BatchBuffers {
     DevBuf<float> vbox;            // per scan: min xyz, max xyz (ordered ints during reduce)
     DevBuf<int32_t> vgrid;         // per scan: minb[3], divb[3], refused, pad
     size_t n_scans = 0, n_tiles = 0, n_slots = 0;
+    size_t max_tiles = 0;          // capacity in search tiles (fixed at creation)
+    // CUDA graph of the alignment loop, replayed while the launch shape stays the same
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<unsigned long long> graph_key;
+    uint64_t graph_kernels = 0;
+    ~BatchBuffers()
+    {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    }
     int trace_len = 0;
 };
 
@@ -87,7 +96,9 @@ struct IcpConfig {
 };
 
 // Enqueue the whole alignment of every scan in the batch on `st` (no host sync inside).
-int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStream_t st, SearchTimer *timer);
+// T_init: n_scans x 16 floats (column-major), device-readable (pinned host memory is fine).
+int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const float *T_init, cudaStream_t st,
+              SearchTimer *timer);
 // standalone search over n already-transformed queries (device pointers)
 int nn_search_device(const MapView &map, const float4 *queries, size_t n, float limit, int32_t *idx, float *d2,
                      cudaStream_t st);

@@ -15,6 +15,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdlib>
+#include <vector>
 
 #include "icp.cuh"
 #include "nn_device.cuh"
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(kThreads)
     __shared__ unsigned short s_queue[kTile], s_far[kTile];
     __shared__ unsigned long long s_key[kTile];
     __shared__ float s_b2[kTile];
-    __shared__ uint32_t s_nq, s_nfar, s_next;
+    __shared__ uint32_t s_nq, s_nfar, s_nfar_none, s_next;
     __shared__ float sT[16];
     __shared__ double sred[kThreads / 32][kAccum];
     const uint32_t none_hi = __float_as_uint(limit);
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(kThreads)
             s_next = atomicAdd(fetch, 1u);
             s_nq = 0;
             s_nfar = 0;
+            s_nfar_none = 0;
         }
         __syncthreads();
         const uint32_t ti = s_next;
@@ -286,12 +288,18 @@ __global__ void __launch_bounds__(kThreads)
             s_key[r] = key;
             s_pos[r] = pos;
             s_b2[r] = b2;
-            if (far) s_far[atomicAdd(&s_nfar, 1u)] = (unsigned short)r;
+            // two classes, filled from the two ends of the list: queries that have found nothing yet
+            // walk every row within the threshold radius and cost several times the others, so
+            // they are packed together
+            if (far) {
+                if ((uint32_t)(key >> 32) < none_hi) s_far[atomicAdd(&s_nfar, 1u)] = (unsigned short)r;
+                else s_far[kTile - 1 - atomicAdd(&s_nfar_none, 1u)] = (unsigned short)r;
+            }
         }
         __syncthreads();
-        const uint32_t nfar = s_nfar;
-        for (uint32_t i = threadIdx.x; i < nfar; i += kThreads) {
-            const uint32_t r = s_far[i];
+        const uint32_t nfar = s_nfar, nfar_none = s_nfar_none;
+        for (uint32_t i = threadIdx.x; i < nfar + nfar_none; i += kThreads) {
+            const uint32_t r = i < nfar_none ? s_far[kTile - 1 - i] : s_far[i - nfar_none];
             const float4 p = s_q[r];
             if (make_cert) {
                 NNBest<true> B;
@@ -920,9 +928,27 @@ static int reduce_and_solve(const IcpConfig &cfg, BatchBuffers &b, int pass, int
         if (timer) SSF_TRY(timer->end(st));        \
     } while (0)
 
-int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStream_t st, SearchTimer *timer)
+static int search_grid(const BatchBuffers &b, unsigned *grid)
 {
-    if (b.n_scans == 0) return SSF_OK;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        SSF_CUDA(cudaGetDevice(&dev));
+        SSF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // persistent blocks; sized by the batch CAPACITY so that the launch shape (and a captured graph)
+    // does not change with the number of points of an upload -- surplus blocks fetch once and exit
+    size_t g = (size_t)n_sm * 8u;
+    if (g > b.max_tiles) g = b.max_tiles;
+    *grid = (unsigned)(g ? g : 1);
+    return SSF_OK;
+}
+
+// the launches of one batch alignment (everything after the voxel stage), in stream order
+static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const float *T_init, bool certs,
+                         unsigned grid, cudaStream_t st, SearchTimer *timer)
+{
+    SSF_TRY(init_states(b, T_init, st));
     const unsigned tiles = (unsigned)b.n_tiles, scans = (unsigned)b.n_scans;
     const float limit = cfg.max_corr;
     ScanState *S = b.state.p;
@@ -931,24 +957,8 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
         SSF_LAUNCHED();
         return SSF_OK;
     }
-    unsigned grid = 1;
-    // SSF_NO_CERT=1 turns the search certificates off (every query walks every iteration): the
-    // results must not change by a single bit (tests/test_gpu_parity.py::test_certificates_change_nothing)
-    const char *nc = getenv("SSF_NO_CERT");
-    const bool certs = !(nc && atoi(nc) != 0);
     if (cfg.mode != SSF_MODE_REFERENCE) {
-        // persistent search blocks: counters[0] = number of active tiles, counters[1 + i] = fetch
-        // counter of launch i
-        static int n_sm = 0;
-        if (n_sm == 0) {
-            int dev = 0;
-            SSF_CUDA(cudaGetDevice(&dev));
-            SSF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        }
-        grid = (unsigned)n_sm * 8u;
-        if (grid > tiles) grid = tiles;
-        SSF_TRY(b.active.reserve(tiles));
-        SSF_TRY(b.counters.reserve((size_t)cfg.num_iterations + 3));
+        // counters[0] = number of active tiles, counters[1 + i] = fetch counter of search launch i
         // (zeroed by a kernel: memsets and copies on the compute stream can queue behind the other
         // batch's H2D copy on a copy engine and stall the pipeline)
         zero_u32_kernel<<<(unsigned)((cfg.num_iterations + 3 + 255) / 256), 256, 0, st>>>(b.counters.p,
@@ -971,7 +981,6 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
                 TIMED_SEARCH((search_accum_kernel<ACC_GN_P2P><<<grid, kThreads, 0, st>>>(
                     map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p, certs && i > 0,
                     b.active.p, b.counters.p, b.counters.p + 1 + i)));
-            g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
             SSF_TRY(reduce_and_solve(cfg, b, i, 0, st));
         }
     } else if (cfg.mode == SSF_MODE_O3D_P2P) {
@@ -979,7 +988,6 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
             TIMED_SEARCH((search_accum_kernel<ACC_KABSCH><<<grid, kThreads, 0, st>>>(
                 map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p, certs && i > 0,
                 b.active.p, b.counters.p, b.counters.p + 1 + i)));
-            g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
             SSF_TRY(reduce_and_solve(cfg, b, i, 1, st));
         }
     } else if (cfg.mode == SSF_MODE_REFERENCE) {
@@ -1012,6 +1020,85 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, cudaStr
     }
     results_kernel<<<(scans + 127) / 128, 128, 0, st>>>(S, b.results.p, scans, cfg.mode, cfg.acc_err);
     SSF_LAUNCHED();
+    return SSF_OK;
+}
+
+// The Gauss-Newton / Open3D-flow loop is a fixed launch sequence whose shape depends only on the
+// batch capacity, the scan count and the parameters -- all data-dependent control lives in device
+// state -- so it is captured once into a CUDA graph and replayed: one graph launch per alignment,
+// no host round trip, no per-kernel launch latency.  (REFERENCE mode launches per-tile grids that
+// follow the upload's point count and is enqueued directly; so are runs with the search timer or
+// the cross-rank exchange hook, which are host-side actions.)
+int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const float *T_init, cudaStream_t st,
+              SearchTimer *timer)
+{
+    if (b.n_scans == 0) return SSF_OK;
+    // SSF_NO_CERT=1 turns the search certificates off (every query walks every iteration): the
+    // results must not change by a single bit (tests/test_gpu_parity.py::test_certificates_change_nothing)
+    const char *nc = getenv("SSF_NO_CERT");
+    const bool certs = !(nc && atoi(nc) != 0);
+    unsigned grid = 1;
+    SSF_TRY(search_grid(b, &grid));
+    if (cfg.mode != SSF_MODE_REFERENCE) {  // allocations happen here, never inside a capture
+        SSF_TRY(b.active.reserve(b.max_tiles ? b.max_tiles : 1));
+        SSF_TRY(b.counters.reserve((size_t)cfg.num_iterations + 3));
+    }
+    const char *ng = getenv("SSF_NO_GRAPH");
+    const bool graphable = cfg.mode != SSF_MODE_REFERENCE && b.n_tiles > 0 && !cfg.allreduce &&
+                           !(timer && timer->enabled) && !(ng && atoi(ng) != 0);
+    if (!graphable) {
+        if (cfg.mode != SSF_MODE_REFERENCE)
+            g_queries.fetch_add((uint64_t)b.n_slots * (uint64_t)cfg.num_iterations, std::memory_order_relaxed);
+        return enqueue_batch(map, cfg, b, T_init, certs, grid, st, timer);
+    }
+
+    std::vector<unsigned long long> key;
+    auto put = [&](const void *p, size_t n) {
+        const unsigned char *c = static_cast<const unsigned char *>(p);
+        for (size_t i = 0; i < n; i += 8) {
+            unsigned long long w = 0;
+            memcpy(&w, c + i, n - i < 8 ? n - i : 8);
+            key.push_back(w);
+        }
+    };
+    put(&map, sizeof(map));
+    put(&cfg.max_corr, sizeof(float)); put(&cfg.acc_err, sizeof(float)); put(&cfg.eps, sizeof(float));
+    const unsigned long long scalars[] = {(unsigned long long)cfg.num_iterations, (unsigned long long)cfg.mode,
+                                          (unsigned long long)certs, (unsigned long long)grid, (unsigned long long)b.n_scans};
+    put(scalars, sizeof(scalars));
+    const void *ptrs[] = {b.src.p, b.corr.p, b.cert_p.p, b.cert_pos.p, b.tile_scan.p, b.active.p, b.counters.p,
+                          b.partials.p, b.sums.p, b.state.p, b.results.p, b.trace_err.p, b.trace_search.p, T_init};
+    put(ptrs, sizeof(ptrs));
+    if (!b.graph_exec || key != b.graph_key) {
+        if (b.graph_exec) {
+            cudaGraphExecDestroy(b.graph_exec);
+            b.graph_exec = nullptr;
+        }
+        cudaGraph_t graph = nullptr;
+        SSF_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const uint64_t before = g_launches.load();
+        const int rc = enqueue_batch(map, cfg, b, T_init, certs, grid, st, nullptr);
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        b.graph_kernels = g_launches.load() - before;
+        g_launches.fetch_sub(b.graph_kernels);  // counted when the graph is launched
+        if (rc != SSF_OK || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != SSF_OK) return rc;
+            set_error("stream capture failed: %s", cudaGetErrorString(ce));
+            return SSF_ERR_CUDA;
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&b.graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+            b.graph_exec = nullptr;
+            set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+            return SSF_ERR_CUDA;
+        }
+        b.graph_key = key;
+    }
+    SSF_CUDA(cudaGraphLaunch(b.graph_exec, st));
+    g_launches.fetch_add(b.graph_kernels, std::memory_order_relaxed);
+    g_queries.fetch_add((uint64_t)b.n_slots * (uint64_t)cfg.num_iterations, std::memory_order_relaxed);
     return SSF_OK;
 }
 
