@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(128)
 //   S  the queries that could not be confirmed, packed densely over the threads: full exact walk,
 //      new certificate;
 //   K4 residual / Jacobian terms of the matched queries, 32-value warp reduction paid once per kQ.
-template <int KIND>
-__global__ void __launch_bounds__(kThreads)
+template <int KIND, int THREADS>
+__global__ void __launch_bounds__(THREADS)
     search_accum_kernel(MapView map, const float4 *__restrict__ src, const uint32_t *__restrict__ tile_scan,
                         const ScanState *__restrict__ states, float limit, int32_t *__restrict__ corr,
                         double *__restrict__ partials, float4 *__restrict__ cert_p, uint32_t *__restrict__ cert_pos,
@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(kThreads)
     __shared__ float s_b2[kTile];
     __shared__ uint32_t s_nq, s_nfar, s_nfar_none, s_next;
     __shared__ float sT[16];
-    __shared__ double sred[kThreads / 32][kAccum];
+    constexpr int kQ_ = kTile / THREADS;  // queries per thread
+    __shared__ double sred[THREADS / 32][kAccum];
     const uint32_t none_hi = __float_as_uint(limit);
     const bool searchable = limit > 0.f && map.n_pts > 0;
     const uint32_t n_tiles = *n_active;
@@ -221,11 +222,11 @@ __global__ void __launch_bounds__(kThreads)
         if (threadIdx.x == 0) tile_load_issue(s_q, &s_bar, src + slot0, n_here * (uint32_t)sizeof(float4));
         if (threadIdx.x < 16) sT[threadIdx.x] = z.T[threadIdx.x];
         // certificates of this thread's queries: issue the loads before waiting for the tile
-        float4 cp4[kQ];
-        uint32_t cpos[kQ];
+        float4 cp4[kQ_];
+        uint32_t cpos[kQ_];
 #pragma unroll
-        for (int k = 0; k < kQ; ++k) {
-            const uint32_t r = (uint32_t)k * kThreads + threadIdx.x;
+        for (int k = 0; k < kQ_; ++k) {
+            const uint32_t r = (uint32_t)k * THREADS + threadIdx.x;
             cp4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             cpos[k] = kNoPos;
             if (use_cert && r < n_here) {
@@ -238,8 +239,8 @@ __global__ void __launch_bounds__(kThreads)
         phase ^= 1u;
         // ---- V ----
 #pragma unroll
-        for (int k = 0; k < kQ; ++k) {
-            const uint32_t r = (uint32_t)k * kThreads + threadIdx.x;
+        for (int k = 0; k < kQ_; ++k) {
+            const uint32_t r = (uint32_t)k * THREADS + threadIdx.x;
             if (r >= n_here) continue;
             const float4 s4 = s_q[r];
             const float3 p = transform_point(sT, s4.x, s4.y, s4.z);
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(kThreads)
         // are queued again and finished afterwards, packed densely, so that a warp is not held up
         // by the lanes that drew a far query ----
         const uint32_t nq = s_nq;
-        for (uint32_t i = threadIdx.x; i < nq; i += kThreads) {
+        for (uint32_t i = threadIdx.x; i < nq; i += THREADS) {
             const uint32_t r = s_queue[i];
             const float4 p = s_q[r];
             unsigned long long key;
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(kThreads)
         }
         __syncthreads();
         const uint32_t nfar = s_nfar, nfar_none = s_nfar_none;
-        for (uint32_t i = threadIdx.x; i < nfar + nfar_none; i += kThreads) {
+        for (uint32_t i = threadIdx.x; i < nfar + nfar_none; i += THREADS) {
             const uint32_t r = i < nfar_none ? s_far[kTile - 1 - i] : s_far[i - nfar_none];
             const float4 p = s_q[r];
             if (make_cert) {
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(kThreads)
             }
         }
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < nq; i += kThreads) {
+        for (uint32_t i = threadIdx.x; i < nq; i += THREADS) {
             const uint32_t r = s_queue[i];
             const float4 p = s_q[r];
             const unsigned long long key = s_key[r];
@@ -337,8 +338,8 @@ __global__ void __launch_bounds__(kThreads)
         double v[kAccum];
 #pragma unroll
         for (int i = 0; i < kAccum; ++i) v[i] = 0.0;
-        for (int k = 0; k < kQ; ++k) {
-            const uint32_t r = (uint32_t)k * kThreads + threadIdx.x;
+        for (int k = 0; k < kQ_; ++k) {
+            const uint32_t r = (uint32_t)k * THREADS + threadIdx.x;
             if (r >= n_here) break;
             const uint32_t pos = s_pos[r];
             if (pos == kNoPos) continue;
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(kThreads)
         if (threadIdx.x < kAccum) {
             double sum = 0.0;
 #pragma unroll
-            for (int k = 0; k < kThreads / 32; ++k) sum += sred[k][threadIdx.x];
+            for (int k = 0; k < THREADS / 32; ++k) sum += sred[k][threadIdx.x];
             partials[(size_t)tile * kAccum + threadIdx.x] = sum;
         }
         // (the barrier at the top of the loop orders these reads before the next tile's writes)
@@ -928,7 +929,23 @@ static int reduce_and_solve(const IcpConfig &cfg, BatchBuffers &b, int pass, int
         if (timer) SSF_TRY(timer->end(st));        \
     } while (0)
 
-static int search_grid(const BatchBuffers &b, unsigned *grid)
+// launch the fused search: small batches (a few scans) take one query per thread on 512-thread
+// blocks -- four times the parallelism per tile, for latency --, large ones four queries per thread
+template <int KIND>
+static void launch_search(bool wide, unsigned grid, cudaStream_t st, const MapView &map, const BatchBuffers &b,
+                          float limit, int use_cert, uint32_t *fetch)
+{
+    if (wide)
+        search_accum_kernel<KIND, kTile><<<grid, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, b.state.p, limit, b.corr.p,
+                                                                 b.partials.p, b.cert_p.p, b.cert_pos.p, use_cert,
+                                                                 b.active.p, b.counters.p, fetch);
+    else
+        search_accum_kernel<KIND, kThreads><<<grid, kThreads, 0, st>>>(map, b.src.p, b.tile_scan.p, b.state.p, limit,
+                                                                       b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p,
+                                                                       use_cert, b.active.p, b.counters.p, fetch);
+}
+
+static int search_grid(const BatchBuffers &b, unsigned *grid, bool *wide)
 {
     static int n_sm = 0;
     if (n_sm == 0) {
@@ -939,6 +956,8 @@ static int search_grid(const BatchBuffers &b, unsigned *grid)
     // persistent blocks; sized by the batch CAPACITY so that the launch shape (and a captured graph)
     // does not change with the number of points of an upload -- surplus blocks fetch once and exit
     size_t g = (size_t)n_sm * 8u;
+    *wide = b.max_tiles < 4u * g;  // fewer than four tiles per resident 128-thread block: latency matters
+    if (*wide) g = (size_t)n_sm * 2u;  // 512-thread blocks, two per SM
     if (g > b.max_tiles) g = b.max_tiles;
     *grid = (unsigned)(g ? g : 1);
     return SSF_OK;
@@ -946,7 +965,7 @@ static int search_grid(const BatchBuffers &b, unsigned *grid)
 
 // the launches of one batch alignment (everything after the voxel stage), in stream order
 static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const float *T_init, bool certs,
-                         unsigned grid, cudaStream_t st, SearchTimer *timer)
+                         unsigned grid, bool wide, cudaStream_t st, SearchTimer *timer)
 {
     SSF_TRY(init_states(b, T_init, st));
     const unsigned tiles = (unsigned)b.n_tiles, scans = (unsigned)b.n_scans;
@@ -974,20 +993,14 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
         }
         for (int i = 0; i < cfg.num_iterations; ++i) {
             if (cfg.mode == SSF_MODE_GN_P2PLANE)
-                TIMED_SEARCH((search_accum_kernel<ACC_GN_P2PLANE><<<grid, kThreads, 0, st>>>(
-                    map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p, certs && i > 0,
-                    b.active.p, b.counters.p, b.counters.p + 1 + i)));
+                TIMED_SEARCH(launch_search<ACC_GN_P2PLANE>(wide, grid, st, map, b, limit, certs && i > 0, b.counters.p + 1 + i));
             else
-                TIMED_SEARCH((search_accum_kernel<ACC_GN_P2P><<<grid, kThreads, 0, st>>>(
-                    map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p, certs && i > 0,
-                    b.active.p, b.counters.p, b.counters.p + 1 + i)));
+                TIMED_SEARCH(launch_search<ACC_GN_P2P>(wide, grid, st, map, b, limit, certs && i > 0, b.counters.p + 1 + i));
             SSF_TRY(reduce_and_solve(cfg, b, i, 0, st));
         }
     } else if (cfg.mode == SSF_MODE_O3D_P2P) {
         for (int i = 0; i <= cfg.num_iterations; ++i) {
-            TIMED_SEARCH((search_accum_kernel<ACC_KABSCH><<<grid, kThreads, 0, st>>>(
-                map, b.src.p, b.tile_scan.p, S, limit, b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p, certs && i > 0,
-                b.active.p, b.counters.p, b.counters.p + 1 + i)));
+            TIMED_SEARCH(launch_search<ACC_KABSCH>(wide, grid, st, map, b, limit, certs && i > 0, b.counters.p + 1 + i));
             SSF_TRY(reduce_and_solve(cfg, b, i, 1, st));
         }
     } else if (cfg.mode == SSF_MODE_REFERENCE) {
@@ -1038,7 +1051,8 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
     const char *nc = getenv("SSF_NO_CERT");
     const bool certs = !(nc && atoi(nc) != 0);
     unsigned grid = 1;
-    SSF_TRY(search_grid(b, &grid));
+    bool wide = false;
+    SSF_TRY(search_grid(b, &grid, &wide));
     if (cfg.mode != SSF_MODE_REFERENCE) {  // allocations happen here, never inside a capture
         SSF_TRY(b.active.reserve(b.max_tiles ? b.max_tiles : 1));
         SSF_TRY(b.counters.reserve((size_t)cfg.num_iterations + 3));
@@ -1049,7 +1063,7 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
     if (!graphable) {
         if (cfg.mode != SSF_MODE_REFERENCE)
             g_queries.fetch_add((uint64_t)b.n_slots * (uint64_t)cfg.num_iterations, std::memory_order_relaxed);
-        return enqueue_batch(map, cfg, b, T_init, certs, grid, st, timer);
+        return enqueue_batch(map, cfg, b, T_init, certs, grid, wide, st, timer);
     }
 
     std::vector<unsigned long long> key;
@@ -1064,7 +1078,8 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
     put(&map, sizeof(map));
     put(&cfg.max_corr, sizeof(float)); put(&cfg.acc_err, sizeof(float)); put(&cfg.eps, sizeof(float));
     const unsigned long long scalars[] = {(unsigned long long)cfg.num_iterations, (unsigned long long)cfg.mode,
-                                          (unsigned long long)certs, (unsigned long long)grid, (unsigned long long)b.n_scans};
+                                          (unsigned long long)certs, (unsigned long long)grid, (unsigned long long)b.n_scans,
+                                          (unsigned long long)wide};
     put(scalars, sizeof(scalars));
     const void *ptrs[] = {b.src.p, b.corr.p, b.cert_p.p, b.cert_pos.p, b.tile_scan.p, b.active.p, b.counters.p,
                           b.partials.p, b.sums.p, b.state.p, b.results.p, b.trace_err.p, b.trace_search.p, T_init};
@@ -1077,7 +1092,7 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
         cudaGraph_t graph = nullptr;
         SSF_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         const uint64_t before = g_launches.load();
-        const int rc = enqueue_batch(map, cfg, b, T_init, certs, grid, st, nullptr);
+        const int rc = enqueue_batch(map, cfg, b, T_init, certs, grid, wide, st, nullptr);
         const cudaError_t ce = cudaStreamEndCapture(st, &graph);
         b.graph_kernels = g_launches.load() - before;
         g_launches.fetch_sub(b.graph_kernels);  // counted when the graph is launched
