@@ -652,8 +652,8 @@ extern "C" int ssf_batch_create(ssf_icp *icp, size_t max_scans, size_t max_total
     auto chk = [&](int r) { if (rc == SSF_OK) rc = r; };
     chk(b->buf.src.reserve(slots));
     chk(b->buf.corr.reserve(slots));
-    chk(b->buf.cert_p.reserve(slots));
-    chk(b->buf.cert_pos.reserve(slots));
+    chk(b->buf.cert.reserve(slots));
+    chk(b->buf.pose_hist.reserve(max_scans * 32 * 16));
     chk(b->buf.tile_scan.reserve(tiles));
     b->buf.max_tiles = tiles;
     chk(b->buf.partials.reserve(tiles * kAccum));

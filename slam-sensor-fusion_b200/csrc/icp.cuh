@@ -37,8 +37,8 @@ struct BatchBuffers {
     DevBuf<float4> P;          // REFERENCE: transformed source, advanced in place
     DevBuf<float4> Q;          // REFERENCE: matched target point per row
     DevBuf<int32_t> corr;      // correspondence (original target index) or -1
-    DevBuf<float4> cert_p;     // search certificates: query position + radius (nn_device.cuh)
-    DevBuf<uint32_t> cert_pos; // ... and the neighbour's position in the sorted map
+    DevBuf<uint2> cert;        // search certificates: (radius | issuing iteration, neighbour position), nn_device.cuh
+    DevBuf<float> pose_hist;   // [scan][kCertHist][16]: pose used by search launch i (certificates refer to it)
     DevBuf<uint32_t> tile_scan;
     DevBuf<uint32_t> active;     // tiles that hold points (search kernel work list)
     DevBuf<uint32_t> counters;   // [0] number of active tiles, [1 + i] tile fetch counter of search launch i

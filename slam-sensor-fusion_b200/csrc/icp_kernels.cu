@@ -39,7 +39,7 @@ extern "C" int ssf_debug_nn_stats(unsigned long long *out, int reset)
 // state init / results
 // =========================================================================================
 __global__ void init_states_kernel(ScanState *st, const float *T_init, uint32_t n_scans, float *trace_err,
-                                   int32_t *trace_search, int trace_len)
+                                   int32_t *trace_search, int trace_len, float *pose_hist)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_scans) return;
@@ -48,6 +48,7 @@ __global__ void init_states_kernel(ScanState *st, const float *T_init, uint32_t 
         const float v = T_init[16 * s + i];
         z.T[i] = v;
         z.T_init[i] = v;
+        pose_hist[((size_t)s * kCertHist) * 16 + i] = v;  // pose of search launch 0
         z.T_step[i] = (i % 5 == 0) ? 1.f : 0.f;
     }
     z.last_error = FLT_MAX;
@@ -74,7 +75,8 @@ int init_states(BatchBuffers &b, const float *T_init_dev, cudaStream_t st)
 {
     if (b.n_scans == 0) return SSF_OK;
     init_states_kernel<<<(unsigned)((b.n_scans + 127) / 128), 128, 0, st>>>(b.state.p, T_init_dev, (uint32_t)b.n_scans,
-                                                                          b.trace_err.p, b.trace_search.p, b.trace_len);
+                                                                          b.trace_err.p, b.trace_search.p, b.trace_len,
+                                                                          b.pose_hist.p);
     SSF_LAUNCHED();
     return SSF_OK;
 }
@@ -177,9 +179,9 @@ template <int KIND, int THREADS>
 __global__ void __launch_bounds__(THREADS)
     search_accum_kernel(MapView map, const float4 *__restrict__ src, const uint32_t *__restrict__ tile_scan,
                         const ScanState *__restrict__ states, float limit, int32_t *__restrict__ corr,
-                        double *__restrict__ partials, float4 *__restrict__ cert_p, uint32_t *__restrict__ cert_pos,
-                        int use_cert, const uint32_t *__restrict__ active, const uint32_t *__restrict__ n_active,
-                        uint32_t *__restrict__ fetch)
+                        double *__restrict__ partials, uint2 *__restrict__ cert, const float *__restrict__ pose_hist,
+                        int use_cert, int pass, const uint32_t *__restrict__ active,
+                        const uint32_t *__restrict__ n_active, uint32_t *__restrict__ fetch)
 {
     __shared__ __align__(128) float4 s_q[kTile];  // TMA destination; transformed in place, w = owned by this rank
     __shared__ __align__(8) unsigned long long s_bar;
@@ -218,21 +220,17 @@ __global__ void __launch_bounds__(THREADS)
         const size_t slot0 = (size_t)z.pt_begin + row0;
         // a certificate only pays off if the next pose update is small: write them once the last
         // update was below a few margins (the updates shrink fast)
-        const bool make_cert = z.last_step < 4.0f * map.cert_mu;
+        const bool make_cert = z.last_step < 4.0f * map.cert_mu && pass < kCertHist;
+        const float *hist = pose_hist + (size_t)scan * kCertHist * 16;
         if (threadIdx.x == 0) tile_load_issue(s_q, &s_bar, src + slot0, n_here * (uint32_t)sizeof(float4));
         if (threadIdx.x < 16) sT[threadIdx.x] = z.T[threadIdx.x];
         // certificates of this thread's queries: issue the loads before waiting for the tile
-        float4 cp4[kQ_];
-        uint32_t cpos[kQ_];
+        uint2 crt[kQ_];
 #pragma unroll
         for (int k = 0; k < kQ_; ++k) {
             const uint32_t r = (uint32_t)k * THREADS + threadIdx.x;
-            cp4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            cpos[k] = kNoPos;
-            if (use_cert && r < n_here) {
-                cp4[k] = cert_p[slot0 + r];
-                cpos[k] = cert_pos[slot0 + r];
-            }
+            crt[k] = make_uint2(0u, kNoPos);
+            if (use_cert && r < n_here) crt[k] = cert[slot0 + r];
         }
         __syncthreads();
         tile_bar_wait(&s_bar, phase);
@@ -253,15 +251,20 @@ __global__ void __launch_bounds__(THREADS)
             s_pos[r] = kNoPos;
             if (!mine || !ok) {
                 corr[slot0 + r] = mine ? -1 : -2;
-                if (!use_cert || mine) cert_p[slot0 + r] = make_float4(0.f, 0.f, 0.f, 0.f);  // no certificate
+                if (!use_cert || mine) cert[slot0 + r] = make_uint2(0u, kNoPos);  // no certificate
                 continue;
             }
-            unsigned long long key;
-            if (use_cert && nn_verify(map, cp4[k], cpos[k], p.x, p.y, p.z, limit, key)) {
-                const bool hit = (uint32_t)(key >> 32) < none_hi;
-                corr[slot0 + r] = hit ? (int)(uint32_t)key : -1;
-                if (hit) s_pos[r] = cpos[k];
-                continue;
+            const float L = __uint_as_float(crt[k].x & ~31u);
+            if (L > 0.f) {
+                // where this query was when the certificate was issued: same source point, the pose
+                // of that search launch (bit-identical to the position searched then)
+                const float3 pc = transform_point(hist + (crt[k].x & 31u) * 16, s4.x, s4.y, s4.z);
+                unsigned long long key;
+                if (nn_verify(map, pc.x, pc.y, pc.z, L, crt[k].y, p.x, p.y, p.z, limit, key)) {
+                    // same neighbour as before: corr[] already holds its index
+                    if ((uint32_t)(key >> 32) < none_hi) s_pos[r] = crt[k].y;
+                    continue;
+                }
             }
             s_queue[atomicAdd(&s_nq, 1u)] = (unsigned short)r;
         }
@@ -328,8 +331,7 @@ __global__ void __launch_bounds__(THREADS)
                 B.key = key; B.b2 = s_b2[r]; B.mu = map.cert_mu;
                 radius = cert_radius(B);
             }
-            cert_p[slot0 + r] = make_float4(p.x, p.y, p.z, radius);
-            cert_pos[slot0 + r] = hit ? s_pos[r] : kNoPos;
+            cert[slot0 + r] = make_uint2(cert_pack(radius, pass), hit ? s_pos[r] : kNoPos);
             if (!hit) s_pos[r] = kNoPos;
             else NN_STAT(5, 1);
         }
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const ScanState *__restrict
 }
 
 // one thread: normal equations -> Cholesky -> pose update -> stop rules (sv = the scan's kAccum totals)
-__device__ void gn_solve(ScanState &z, const double *sv, int pass, float acc_err, float eps)
+__device__ void gn_solve(ScanState &z, const double *sv, int pass, float acc_err, float eps, float *hist)
 {
     const long long K = (long long)(sv[28] + 0.5);
     z.n_searches += 1;
@@ -459,6 +461,8 @@ __device__ void gn_solve(ScanState &z, const double *sv, int pass, float acc_err
     double Ts[16];
     se3_from_twist(x, Ts);
     compose_round(Ts, z.T);
+    if (pass + 1 < kCertHist)
+        for (int i = 0; i < 16; ++i) hist[(pass + 1) * 16 + i] = z.T[i];  // pose of search launch pass + 1
     z.iterations += 1;
     double mx = 0.0;
     for (int u = 0; u < 6; ++u) mx = fmax(mx, fabs(x[u]));
@@ -467,7 +471,7 @@ __device__ void gn_solve(ScanState &z, const double *sv, int pass, float acc_err
     if (mx < (double)eps) { z.converged = 1; z.done = 1; }
 }
 
-__device__ void o3d_solve(ScanState &z, const double *sv, int pass, int max_iteration)
+__device__ void o3d_solve(ScanState &z, const double *sv, int pass, int max_iteration, float *hist)
 {
     const long long K = (long long)(sv[0] + 0.5);
     z.n_searches += 1;
@@ -505,12 +509,15 @@ __device__ void o3d_solve(ScanState &z, const double *sv, int pass, int max_iter
         z.last_step = (float)mv;
     }
     compose_round(Ts, z.T);
+    if (pass + 1 < kCertHist)
+        for (int i = 0; i < 16; ++i) hist[(pass + 1) * 16 + i] = z.T[i];  // pose of search launch pass + 1
     z.iterations += 1;
 }
 
 // the sums arrive from outside (map sharding: all-reduced across ranks)
 __global__ void __launch_bounds__(32) solve_kernel(ScanState *states, const double *__restrict__ sums, int pass,
-                                                   int o3d, float acc_err, float eps, int max_iteration)
+                                                   int o3d, float acc_err, float eps, int max_iteration,
+                                                   float *pose_hist)
 {
     __shared__ double sv[kAccum];
     ScanState &z = states[blockIdx.x];
@@ -518,14 +525,15 @@ __global__ void __launch_bounds__(32) solve_kernel(ScanState *states, const doub
     sv[threadIdx.x] = sums[(size_t)blockIdx.x * kAccum + threadIdx.x];
     __syncwarp();
     if (threadIdx.x != 0) return;
-    if (o3d) o3d_solve(z, sv, pass, max_iteration);
-    else gn_solve(z, sv, pass, acc_err, eps);
+    float *hist = pose_hist + (size_t)blockIdx.x * kCertHist * 16;
+    if (o3d) o3d_solve(z, sv, pass, max_iteration, hist);
+    else gn_solve(z, sv, pass, acc_err, eps, hist);
 }
 
 // single GPU: ordered sum of the scan's partial rows and the solve in one launch
 __global__ void __launch_bounds__(256)
     rowsum_solve_kernel(ScanState *states, const double *__restrict__ partials, double *__restrict__ sums, int pass,
-                        int o3d, float acc_err, float eps, int max_iteration)
+                        int o3d, float acc_err, float eps, int max_iteration, float *pose_hist)
 {
     __shared__ double sw[8][kAccum];
     __shared__ double sv[kAccum];
@@ -545,8 +553,9 @@ __global__ void __launch_bounds__(256)
     sv[lane] = tot;
     __syncwarp();
     if (lane != 0) return;
-    if (o3d) o3d_solve(z, sv, pass, max_iteration);
-    else gn_solve(z, sv, pass, acc_err, eps);
+    float *hist = pose_hist + (size_t)blockIdx.x * kCertHist * 16;
+    if (o3d) o3d_solve(z, sv, pass, max_iteration, hist);
+    else gn_solve(z, sv, pass, acc_err, eps, hist);
 }
 
 // =========================================================================================
@@ -905,7 +914,7 @@ static int reduce_and_solve(const IcpConfig &cfg, BatchBuffers &b, int pass, int
 {
     if (!cfg.allreduce) {
         rowsum_solve_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, b.sums.p, pass, o3d,
-                                                                 cfg.acc_err, cfg.eps, cfg.num_iterations);
+                                                                 cfg.acc_err, cfg.eps, cfg.num_iterations, b.pose_hist.p);
         SSF_LAUNCHED();
         return SSF_OK;
     }
@@ -916,7 +925,7 @@ static int reduce_and_solve(const IcpConfig &cfg, BatchBuffers &b, int pass, int
         return SSF_ERR_COMM;
     }
     solve_kernel<<<(unsigned)b.n_scans, 32, 0, st>>>(b.state.p, b.sums.p, pass, o3d, cfg.acc_err, cfg.eps,
-                                                     cfg.num_iterations);
+                                                     cfg.num_iterations, b.pose_hist.p);
     SSF_LAUNCHED();
     return SSF_OK;
 }
@@ -933,16 +942,16 @@ static int reduce_and_solve(const IcpConfig &cfg, BatchBuffers &b, int pass, int
 // blocks -- four times the parallelism per tile, for latency --, large ones four queries per thread
 template <int KIND>
 static void launch_search(bool wide, unsigned grid, cudaStream_t st, const MapView &map, const BatchBuffers &b,
-                          float limit, int use_cert, uint32_t *fetch)
+                          float limit, int use_cert, int pass, uint32_t *fetch)
 {
     if (wide)
         search_accum_kernel<KIND, kTile><<<grid, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, b.state.p, limit, b.corr.p,
-                                                                 b.partials.p, b.cert_p.p, b.cert_pos.p, use_cert,
+                                                                 b.partials.p, b.cert.p, b.pose_hist.p, use_cert, pass,
                                                                  b.active.p, b.counters.p, fetch);
     else
         search_accum_kernel<KIND, kThreads><<<grid, kThreads, 0, st>>>(map, b.src.p, b.tile_scan.p, b.state.p, limit,
-                                                                       b.corr.p, b.partials.p, b.cert_p.p, b.cert_pos.p,
-                                                                       use_cert, b.active.p, b.counters.p, fetch);
+                                                                       b.corr.p, b.partials.p, b.cert.p, b.pose_hist.p,
+                                                                       use_cert, pass, b.active.p, b.counters.p, fetch);
 }
 
 static int search_grid(const BatchBuffers &b, unsigned *grid, bool *wide)
@@ -993,14 +1002,14 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
         }
         for (int i = 0; i < cfg.num_iterations; ++i) {
             if (cfg.mode == SSF_MODE_GN_P2PLANE)
-                TIMED_SEARCH(launch_search<ACC_GN_P2PLANE>(wide, grid, st, map, b, limit, certs && i > 0, b.counters.p + 1 + i));
+                TIMED_SEARCH(launch_search<ACC_GN_P2PLANE>(wide, grid, st, map, b, limit, certs && i > 0, i, b.counters.p + 1 + i));
             else
-                TIMED_SEARCH(launch_search<ACC_GN_P2P>(wide, grid, st, map, b, limit, certs && i > 0, b.counters.p + 1 + i));
+                TIMED_SEARCH(launch_search<ACC_GN_P2P>(wide, grid, st, map, b, limit, certs && i > 0, i, b.counters.p + 1 + i));
             SSF_TRY(reduce_and_solve(cfg, b, i, 0, st));
         }
     } else if (cfg.mode == SSF_MODE_O3D_P2P) {
         for (int i = 0; i <= cfg.num_iterations; ++i) {
-            TIMED_SEARCH(launch_search<ACC_KABSCH>(wide, grid, st, map, b, limit, certs && i > 0, b.counters.p + 1 + i));
+            TIMED_SEARCH(launch_search<ACC_KABSCH>(wide, grid, st, map, b, limit, certs && i > 0, i, b.counters.p + 1 + i));
             SSF_TRY(reduce_and_solve(cfg, b, i, 1, st));
         }
     } else if (cfg.mode == SSF_MODE_REFERENCE) {
@@ -1081,7 +1090,7 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
                                           (unsigned long long)certs, (unsigned long long)grid, (unsigned long long)b.n_scans,
                                           (unsigned long long)wide};
     put(scalars, sizeof(scalars));
-    const void *ptrs[] = {b.src.p, b.corr.p, b.cert_p.p, b.cert_pos.p, b.tile_scan.p, b.active.p, b.counters.p,
+    const void *ptrs[] = {b.src.p, b.corr.p, b.cert.p, b.pose_hist.p, b.tile_scan.p, b.active.p, b.counters.p,
                           b.partials.p, b.sums.p, b.state.p, b.results.p, b.trace_err.p, b.trace_search.p, T_init};
     put(ptrs, sizeof(ptrs));
     if (!b.graph_exec || key != b.graph_key) {

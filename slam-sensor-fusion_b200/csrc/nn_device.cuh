@@ -381,6 +381,14 @@ __device__ __forceinline__ NNHit nn_query(const MapView &m, float px, float py, 
 // the d2 evaluated here -- bit for bit -- and is skipped.  For a query without a neighbour the
 // same L bounds ALL points: it stays unmatched while (L - |p' - p|)^2 * (1 - 2e-6) >= limit.
 constexpr uint32_t kNoPos = 0xFFFFFFFFu;
+// A certificate is 8 bytes per query: (radius L with the low 5 mantissa bits replaced by the
+// iteration that issued it, neighbour position).  The query position of that iteration is
+// recomputed from the scan's pose history (ScanState poses of the first kCertHist iterations).
+constexpr int kCertHist = 32;
+__device__ __forceinline__ uint32_t cert_pack(float L, int iteration)
+{
+    return (__float_as_uint(fmaxf(L, 0.f)) & ~31u) | ((uint32_t)iteration & 31u);  // truncation only shrinks L
+}
 
 // L of a finished CERT walk (rounded down)
 __device__ __forceinline__ float cert_radius(const NNBest<true> &B)
@@ -390,16 +398,16 @@ __device__ __forceinline__ float cert_radius(const NNBest<true> &B)
     return fminf(s1, s2);
 }
 
-// cert = (p.xyz, L), pos = neighbour position or kNoPos.  Returns true when the old result stands;
-// then key = packed (d2, index) of the neighbour at the new position (or the none sentinel).
-__device__ __forceinline__ bool nn_verify(const MapView &m, const float4 cert, uint32_t pos, float px, float py, float pz,
-                                          float limit, unsigned long long &key)
+// (cx, cy, cz) = where the query was when the certificate of radius L was issued, pos = neighbour
+// position or kNoPos.  Returns true when the old result stands; then key = packed (d2, index) of
+// the neighbour at the new position (or the none sentinel).
+__device__ __forceinline__ bool nn_verify(const MapView &m, float cx, float cy, float cz, float L, uint32_t pos, float px,
+                                          float py, float pz, float limit, unsigned long long &key)
 {
-    if (!(cert.w > 0.f)) return false;
-    const float mx = __fsub_rn(px, cert.x), my = __fsub_rn(py, cert.y), mz = __fsub_rn(pz, cert.z);
+    const float mx = __fsub_rn(px, cx), my = __fsub_rn(py, cy), mz = __fsub_rn(pz, cz);
     const float mv2 = __fadd_ru(__fadd_ru(__fmul_ru(mx, mx), __fmul_ru(my, my)), __fmul_ru(mz, mz));
     const float mv = __fmul_ru(sqrt_up(mv2), 1.000001f);  // >= |p' - p|
-    const float rest = __fsub_rd(cert.w, mv);
+    const float rest = __fsub_rd(L, mv);
     if (!(rest > 0.f)) return false;
     const float thr = __fmul_rd(__fmul_rd(rest, rest), kShrink);  // every OTHER point has float d2 > thr
     const unsigned long long none = (unsigned long long)__float_as_uint(limit) << 32;

@@ -150,20 +150,26 @@ __global__ void vb_init_kernel(int *vbox, uint32_t n_scans)
     vbox[8 * s + 7] = 0;
 }
 
-__global__ void __launch_bounds__(kTile)
+// one block per sort tile (kSlotAlign consecutive slots of one scan), eight points per thread
+__global__ void __launch_bounds__(256)
     vb_bbox_kernel(const float4 *__restrict__ raw, const uint32_t *__restrict__ tile_scan,
                    const uint32_t *__restrict__ meta, int *vbox)
 {
-    const uint32_t s = tile_scan[blockIdx.x];
-    const uint32_t n = meta[5 * s + 1], pt_begin = meta[5 * s + 2], tile_begin = meta[5 * s + 3];
-    const uint32_t row = (blockIdx.x - tile_begin) * kTile + threadIdx.x;
+    const uint32_t base = blockIdx.x * kSlotAlign;
+    const uint32_t s = tile_scan[base / kTile];
+    const uint32_t n = meta[5 * s + 1], pt_begin = meta[5 * s + 2];
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     uint32_t cnt = 0;
-    if (row < n) {
-        const float4 p = raw[(size_t)pt_begin + row];
-        if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-            mn[0] = mx[0] = p.x; mn[1] = mx[1] = p.y; mn[2] = mx[2] = p.z;
-            cnt = 1;
+#pragma unroll
+    for (int i = 0; i < kSlotAlign / 256; ++i) {
+        const uint32_t slot = base + (uint32_t)i * 256 + threadIdx.x;
+        if (slot - pt_begin < n) {
+            const float4 p = raw[slot];
+            if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+                mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+                mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+                ++cnt;
+            }
         }
     }
 #pragma unroll
@@ -176,8 +182,8 @@ __global__ void __launch_bounds__(kTile)
         cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
     }
     // one atomic set per block (a tile belongs to one scan), not per warp
-    __shared__ float smn[kTile / 32][3], smx[kTile / 32][3];
-    __shared__ uint32_t scnt[kTile / 32];
+    __shared__ float smn[8][3], smx[8][3];
+    __shared__ uint32_t scnt[8];
     const int warp = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
@@ -187,7 +193,7 @@ __global__ void __launch_bounds__(kTile)
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t c = 0;
-        for (int w = 0; w < kTile / 32; ++w) {
+        for (int w = 0; w < 8; ++w) {
             c += scnt[w];
 #pragma unroll
             for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], smn[w][k]); mx[k] = fmaxf(mx[k], smx[w][k]); }
@@ -417,7 +423,7 @@ int voxel_downsample_batch(BatchBuffers &b, const uint32_t *meta_dev, float leaf
     vb_segs_kernel<<<sb, 128, 0, st>>>(meta_dev, n_scans, b.vsegs.p);
     SSF_LAUNCHED();
     if (tiles > 0) {
-        vb_bbox_kernel<<<tiles, kTile, 0, st>>>(b.raw.p, b.tile_scan.p, meta_dev, vbox);
+        vb_bbox_kernel<<<n_sort_tiles, 256, 0, st>>>(b.raw.p, b.tile_scan.p, meta_dev, vbox);
         SSF_LAUNCHED();
         vb_grid_kernel<<<sb, 128, 0, st>>>(vbox, b.vgrid.p, n_scans, inv);
         SSF_LAUNCHED();
