@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(THREADS)
             s_pos[r] = kNoPos;
             if (!mine || !ok) {
                 corr[slot0 + r] = mine ? -1 : -2;
-                if (!use_cert || mine) cert[slot0 + r] = make_uint2(0u, kNoPos);  // no certificate
+                cert[slot0 + r] = make_uint2(0u, kNoPos);  // no certificate (corr[] no longer holds a neighbour)
                 continue;
             }
             const float L = __uint_as_float(crt[k].x & ~31u);
