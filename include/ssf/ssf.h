@@ -111,7 +111,7 @@ void ssf_icp_destroy(ssf_icp *icp);
 int ssf_icp_set_params(ssf_icp *icp, const ssf_icp_params *params);
 int ssf_icp_get_params(const ssf_icp *icp, ssf_icp_params *out);
 /* setTargetPointCloud (icp_point_to_point.cpp:49-55): copy the map to HBM and build the
- * voxel-hash index that replaces kdtree_.setInputCloud.  normals (optional, same count)
+ * voxel-grid index that replaces kdtree_.setInputCloud.  normals (optional, same count)
  * are required by SSF_MODE_GN_P2PLANE.  The map stays resident until the next call. */
 int ssf_icp_set_target(ssf_icp *icp, const float *xyz, size_t n, size_t stride_bytes, const float *normals,
                        size_t normals_stride_bytes);

@@ -437,7 +437,7 @@ class BruteForceAlignment:
     def __init__(self, context: Context | None = None):
         self._p = capi.BfaParams(0.1, 0.1, 0.05, 1.5, 1.5, 0.1, float(np.float32(np.pi) / np.float32(18.0)),
                                  float(np.float32(np.pi) / np.float32(6.0)), 0.1)
-        self._icp = ICPPointToPoint(1.0, 1, 0.0, 0.0, context=context)  # holds the target's voxel hash
+        self._icp = ICPPointToPoint(1.0, 1, 0.0, 0.0, context=context)  # holds the target's map index
         self._prev = np.eye(4, dtype=np.float32)
         self._best = np.eye(4, dtype=np.float32)
         self._done = False
