@@ -211,7 +211,9 @@ def config_of(args, w):
     return {"workload": f"{args.workload}: {w['desc']}", "scans_per_step": args.scans_per_step,
             "map_points": w["map_points"], "scan_rays": w["beams"] * w["azimuths"], "voxel_leaf": w["leaf"],
             "mode": w["mode"], "max_correspondence_dist": THR, "iterations": ITERS,
-            "parallelism": (f"map-sharded x{args.gpus} (scans replicated, per-iteration all-reduce)" if w.get("sharded")
+            "parallelism": (f"map-sharded x{args.gpus} (scans replicated, per-iteration sum of 32 doubles per scan: " +
+                            ("in-kernel exchange over peer memory" if args.exchange == "peer" else "NCCL all-reduce hook") + ")"
+                            if w.get("sharded")
                             else f"scan-sharded x{args.gpus} (map replicated)"),
             "l2": args.l2_note}
 
@@ -249,7 +251,10 @@ def run_gpu(args, rank, world, local_rank):
         from ssf_gpu import shard
         sh = shard.shard_map(xyz, nrm, rank, world, THR)
         icp.setTargetShard(sh)
-        icp.setAllreduce(shard.torch_allreduce_hook(local_rank))
+        if args.exchange == "peer":
+            shard.setup_peer_exchange(icp, rank, world, max_scans=B)
+        else:
+            icp.setAllreduce(shard.torch_allreduce_hook(local_rank))
         log(f"[bench r{rank}] shard {sh['points'].shape[0]} of {xyz.shape[0]} pts, columns {sh['own']}")
     else:
         icp.setTargetPointCloud(xyz, nrm)
@@ -449,6 +454,8 @@ def main():
     ap.add_argument("--scans-per-step", type=int, default=0, help="default: 64 (16 for c3)")
     ap.add_argument("--cpu-scans", type=int, default=8, help="scans in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="map-sharded workloads: in-kernel exchange over peer memory (default) or the NCCL all-reduce hook")
     args = ap.parse_args()
     args.l2_note = "n/a (CPU run)"
     if args.scans_per_step <= 0:

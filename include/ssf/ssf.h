@@ -227,6 +227,17 @@ int ssf_icp_set_target_shard(ssf_icp *icp, const float *xyz, size_t n, size_t st
  * Return 0 on success.  (bench.py passes torch.distributed.all_reduce over NCCL.) */
 typedef int (*ssf_allreduce_fn)(void *user, double *buf, size_t count, void *cuda_stream);
 int ssf_icp_set_allreduce(ssf_icp *icp, ssf_allreduce_fn fn, void *user);
+/* In-kernel exchange instead of the hook (one process per GPU, all on one NVLink box): every rank
+ * creates its exchange buffer and gets a 64-byte CUDA IPC handle, the caller gathers the handles of
+ * all ranks (any transport: torch.distributed, MPI, a file) and hands the rank-ordered array
+ * (world x 64 bytes) to ssf_icp_exchange_open.  From then on the row-sum kernel stores this rank's
+ * per-scan rows straight into every rank's buffer (peer stores over NVLink) and the solve kernel
+ * waits for all ranks' epoch flags and adds the rows in rank order -- no host call and no NCCL
+ * collective per iteration.  All ranks must run the same sequence of alignments with the same
+ * scans; max_scans bounds the scans per batch.  world <= 32. */
+int ssf_icp_exchange_create(ssf_icp *icp, int rank, int world, size_t max_scans, unsigned char handle_out[64]);
+int ssf_icp_exchange_open(ssf_icp *icp, const unsigned char *handles /* world x 64 bytes, rank order */);
+int ssf_icp_exchange_close(ssf_icp *icp);
 
 /* ---- profiling hook ------------------------------------------------------------------- */
 /* When enabled, every launch of the NN-search kernels (K3) on this context is bracketed by a

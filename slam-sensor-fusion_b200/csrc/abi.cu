@@ -77,6 +77,18 @@ struct ssf_icp {
     bool in_shard_call = false;
     AllreduceFn allreduce = nullptr;  // map sharding hook
     void *allreduce_user = nullptr;
+    // map sharding, in-kernel exchange (XchView in icp.cuh)
+    struct {
+        int rank = 0, world = 0;
+        size_t max_scans = 0, bytes = 0;
+        void *local = nullptr;             // this rank's buffer (cudaMalloc)
+        std::vector<void *> peers;         // every rank's buffer as seen from this device
+        std::vector<bool> opened;          // peers[r] came from cudaIpcOpenMemHandle
+        DevBuf<void *> peers_dev;
+        DevBuf<uint32_t> counter;
+        unsigned long long epoch = 1;      // next epoch to use (flags start at 0)
+        bool ready = false;
+    } xch;
     DevBuf<float4> q_dev;  // ssf_nn_search temporaries
     DevBuf<int32_t> q_idx;
     DevBuf<float> q_d2;
@@ -257,12 +269,15 @@ extern "C" int ssf_icp_create(ssf_ctx *ctx, const ssf_icp_params *params, ssf_ic
     return SSF_OK;
 }
 
+static void exchange_release(ssf_icp *icp);
+
 extern "C" void ssf_icp_destroy(ssf_icp *icp)
 {
     if (!icp) return;
     cudaSetDevice(icp->ctx->device);
     cudaStreamSynchronize(icp->ctx->stream);
     if (icp->single) ssf_batch_destroy(icp->single);
+    exchange_release(icp);
     delete icp;
 }
 
@@ -348,6 +363,85 @@ extern "C" int ssf_icp_set_allreduce(ssf_icp *icp, ssf_allreduce_fn fn, void *us
     SSF_ARG(icp, "ssf_icp_set_allreduce: icp == NULL");
     icp->allreduce = fn;
     icp->allreduce_user = user;
+    return SSF_OK;
+}
+
+static void exchange_release(ssf_icp *icp)
+{
+    auto &x = icp->xch;
+    for (size_t r = 0; r < x.peers.size(); ++r)
+        if (x.opened[r] && x.peers[r]) cudaIpcCloseMemHandle(x.peers[r]);
+    x.peers.clear();
+    x.opened.clear();
+    if (x.local) cudaFree(x.local);
+    x.local = nullptr;
+    x.ready = false;
+    x.world = 0;
+}
+
+extern "C" int ssf_icp_exchange_create(ssf_icp *icp, int rank, int world, size_t max_scans, unsigned char handle_out[64])
+{
+    SSF_ARG(icp && handle_out, "ssf_icp_exchange_create: NULL argument");
+    SSF_ARG(world >= 1 && world <= 32 && rank >= 0 && rank < world, "ssf_icp_exchange_create: bad rank / world (<= 32)");
+    SSF_ARG(max_scans >= 1 && max_scans < (1u << 24), "ssf_icp_exchange_create: max_scans out of range");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    SSF_TRY(use_device(icp->ctx));
+    exchange_release(icp);
+    auto &x = icp->xch;
+    x.rank = rank;
+    x.world = world;
+    x.max_scans = max_scans;
+    x.bytes = (size_t)2 * world * max_scans * kAccum * sizeof(double) + (size_t)2 * world * sizeof(unsigned long long);
+    SSF_CUDA(cudaMalloc(&x.local, x.bytes));
+    SSF_CUDA(cudaMemset(x.local, 0, x.bytes));
+    SSF_TRY(x.counter.reserve(1));
+    SSF_CUDA(cudaMemset(x.counter.p, 0, sizeof(uint32_t)));
+    SSF_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    SSF_CUDA(cudaIpcGetMemHandle(&h, x.local));
+    memcpy(handle_out, &h, 64);
+    x.epoch = 1;
+    return SSF_OK;
+}
+
+extern "C" int ssf_icp_exchange_open(ssf_icp *icp, const unsigned char *handles)
+{
+    SSF_ARG(icp && handles, "ssf_icp_exchange_open: NULL argument");
+    auto &x = icp->xch;
+    if (!x.local || x.world < 1) {
+        set_error("ssf_icp_exchange_open: call ssf_icp_exchange_create first");
+        return SSF_ERR_STATE;
+    }
+    SSF_TRY(use_device(icp->ctx));
+    x.peers.assign(x.world, nullptr);
+    x.opened.assign(x.world, false);
+    for (int r = 0; r < x.world; ++r) {
+        if (r == x.rank) {
+            x.peers[r] = x.local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)64 * r, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&x.peers[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+            cudaGetLastError();
+            return SSF_ERR_COMM;
+        }
+        x.opened[r] = true;
+    }
+    SSF_TRY(x.peers_dev.reserve(x.world));
+    SSF_CUDA(cudaMemcpy(x.peers_dev.p, x.peers.data(), x.world * sizeof(void *), cudaMemcpyHostToDevice));
+    x.ready = true;
+    return SSF_OK;
+}
+
+extern "C" int ssf_icp_exchange_close(ssf_icp *icp)
+{
+    SSF_ARG(icp, "ssf_icp_exchange_close: icp == NULL");
+    SSF_TRY(use_device(icp->ctx));
+    cudaStreamSynchronize(icp->ctx->stream);
+    exchange_release(icp);
     return SSF_OK;
 }
 
@@ -832,6 +926,19 @@ extern "C" int ssf_batch_run(ssf_batch *b)
     if (icp->map.sharded) {
         cfg.allreduce = icp->allreduce;
         cfg.allreduce_user = icp->allreduce_user;
+        if (icp->xch.ready) {
+            if (buf.n_scans > icp->xch.max_scans) {
+                set_error("ssf_batch_run: %zu scans exceed the exchange capacity (%zu)", buf.n_scans, icp->xch.max_scans);
+                return SSF_ERR_INVALID;
+            }
+            cfg.xch.peers = icp->xch.peers_dev.p;
+            cfg.xch.rank = icp->xch.rank;
+            cfg.xch.world = icp->xch.world;
+            cfg.xch.max_scans = (uint32_t)icp->xch.max_scans;
+            cfg.xch.counter = icp->xch.counter.p;
+            cfg.xch_epoch = icp->xch.epoch;
+            icp->xch.epoch += (unsigned long long)p.num_iterations + 2;  // one epoch per pass (O3D runs one more)
+        }
     }
     SSF_TRY(run_batch(icp->map.view, cfg, buf, b->T_init_pinned.p, ctx->stream, &ctx->timer));
     SSF_CUDA(cudaEventRecord(b->ev1, ctx->stream));

@@ -84,6 +84,18 @@ struct SearchTimer {
 // all-reduce hook (map sharding): sum `count` doubles at `buf` across ranks, enqueued on `stream`
 typedef int (*AllreduceFn)(void *user, double *buf, size_t count, void *stream);
 
+// Map sharding, in-kernel exchange: every rank owns one buffer (rows[2][world][max_scans][32] doubles
+// followed by flags[2][world] u64) and holds peer pointers to all of them (CUDA IPC over NVLink).
+// The row-sum kernel STORES this rank's per-scan rows into every rank's buffer and then publishes an
+// epoch in each rank's flag; the solve kernel waits for all ranks' flags and adds the rows in rank
+// order -- an all-gather + ordered reduction inside the two kernels, no host hook, no NCCL call.
+struct XchView {
+    void *const *peers = nullptr;  // device array [world] of buffer base pointers (own entry included)
+    int rank = 0, world = 0;
+    uint32_t max_scans = 0;
+    uint32_t *counter = nullptr;   // blocks of the row-sum kernel that have stored their row
+};
+
 struct IcpConfig {
     float max_corr;
     int num_iterations;
@@ -93,6 +105,8 @@ struct IcpConfig {
     int reduce;
     AllreduceFn allreduce = nullptr;
     void *allreduce_user = nullptr;
+    XchView xch;                      // world > 0: exchange in-kernel instead of through the hook
+    unsigned long long xch_epoch = 0; // epoch of the first exchange of this run
 };
 
 // Enqueue the whole alignment of every scan in the batch on `st` (no host sync inside).

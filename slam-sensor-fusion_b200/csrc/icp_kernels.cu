@@ -907,11 +907,96 @@ int SearchTimer::end(cudaStream_t st)
     return SSF_OK;
 }
 
+// ---- in-kernel exchange of the per-scan rows across ranks (map sharding) ---------------------------
+__device__ __forceinline__ double *xch_rows(void *base, const XchView &x, int par, int r)
+{
+    return reinterpret_cast<double *>(base) + ((size_t)(par * x.world + r) * x.max_scans) * kAccum;
+}
+__device__ __forceinline__ unsigned long long *xch_flag(void *base, const XchView &x, int par, int r)
+{
+    return reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(base) +
+                                                  (size_t)2 * x.world * x.max_scans * kAccum) +
+           par * x.world + r;
+}
+
+// ordered sum of a scan's partial rows, stored into EVERY rank's buffer (peer stores over NVLink);
+// the last block to finish publishes the epoch to every rank
+__global__ void __launch_bounds__(256)
+    rowsum_xchg_kernel(const ScanState *__restrict__ states, const double *__restrict__ partials, XchView x,
+                       unsigned long long epoch)
+{
+    __shared__ double sw[8][kAccum];
+    const ScanState &z = states[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int par = (int)(epoch & 1ull);
+    double s = 0.0;
+    if (!z.done) {
+        const uint32_t n_tiles = (z.n_pts + kTile - 1) / kTile;
+        for (uint32_t t = warp; t < n_tiles; t += 8) s += partials[(size_t)(z.tile_begin + t) * kAccum + lane];
+    }
+    sw[warp][lane] = s;
+    __syncthreads();
+    if (warp != 0) return;
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += sw[w][lane];
+    for (int r = 0; r < x.world; ++r) xch_rows(x.peers[r], x, par, x.rank)[(size_t)blockIdx.x * kAccum + lane] = tot;
+    __threadfence_system();
+    __syncwarp();
+    if (lane != 0) return;
+    if (atomicAdd(x.counter, 1u) == gridDim.x - 1) {  // every block's row is out: publish
+        *x.counter = 0;
+        __threadfence_system();
+        for (int r = 0; r < x.world; ++r) {
+            unsigned long long *f = xch_flag(x.peers[r], x, par, x.rank);
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+        }
+    }
+}
+
+// wait for every rank's rows of this epoch, add them in rank order (identical on all ranks), solve
+__global__ void __launch_bounds__(32)
+    solve_xchg_kernel(ScanState *states, XchView x, unsigned long long epoch, double *__restrict__ sums, int pass, int o3d,
+                      float acc_err, float eps, int max_iteration, float *pose_hist)
+{
+    __shared__ double sv[kAccum];
+    ScanState &z = states[blockIdx.x];
+    if (z.done) return;
+    const int lane = threadIdx.x, par = (int)(epoch & 1ull);
+    void *mine = x.peers[x.rank];
+    if (lane < x.world) {
+        const unsigned long long *f = xch_flag(mine, x, par, lane);
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        } while (v < epoch);
+    }
+    __syncwarp();
+    double tot = 0.0;
+    for (int r = 0; r < x.world; ++r) tot += __ldcg(xch_rows(mine, x, par, r) + (size_t)blockIdx.x * kAccum + lane);
+    sums[(size_t)blockIdx.x * kAccum + lane] = tot;
+    sv[lane] = tot;
+    __syncwarp();
+    if (lane != 0) return;
+    float *hist = pose_hist + (size_t)blockIdx.x * kCertHist * 16;
+    if (o3d) o3d_solve(z, sv, pass, max_iteration, hist);
+    else gn_solve(z, sv, pass, acc_err, eps, hist);
+}
+
 // per-scan totals of the partial rows and the solve.  Map sharding: the totals are summed across
 // ranks through the caller's hook (one small all-reduce per iteration: n_scans x 32 doubles) between
 // the two; otherwise both run in one launch.
 static int reduce_and_solve(const IcpConfig &cfg, BatchBuffers &b, int pass, int o3d, cudaStream_t st)
 {
+    if (cfg.xch.world > 0) {  // in-kernel exchange over peer memory
+        const unsigned long long epoch = cfg.xch_epoch + (unsigned long long)pass;
+        rowsum_xchg_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, cfg.xch, epoch);
+        SSF_LAUNCHED();
+        solve_xchg_kernel<<<(unsigned)b.n_scans, 32, 0, st>>>(b.state.p, cfg.xch, epoch, b.sums.p, pass, o3d, cfg.acc_err,
+                                                              cfg.eps, cfg.num_iterations, b.pose_hist.p);
+        SSF_LAUNCHED();
+        return SSF_OK;
+    }
     if (!cfg.allreduce) {
         rowsum_solve_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, b.sums.p, pass, o3d,
                                                                  cfg.acc_err, cfg.eps, cfg.num_iterations, b.pose_hist.p);
@@ -1067,7 +1152,7 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
         SSF_TRY(b.counters.reserve((size_t)cfg.num_iterations + 3));
     }
     const char *ng = getenv("SSF_NO_GRAPH");
-    const bool graphable = cfg.mode != SSF_MODE_REFERENCE && b.n_tiles > 0 && !cfg.allreduce &&
+    const bool graphable = cfg.mode != SSF_MODE_REFERENCE && b.n_tiles > 0 && !cfg.allreduce && cfg.xch.world == 0 &&
                            !(timer && timer->enabled) && !(ng && atoi(ng) != 0);
     if (!graphable) {
         if (cfg.mode != SSF_MODE_REFERENCE)

@@ -200,6 +200,22 @@ class ICPPointToPoint:
         self._allreduce_hook = hook
         capi.check(capi.lib().ssf_icp_set_allreduce(self._h, ctypes.cast(hook, ctypes.c_void_p), None))
 
+    def exchangeCreate(self, rank: int, world: int, max_scans: int) -> bytes:
+        """This rank's exchange buffer for the in-kernel sum across map shards; returns its 64-byte
+        CUDA IPC handle (gather the handles of all ranks, then ``exchangeOpen``)."""
+        h = (ctypes.c_ubyte * 64)()
+        capi.check(capi.lib().ssf_icp_exchange_create(self._h, int(rank), int(world), int(max_scans), h))
+        return bytes(h)
+
+    def exchangeOpen(self, handles) -> None:
+        """``handles``: the 64-byte handles of all ranks, in rank order."""
+        blob = b"".join(bytes(x) for x in handles)
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        capi.check(capi.lib().ssf_icp_exchange_open(self._h, buf))
+
+    def exchangeClose(self) -> None:
+        capi.check(capi.lib().ssf_icp_exchange_close(self._h))
+
     # -- calculateAlignment (icp_point_to_point.cpp:185-254) ---------------------------------------
     def calculateAlignment(self) -> ICPResult:
         r = IcpResult()

@@ -3,7 +3,8 @@
 * scans sharded, map replicated (offline reprocessing, BASELINE config 4): ``scan_range``;
 * map sharded by cell columns with a one-cell halo, scans replicated, one small all-reduce per
   iteration (configs 3 and 5): ``global_grid`` / ``partition_columns`` / ``shard_map`` and the
-  ``torch_allreduce_hook`` that plugs ``torch.distributed`` into ``ssf_icp_set_allreduce``.
+  ``torch_allreduce_hook`` that plugs ``torch.distributed`` into ``ssf_icp_set_allreduce``, and
+  ``setup_peer_exchange`` for the in-kernel exchange over CUDA IPC peer memory.
 
 Pure numpy (+ optional torch for the hook); covered on CPU by tests/test_sharding_gloo.py.
 """
@@ -78,6 +79,18 @@ class ShardInfo(ctypes.Structure):
 
 
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
+
+
+def setup_peer_exchange(icp, rank: int, world: int, max_scans: int, group=None) -> None:
+    """In-kernel exchange of the per-scan sums (``ssf_icp_exchange_*``): every rank creates its
+    buffer, the 64-byte CUDA IPC handles travel through ``torch.distributed.all_gather_object`` once,
+    and from then on the kernels store into each other's memory over NVLink -- no per-iteration hook."""
+    import torch.distributed as dist
+    mine = icp.exchangeCreate(rank, world, max_scans)
+    handles = [None] * world
+    dist.all_gather_object(handles, mine, group=group)
+    icp.exchangeOpen(handles)
+    dist.barrier(group=group)  # nobody starts storing before every rank has its buffer mapped
 
 
 class _DevArray:

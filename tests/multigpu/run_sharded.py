@@ -27,6 +27,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--map-points", type=int, default=1_000_000)
     ap.add_argument("--mode", default="p2plane", choices=["p2plane", "p2p", "o3d"])
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="nccl: all-reduce hook per iteration; peer: in-kernel exchange over CUDA IPC peer memory")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -42,7 +44,10 @@ def main():
     icp = ssf_gpu.ICPPointToPoint(0.5, 10, 0.0, 0.0, mode=mode, context=ctx)
     s = shard.shard_map(xyz, nrm, rank, world, 0.5)
     icp.setTargetShard(s)
-    icp.setAllreduce(shard.torch_allreduce_hook(local))
+    if args.exchange == "peer":
+        shard.setup_peer_exchange(icp, rank, world, max_scans=16)
+    else:
+        icp.setAllreduce(shard.torch_allreduce_hook(local))
     res = icp.align_batch(scans, inits)
     # per-row correspondences of the first scan from every rank (-2 = not owned)
     icp.setSourcePointCloud(scans[0])

@@ -18,14 +18,15 @@ def _n_gpus():
         return 0
 
 
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
 @pytest.mark.parametrize("mode", ["p2plane", "o3d"])
-def test_map_sharded_equals_unsharded(mode):
+def test_map_sharded_equals_unsharded(mode, exchange):
     n = _n_gpus()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}",
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multigpu", "run_sharded.py"),
-           "--mode", mode]
+           "--mode", mode, "--exchange", exchange]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "-> OK" in r.stdout
