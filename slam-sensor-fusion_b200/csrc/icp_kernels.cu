@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(THREADS)
     __shared__ unsigned short s_queue[kTile], s_far[kTile];
     __shared__ unsigned long long s_key[kTile];
     __shared__ float s_b2[kTile];
+    __shared__ uint32_t s_skip[kTile];
     __shared__ uint32_t s_nq, s_nfar, s_nfar_none, s_next;
     __shared__ float sT[16];
     constexpr int kQ_ = kTile / THREADS;  // queries per thread
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(THREADS)
                     continue;
                 }
             }
+            s_pos[r] = use_cert ? crt[k].y : kNoPos;  // last iteration's neighbour seeds the walk
             s_queue[atomicAdd(&s_nq, 1u)] = (unsigned short)r;
         }
         __syncthreads();
@@ -282,13 +284,14 @@ __global__ void __launch_bounds__(THREADS)
             bool far;
             if (make_cert) {
                 NNBest<true> B;
-                far = nn_walk_near<true>(map, p.x, p.y, p.z, limit, map.cert_mu, B);
+                far = nn_walk_near<true>(map, p.x, p.y, p.z, limit, map.cert_mu, B, s_pos[r]);
                 key = B.key; pos = B.pos; b2 = B.b2;
             } else {
                 NNBest<false> B;
-                far = nn_walk_near<false>(map, p.x, p.y, p.z, limit, 0.f, B);
+                far = nn_walk_near<false>(map, p.x, p.y, p.z, limit, 0.f, B, s_pos[r]);
                 key = B.key; pos = B.pos;
             }
+            if (far) s_skip[r] = s_pos[r];  // (read before s_pos is overwritten)
             s_key[r] = key;
             s_pos[r] = pos;
             s_b2[r] = b2;
@@ -308,12 +311,14 @@ __global__ void __launch_bounds__(THREADS)
             if (make_cert) {
                 NNBest<true> B;
                 B.key = s_key[r]; B.pos = s_pos[r]; B.b2 = s_b2[r]; B.mu = map.cert_mu;
+                B.skip = s_skip[r];
                 B.refresh();
                 nn_walk_far<true>(map, p.x, p.y, p.z, B);
                 s_key[r] = B.key; s_pos[r] = B.pos; s_b2[r] = B.b2;
             } else {
                 NNBest<false> B;
                 B.key = s_key[r]; B.pos = s_pos[r];
+                B.skip = kNoPos;
                 nn_walk_far<false>(map, p.x, p.y, p.z, B);
                 s_key[r] = B.key; s_pos[r] = B.pos;
             }

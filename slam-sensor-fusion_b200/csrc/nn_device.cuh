@@ -107,6 +107,7 @@ template <bool CERT>
 struct NNBest {
     unsigned long long key;
     uint32_t pos;
+    uint32_t skip;  // position of a candidate evaluated up front (the previous neighbour): not counted twice
     float b2, bdm, mu;
     __device__ __forceinline__ float bd() const { return __uint_as_float((uint32_t)(key >> 32)); }
     // bound to prune with
@@ -128,7 +129,7 @@ __device__ __forceinline__ void cand_update(NNBest<CERT> &B, const float4 &q, ui
     const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
     const unsigned long long k = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(q.w);
     if (CERT) {  // padding slots (valid == false) must not pose as a second point at the same distance
-        const float dv = valid ? d2 : FLT_MAX;
+        const float dv = (valid && j != B.skip) ? d2 : FLT_MAX;
         B.b2 = fminf(B.b2, fmaxf(dv, B.bd()));
     }
     if (k < B.key) { B.key = k; B.pos = j; }
@@ -264,15 +265,25 @@ constexpr uint32_t kRowZ = pack8(0, 1, 1, 0, -1, -1, 1, -1);
 // B.key < (bits(limit) << 32) iff a point was found.
 // Near part: own row and ring 1.  Returns true when rings 2.. are still within reach of the bound
 // (then nn_walk_far must follow, possibly later and in another thread: B carries all the state).
+// seed: position (in the sorted map) of a point worth trying first -- the neighbour found by the
+// previous iteration -- or kNoPos.  It only tightens the bound the walk starts with; the result is
+// that of the unseeded walk.
 template <bool CERT>
 __device__ __forceinline__ bool nn_walk_near(const MapView &m, float px, float py, float pz, float limit, float mu,
-                                             NNBest<CERT> &B)
+                                             NNBest<CERT> &B, uint32_t seed = 0xFFFFFFFFu)
 {
-    B.key = (unsigned long long)__float_as_uint(limit) << 32;
+    const unsigned long long none = (unsigned long long)__float_as_uint(limit) << 32;
+    B.key = none;
     B.pos = 0;
+    B.skip = 0xFFFFFFFFu;
     B.b2 = FLT_MAX;
     B.mu = mu;
     B.bdm = limit;
+    if (seed != 0xFFFFFFFFu) {
+        cand_update(B, __ldg(&m.pts[seed]), seed, true, px, py, pz);
+        B.skip = seed;
+    }
+    const bool seeded = B.key < none;
     B.refresh();
     NN_STAT(3, 1);
     {   // farther from the map's bounding box than the (inflated) limit: nothing to look at
@@ -290,10 +301,15 @@ __device__ __forceinline__ bool nn_walk_near(const MapView &m, float px, float p
     q.xdn2 = gap_sq(ax.dn);
     q.xup2 = gap_sq(ax.up);
     q.xlim2 = gap_sq(__fadd_rd(fminf(ax.dn, ax.up), m.hq));
-    // own row: seed with the cells cx-1..cx+1, then whatever else of the row is still in reach
+    // own row: with a seed, just the cells its distance reaches; else start with the cells
+    // cx-1..cx+1, then whatever else of the row is still in reach
     if (q.cy >= 0 && q.cy < m.ny && q.cz >= 0 && q.cz < m.nz) {
-        scan_cells(m, q, max(q.cx - 1, 0), min(q.cx + 1, m.nx - 1), q.cy, q.cz, B);
-        if (!(__fmul_ru(B.prune(), kGrow) < q.xlim2)) visit_row(m, q, q.cy, q.cz, 0.f, true, B);
+        if (seeded) {
+            visit_row(m, q, q.cy, q.cz, 0.f, false, B);
+        } else {
+            scan_cells(m, q, max(q.cx - 1, 0), min(q.cx + 1, m.nx - 1), q.cy, q.cz, B);
+            if (!(__fmul_ru(B.prune(), kGrow) < q.xlim2)) visit_row(m, q, q.cy, q.cz, 0.f, true, B);
+        }
     }
     // ring 1: which of the eight rows can still hold a better point?
     const int sy = ay.up <= ay.dn ? 1 : -1, sz = az.up <= az.dn ? 1 : -1;

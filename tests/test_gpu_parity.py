@@ -256,6 +256,43 @@ def test_certificates_change_nothing(gpu, c1_world, small_world, mode, monkeypat
             assert np.float32(x.error).view(np.uint32) == np.float32(y.error).view(np.uint32)
 
 
+def test_batched_voxel_stage_matches_oracle(gpu, ora, small_world):
+    """Scans of different sizes (one empty, one with NaNs, one whose voxel grid PCL refuses) go through the
+    segmented voxel stage in ONE batch; every scan must enter the loop with exactly the oracle's centroids."""
+    from ssf_gpu import synth
+    w = small_world
+    tree = ora.KdTree(w["map"])
+    scans, inits = [], []
+    for k, az in enumerate((256, 1024, 700)):
+        T = synth.street_pose(4 + 9 * k, half=w["half"])
+        scans.append(synth.make_scan(T, beams=16, azimuths=az, scan_id=90 + k, max_range=60.0))
+        inits.append(synth.perturb_pose(T, 90 + k))
+    bad = scans[1].copy()
+    bad[::97, 1] = np.nan  # dropped by the voxel grid
+    scans.append(bad)
+    inits.append(inits[1])
+    scans.append(np.zeros((0, 4), np.float32))
+    inits.append(np.eye(4))
+    icp = gpu.ICPPointToPoint(0.5, 10, 0.0, 0.0, mode=gpu.MODE_GN_P2PLANE)
+    icp.setTargetPointCloud(w["map"], w["normals"])
+    icp.setSourceVoxelLeaf(0.2)
+    res = icp.align_batch(scans, inits)
+    assert res[-1].aborted and res[-1].n_source == 0
+    for s, T0, r in zip(scans[:-1], inits[:-1], res[:-1]):
+        vox, refused = ora.voxel_grid(s, 0.2)
+        assert not refused and r.n_source == vox.shape[0]
+        o, _ = ora.icp_gn(tree, vox, T0, mode="p2plane", normals=w["normals"], num_iterations=10)
+        dt, dr = pose_delta(r.transformation, o.T)
+        assert dt < TOL_T and dr < TOL_R and abs(r.iterations - o.iterations) <= 1 and r.k_final == o.k_final
+    # the same scans one at a time: bit-identical to the batch
+    for s, T0, r in zip(scans[:-1], inits[:-1], res[:-1]):
+        icp.setSourcePointCloud(s)
+        icp.setInitialTransformation(T0)
+        r1 = icp.calculateAlignment()
+        assert np.array_equal(r1.transformation.view(np.uint32), r.transformation.view(np.uint32))
+        assert (r1.n_source, r1.k_final) == (r.n_source, r.k_final)
+
+
 def test_golden_fixture(gpu):
     """CUDA path against the committed golden vectors (tests/golden/c1_mini.npz)."""
     import os
