@@ -316,26 +316,40 @@ __global__ void __launch_bounds__(kSortThreads)
 }
 
 // in-place exclusive scan of every segment's [digit][tile] counts, starting at the segment's base
-// offset (a segment keeps its slot range): one block per segment, 4096 counts per trip
-__global__ void __launch_bounds__(kScanThreads)
+// offset (a segment keeps its slot range): one 1024-thread block per segment, 16 counts per thread and trip
+constexpr int kSegScanThreads = 1024;
+constexpr int kSegScanItems = 16;
+__global__ void __launch_bounds__(kSegScanThreads)
     seg_scan_kernel(uint32_t *__restrict__ ghist, const uint4 *__restrict__ segs, uint32_t entries_per_tile)
 {
+    __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
     const uint4 sg = segs[blockIdx.x];  // first tile, tiles, base offset
     uint32_t *h = ghist + (size_t)entries_per_tile * sg.x;
     const uint32_t n = entries_per_tile * sg.y;
-    uint32_t carry = sg.z;
-    for (uint32_t off = 0; off < n; off += kScanTile) {
-        const uint32_t base = off + threadIdx.x * kScanItems;
-        uint32_t v[kScanItems], sum = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t carry = sg.z;  // the same in every thread
+    for (uint32_t off = 0; off < n; off += kSegScanThreads * kSegScanItems) {
+        const uint32_t base = off + threadIdx.x * kSegScanItems;
+        uint32_t v[kSegScanItems], sum = 0;
 #pragma unroll
-        for (int i = 0; i < kScanItems; ++i) {
+        for (int i = 0; i < kSegScanItems; ++i) {
             v[i] = base + i < n ? h[base + i] : 0u;
             sum += v[i];
         }
-        uint32_t prefix = block_excl_scan_256(sum, &s_total) + carry;
+        const uint32_t incl = warp_incl_scan(sum);
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = s_warp[lane];
+            const uint32_t wi = warp_incl_scan(w);
+            s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+            if (lane == 31) s_total = wi;
+        }
+        __syncthreads();
+        uint32_t prefix = incl - sum + s_warp[warp] + carry;
 #pragma unroll
-        for (int i = 0; i < kScanItems; ++i) {
+        for (int i = 0; i < kSegScanItems; ++i) {
             if (base + i < n) h[base + i] = prefix;
             prefix += v[i];
         }
@@ -347,7 +361,7 @@ __global__ void __launch_bounds__(kScanThreads)
 int seg_scan_u32(uint32_t *counts, const uint4 *segs, uint32_t n_segs, uint32_t entries_per_tile, cudaStream_t st)
 {
     if (n_segs == 0) return SSF_OK;
-    seg_scan_kernel<<<n_segs, kScanThreads, 0, st>>>(counts, segs, entries_per_tile);
+    seg_scan_kernel<<<n_segs, kSegScanThreads, 0, st>>>(counts, segs, entries_per_tile);
     SSF_LAUNCHED();
     return SSF_OK;
 }

@@ -331,12 +331,21 @@ __global__ void __launch_bounds__(256)
     const uint32_t base = blockIdx.x * kSlotAlign;
     const uint32_t s = tile_scan[base / kTile];
     const uint32_t seg_begin = meta[5 * s + 2], seg_end = seg_begin + meta[5 * s + 4] * kTile;
-    for (uint32_t l = threadIdx.x; l < (uint32_t)kSlotAlign; l += 256) {
-        const uint32_t k = keys[base + l];
-        s_key[l] = k;
-        if (k != kDeadKey) {
-            const float4 p = raw[vals[base + l]];
-            s_x[l] = p.x; s_y[l] = p.y; s_z[l] = p.z;
+    {   // all loads of a thread issued back to back: keys and indices (coalesced), then the gathers
+        uint32_t kk[kPerThread], vv[kPerThread];
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) {
+            kk[i] = keys[base + i * 256 + threadIdx.x];
+            vv[i] = vals[base + i * 256 + threadIdx.x];
+        }
+        float4 pp[kPerThread];
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) pp[i] = kk[i] != kDeadKey ? raw[vv[i]] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < kPerThread; ++i) {
+            const uint32_t l = i * 256 + threadIdx.x;
+            s_key[l] = kk[i];
+            s_x[l] = pp[i].x; s_y[l] = pp[i].y; s_z[l] = pp[i].z;
         }
     }
     __syncthreads();
