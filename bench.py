@@ -44,6 +44,12 @@ WORKLOADS = {
                sharded=True, scans_per_step=16,
                desc="32-beam scans (~30k pts) point-to-plane GN ICP (10 it, thr 0.5) vs 50M-point map, "
                     "map sharded by cell columns across ranks, one 32-double all-reduce per scan per iteration"),
+    # config 5 per GPU: 62.5M map points per rank (500M on 8), dense scans, tight leaf, 30 iterations.
+    # (PCL's index-overflow guard refuses leaf 0.05 on a 100 m scan, SURVEY 7.3-6: range clamped to 40 m.)
+    "c5": dict(map_points=62_500_000, per_rank=True, beams=128, azimuths=2048, leaf=0.05, mode="gn_p2p", max_range=40.0,
+               sharded=True, scans_per_step=8, iters=30, normals=False,
+               desc="128-beam dense scans (~260k rays) voxel 0.05 m + point-to-point GN ICP (30 it, thr 0.5) vs "
+                    "62.5M map points per rank, map sharded by columns across ranks"),
     "mini": dict(map_points=200_000, beams=16, azimuths=512, leaf=0.2, mode="gn_p2plane", max_range=60.0,
                  desc="smoke-size variant of c2"),
 }
@@ -61,14 +67,15 @@ def peaks():
     return 6650.0, "fallback"
 
 
-def make_workload(name: str, n_scans: int, rank: int, distinct: int = 16):
+def make_workload(name: str, n_scans: int, rank: int, distinct: int = 16, world: int = 1):
     """Map + a batch of raw scans with perturbed initial poses (all seeded)."""
     from ssf_gpu import synth
     w = WORKLOADS[name]
     if w.get("sharded"):
         rank = 0  # map-sharded workloads: every rank registers the SAME scans against its map shard
     t0 = time.time()
-    xyz, nrm, half = synth.make_map(w["map_points"], normals=True)
+    m_points = w["map_points"] * (world if w.get("per_rank") else 1)
+    xyz, nrm, half = synth.make_map(m_points, normals=w.get("normals", True))
     log(f"[bench r{rank}] map {xyz.shape[0]} pts, half extent {half} m, {time.time() - t0:.1f}s")
     t0 = time.time()
     distinct = min(distinct, n_scans)
@@ -141,6 +148,10 @@ def nn_footprint_bytes(map_xyz, queries_world, cell):
     cell entry (8 B) in the 3x3x3 neighbourhood of a query-occupied cell, counted once, plus
     20 B per query (16 B read, 4 B correspondence written)."""
     o = map_xyz[:, :3].min(0)
+    # only map points near the queries can lie in a query cell's neighbourhood: drop the rest first
+    qlo, qhi = queries_world.min(0) - 2 * cell, queries_world.max(0) + 2 * cell
+    near = ((map_xyz[:, :3] >= qlo) & (map_xyz[:, :3] <= qhi)).all(1)
+    map_xyz = map_xyz[near]
     mc = np.floor((map_xyz[:, :3] - o) / cell).astype(np.int64)
     dims = mc.max(0) + 3
     mkey = ((mc[:, 2] + 1) * dims[1] + (mc[:, 1] + 1)) * dims[0] + (mc[:, 0] + 1)
@@ -179,9 +190,9 @@ def run_cpu(args, rank, world):
         q = 0
         for sc, T0 in zip(scans, inits):
             src = oracle.voxel_grid(sc, w["leaf"])[0] if w["leaf"] > 0 else sc
-            if w["mode"] == "gn_p2plane":
-                r, _ = oracle.icp_gn(tree, src, T0, mode="p2plane", normals=nrm, max_correspondence_dist=THR,
-                                     num_iterations=ITERS, threads=threads)
+            if w["mode"] in ("gn_p2plane", "gn_p2p"):
+                r, _ = oracle.icp_gn(tree, src, T0, mode="p2plane" if w["mode"] == "gn_p2plane" else "p2p", normals=nrm,
+                                     max_correspondence_dist=THR, num_iterations=w.get("iters", ITERS), threads=threads)
             else:
                 r, _, _ = oracle.icp_reference(tree, src, T0, THR, ITERS, 0.05, 1e-5, threads=threads)
             q += src.shape[0] * r.n_searches
@@ -210,7 +221,7 @@ def run_cpu(args, rank, world):
 def config_of(args, w):
     return {"workload": f"{args.workload}: {w['desc']}", "scans_per_step": args.scans_per_step,
             "map_points": w["map_points"], "scan_rays": w["beams"] * w["azimuths"], "voxel_leaf": w["leaf"],
-            "mode": w["mode"], "max_correspondence_dist": THR, "iterations": ITERS,
+            "mode": w["mode"], "max_correspondence_dist": THR, "iterations": w.get("iters", ITERS),
             "parallelism": (f"map-sharded x{args.gpus} (scans replicated, per-iteration sum of 32 doubles per scan: " +
                             ("in-kernel exchange over peer memory" if args.exchange == "peer" else "NCCL all-reduce hook") + ")"
                             if w.get("sharded")
@@ -239,12 +250,14 @@ def run_gpu(args, rank, world, local_rank):
             os.dup2(saved, 1)
             os.close(saved)
     B = args.scans_per_step
-    w, xyz, nrm, half, scans, inits, gts = make_workload(args.workload, B, rank)
+    w, xyz, nrm, half, scans, inits, gts = make_workload(args.workload, B, rank, world=world)
+    iters = w.get("iters", ITERS)
     sharded = bool(w.get("sharded")) and world > 1
     ctx = ssf_gpu.Context(local_rank)
-    mode = {"gn_p2plane": ssf_gpu.MODE_GN_P2PLANE, "reference": ssf_gpu.MODE_REFERENCE}[w["mode"]]
+    mode = {"gn_p2plane": ssf_gpu.MODE_GN_P2PLANE, "gn_p2p": ssf_gpu.MODE_GN_P2P,
+            "reference": ssf_gpu.MODE_REFERENCE}[w["mode"]]
     acc, eps = (0.05, 1e-5) if mode == ssf_gpu.MODE_REFERENCE else (0.0, 0.0)
-    icp = ssf_gpu.ICPPointToPoint(THR, ITERS, acc, eps, mode=mode, reduce=ssf_gpu.REDUCE_STRICT, context=ctx)
+    icp = ssf_gpu.ICPPointToPoint(THR, iters, acc, eps, mode=mode, reduce=ssf_gpu.REDUCE_STRICT, context=ctx)
     icp.setSourceVoxelLeaf(w["leaf"])
     t0 = time.time()
     if sharded:
@@ -309,6 +322,8 @@ def run_gpu(args, rank, world, local_rank):
     # inputs of one step: raw scans + map (+ normals).  Smaller than the 126 MB L2 -> flush L2 between
     # timed steps (write a 256 MB buffer); larger -> the step itself streams them
     input_bytes = total * 16 + xyz.shape[0] * 16 * (2 if w["mode"] == "gn_p2plane" else 1)
+    if sharded:
+        input_bytes = total * 16 + sh["points"].shape[0] * 16 * (2 if w["mode"] == "gn_p2plane" else 1)
     flush = input_bytes < 126e6
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}") if flush else None
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -430,9 +445,9 @@ def cpu_baseline(args, w, xyz, nrm, scans, inits):
         t0 = time.time()
         for sc, T0 in zip(scans[:n], inits[:n]):
             src = oracle.voxel_grid(sc, w["leaf"])[0] if w["leaf"] > 0 else sc
-            if w["mode"] == "gn_p2plane":
-                oracle.icp_gn(tree, src, T0, mode="p2plane", normals=nrm, max_correspondence_dist=THR,
-                              num_iterations=ITERS, threads=th)
+            if w["mode"] in ("gn_p2plane", "gn_p2p"):
+                oracle.icp_gn(tree, src, T0, mode="p2plane" if w["mode"] == "gn_p2plane" else "p2p", normals=nrm,
+                              max_correspondence_dist=THR, num_iterations=w.get("iters", ITERS), threads=th)
             else:
                 oracle.icp_reference(tree, src, T0, THR, ITERS, 0.05, 1e-5, threads=th)
         return n / (time.time() - t0)

@@ -365,26 +365,26 @@ __global__ void __launch_bounds__(THREADS)
 #pragma unroll
                 for (int rr = 0; rr < 3; ++rr)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) v[7 + 3 * rr + c] += a[rr] * b[c];
+                    for (int c = 0; c < 3; ++c) v[7 + 3 * rr + c] = fma(a[rr], b[c], v[7 + 3 * rr + c]);
                 const double ex = (double)p.x - q.x, ey = (double)p.y - q.y, ez = (double)p.z - q.z;
-                v[16] += ex * ex + ey * ey + ez * ez;
+                v[16] += fma(ex, ex, fma(ey, ey, ez * ez));
             } else {
                 const double px = p.x, py = p.y, pz = p.z;
                 const double e[3] = {px - (double)q.x, py - (double)q.y, pz - (double)q.z};
                 if (KIND == ACC_GN_P2PLANE) {
                     const float4 nf = __ldg(&map.nrm[pos]);
                     const double n[3] = {nf.x, nf.y, nf.z};
-                    const double a[6] = {py * n[2] - pz * n[1], pz * n[0] - px * n[2], px * n[1] - py * n[0],
-                                         n[0], n[1], n[2]};
-                    const double rs = n[0] * e[0] + n[1] * e[1] + n[2] * e[2];
+                    const double a[6] = {fma(py, n[2], -(pz * n[1])), fma(pz, n[0], -(px * n[2])),
+                                         fma(px, n[1], -(py * n[0])), n[0], n[1], n[2]};
+                    const double rs = fma(n[0], e[0], fma(n[1], e[1], n[2] * e[2]));
                     int t = 0;
 #pragma unroll
                     for (int u = 0; u < 6; ++u)
 #pragma unroll
-                        for (int w = u; w < 6; ++w) v[t++] += a[u] * a[w];
+                        for (int w = u; w < 6; ++w, ++t) v[t] = fma(a[u], a[w], v[t]);
 #pragma unroll
-                    for (int u = 0; u < 6; ++u) v[21 + u] += a[u] * rs;
-                    v[27] += rs * rs;
+                    for (int u = 0; u < 6; ++u) v[21 + u] = fma(a[u], rs, v[21 + u]);
+                    v[27] = fma(rs, rs, v[27]);
                 } else {
                     // J = [-[p]x | I]; J^T J = [[ -[p]x^T -[p]x , [p]x ], [ -[p]x , I ]]
                     const double J[3][6] = {{0, pz, -py, 1, 0, 0}, {-pz, 0, px, 0, 1, 0}, {py, -px, 0, 0, 0, 1}};
