@@ -9,7 +9,6 @@ namespace ssf {
 
 constexpr int kTile = 512;     // queries per block of the search kernels; scans are tile-aligned
 constexpr int kThreads = 128;  // threads of a fused search block
-constexpr int kQ = kTile / kThreads;  // queries per thread there
 constexpr int kAccum = 32;  // doubles per partial row
 constexpr int kSlotAlign = kSortTileSize;  // a scan's slot range is a whole number of sort tiles
 static_assert(kSlotAlign % kTile == 0, "slot alignment must be a multiple of the search tile");
@@ -56,7 +55,6 @@ struct BatchBuffers {
     DevBuf<uint4> vsegs;           // per scan: (first sort tile, sort tiles, 0, 0): run ids restart per scan
     DevBuf<uint4> vsegs_sort;      // per scan: (first sort tile, sort tiles, first slot, 0)
     DevBuf<uint32_t> vruns;        // per sort tile: voxel runs starting in it, then their exclusive scan
-    DevBuf<uint32_t> vflags, vscan;
     DevBuf<float> vbox;            // per scan: min xyz, max xyz (ordered ints during reduce)
     DevBuf<int32_t> vgrid;         // per scan: minb[3], divb[3], refused, pad
     size_t n_scans = 0, n_tiles = 0, n_slots = 0;
