@@ -38,6 +38,13 @@ extern std::atomic<uint64_t> g_queries;
         SSF_CUDA(cudaGetLastError());          \
     } while (0)
 
+#ifdef SSF_BOUNDS
+// debug build only (make bounds): trap on any index outside its array
+#define SSF_CHECK(cond) do { if (!(cond)) { printf("SSF_CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); __trap(); } } while (0)
+#else
+#define SSF_CHECK(cond) ((void)0)
+#endif
+
 // Growable device buffer (never shrinks; freed with its owner).
 template <class T>
 struct DevBuf {
@@ -121,6 +128,7 @@ struct MapView {
     const uint2 *dir;   // directory, ntz*nty*nbx*16 entries
     const uint32_t *cell_start;  // n_cells + 1 offsets into pts
     uint32_t n_pts;  // finite target points
+    uint32_t n_cells;  // occupied cells (cell_start has n_cells + 1 entries)
     float ox, oy, oz, inv_h;
     float hq;        // (1 / inv_h) * (1 - 1e-6), rounded down: under-estimate of the cell edge
     int nx, ny, nz;  // grid extent in cells

@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(THREADS)
         const uint32_t nq = s_nq;
         for (uint32_t i = threadIdx.x; i < nq; i += THREADS) {
             const uint32_t r = s_queue[i];
+            SSF_CHECK(r < n_here);
             const float4 p = s_q[r];
             unsigned long long key;
             uint32_t pos;

@@ -258,6 +258,7 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
     v.nrm = m.has_normals ? m.nrm.p : nullptr;
     v.dir = m.dir.p;
     v.cell_start = m.cell_start.p;
+    v.n_cells = n_cells;
     m.view = v;
     m.n_cells = n_cells;
     m.n_dir = (uint32_t)g.n_dir;

@@ -41,13 +41,6 @@ static __device__ unsigned long long g_nn_stats[8];  // one copy per translation
 #define NN_STAT(i, v) ((void)0)
 #endif
 
-#ifdef SSF_BOUNDS
-// debug build only (make bounds): trap on any index outside its array
-#define SSF_CHECK(cond) do { if (!(cond)) { printf("SSF_CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); __trap(); } } while (0)
-#else
-#define SSF_CHECK(cond) ((void)0)
-#endif
-
 struct NNHit {
     float d2;      // best squared distance (== limit when nothing was found)
     int idx;       // original index of the best target point, -1 if none
@@ -172,6 +165,7 @@ __device__ __forceinline__ void scan_cells(const MapView &m, const NNQuery &q, i
         const int a = max(xa - (bx << 5), 0), b = min(xb - (bx << 5), 31);
         const uint32_t i0 = d.y + __popc(d.x & ((1u << a) - 1u));
         const uint32_t i1 = d.y + __popc(d.x & (0xFFFFFFFFu >> (31 - b)));
+        SSF_CHECK(i0 <= i1 && i1 <= m.n_cells);
         if (i0 == i1) continue;
         NN_STAT(6, 1);
         uint32_t j = __ldg(&m.cell_start[i0]);
@@ -280,6 +274,7 @@ __device__ __forceinline__ bool nn_walk_near(const MapView &m, float px, float p
     B.mu = mu;
     B.bdm = limit;
     if (seed != 0xFFFFFFFFu) {
+        SSF_CHECK(seed < m.n_pts);
         cand_update(B, __ldg(&m.pts[seed]), seed, true, px, py, pz);
         B.skip = seed;
     }
@@ -431,6 +426,7 @@ __device__ __forceinline__ bool nn_verify(const MapView &m, float cx, float cy, 
         key = none;
         return thr >= limit;
     }
+    SSF_CHECK(pos < m.n_pts);
     const float4 q = __ldg(&m.pts[pos]);
     const float dx = __fsub_rn(px, q.x), dy = __fsub_rn(py, q.y), dz = __fsub_rn(pz, q.z);
     const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));

@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(kSortThreads)
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t pos = wh[warp][(k[r] >> shift) & 255u] + rank[r];
+        SSF_CHECK(pos >= seg[blockIdx.x].x * kSortTile && pos < (seg[blockIdx.x].x + seg[blockIdx.x].y) * kSortTile);
         keys_out[pos] = k[r];
         vals_out[pos] = v[r];
     }

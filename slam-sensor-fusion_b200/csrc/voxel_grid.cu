@@ -391,6 +391,7 @@ __global__ void __launch_bounds__(256)
             }
         }
         const float fn = (float)n;
+        SSF_CHECK(seg_begin + rank < seg_end);
         src[seg_begin + rank] = make_float4(__fdiv_rn(cx, fn), __fdiv_rn(cy, fn), __fdiv_rn(cz, fn), 1.0f);
         ++rank;
     }
