@@ -74,6 +74,26 @@ def test_nn_empty_and_far(gpu, ora):
     assert gi.tolist() == [0, -1, -1, 2]
 
 
+@pytest.mark.parametrize("cell", ["0.07", "0.3", "1.5", "6.0"])
+@pytest.mark.parametrize("thr", [0.01, 0.5, 5.0, 400.0])
+def test_nn_any_cell_edge_any_threshold(gpu, ora, cell, thr, monkeypatch):
+    """The ring walk must be exact whatever the ratio of search radius to cell edge: from a radius far
+    below one cell (0.1 m vs 6 m cells) to dozens of rings (20 m vs 7 cm cells), on a surface-like
+    cloud with holes, duplicates and queries outside the map."""
+    monkeypatch.setenv("SSF_CELL_SIZE", cell)
+    rng = np.random.default_rng(int(float(cell) * 100) + int(thr * 10))
+    xy = rng.uniform(-8, 8, (30_000, 2)).astype(np.float32)
+    xy = xy[(np.abs(xy[:, 0]) > 1.0) | (np.abs(xy[:, 1]) > 1.5)]  # a hole in the floor
+    floor = np.c_[xy, 0.02 * rng.standard_normal(len(xy))].astype(np.float32)
+    wall = np.c_[rng.uniform(-8, 8, 8000), np.full(8000, 3.0), rng.uniform(0, 4, 8000)].astype(np.float32)
+    m = np.concatenate([floor, wall, floor[:500]])  # + duplicates (lowest index must win)
+    q = np.concatenate([floor[::7] + rng.normal(0, 0.05, floor[::7].shape).astype(np.float32),
+                        rng.uniform(-12, 12, (3000, 3)).astype(np.float32),   # in and around the map
+                        np.array([[0, 0, 0.3], [0, 0, 3], [100, 100, 100], [-9, 3.0, 2]], np.float32)])
+    n_in = _check_nn(gpu, ora, m, q, thr)
+    assert n_in > (1000 if thr >= 0.5 else 100)
+
+
 def test_nn_synthetic_map(gpu, ora, c1_world):
     w = c1_world
     T0 = w["T0"].astype(np.float32)
