@@ -9,6 +9,7 @@ namespace ssf {
 
 constexpr int kTile = 512;     // queries per block of the search kernels; scans are tile-aligned
 constexpr int kThreads = 128;  // threads of a fused search block
+constexpr int kWideThreads = 512;  // ... for small batches (latency): more threads per tile
 constexpr int kAccum = 32;  // doubles per partial row
 constexpr int kSlotAlign = kSortTileSize;  // a scan's slot range is a whole number of sort tiles
 static_assert(kSlotAlign % kTile == 0, "slot alignment must be a multiple of the search tile");

@@ -1036,7 +1036,7 @@ static void launch_search(bool wide, unsigned grid, cudaStream_t st, const MapVi
                           float limit, int use_cert, int pass, uint32_t *fetch)
 {
     if (wide)
-        search_accum_kernel<KIND, kTile><<<grid, kTile, 0, st>>>(map, b.src.p, b.tile_scan.p, b.state.p, limit, b.corr.p,
+        search_accum_kernel<KIND, kWideThreads><<<grid, kWideThreads, 0, st>>>(map, b.src.p, b.tile_scan.p, b.state.p, limit, b.corr.p,
                                                                  b.partials.p, b.cert.p, b.pose_hist.p, use_cert, pass,
                                                                  b.active.p, b.counters.p, fetch);
     else
