@@ -181,7 +181,9 @@ def run_cpu(args, rank, world):
     from oracle import oracle
     sample = max(1, min(args.cpu_scans, args.scans_per_step))
     w, xyz, nrm, half, scans, inits, gts = make_workload(args.workload, sample, 0, distinct=sample)
-    threads = oracle.max_threads()
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: the oracle takes
+    # its thread count per call, so the environment default does not cap it)
+    threads = max(oracle.max_threads(), len(os.sched_getaffinity(0)))
     t0 = time.time()
     tree = oracle.KdTree(xyz)
     build_s = time.time() - t0
@@ -435,7 +437,7 @@ def run_gpu(args, rank, world, local_rank):
 def cpu_baseline(args, w, xyz, nrm, scans, inits):
     """The oracle port on this box's host cores, bounded sample (rank 0, N = 1 only)."""
     from oracle import oracle
-    threads = oracle.max_threads()
+    threads = max(oracle.max_threads(), len(os.sched_getaffinity(0)))
     t0 = time.time()
     tree = oracle.KdTree(xyz)
     build_s = time.time() - t0
