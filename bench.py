@@ -94,12 +94,48 @@ def make_workload(name: str, n_scans: int, rank: int, distinct: int = 16, world:
 
 
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
+    In-process NVML from a thread, every 2 ms -- the timed region of a default run lasts tens of
+    milliseconds, too short for an `nvidia-smi -lms` child to report even once; nvidia-smi is the
+    fallback when NVML cannot be loaded."""
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.idx, self.rows, self.proc, self.thread, self.stop_flag = gpu_index, [], None, None, False
+        self.nvml, self.handle = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((float(sm), float(mx), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        self.stop_flag = False
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._sample_nvml, daemon=True)
+            self.thread.start()
+            return
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -116,6 +152,20 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        self.stop_flag = True
+        if self.nvml is not None:
+            if self.thread:
+                self.thread.join(timeout=1.0)
+            n = self.nvml
+            bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            sm = [r[0] for r in self.rows]
+            mx = max([r[1] for r in self.rows], default=0.0)
+            reasons = sorted(k for k, b in bits.items() if any(r[2] & b for r in self.rows))
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml, 2 ms period, during the timed regions"}
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
@@ -133,7 +183,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def pose_delta(Ta, Tb):
