@@ -44,6 +44,12 @@ WORKLOADS = {
                sharded=True, scans_per_step=16,
                desc="32-beam scans (~30k pts) point-to-plane GN ICP (10 it, thr 0.5) vs 50M-point map, "
                     "map sharded by cell columns across ranks, one 32-double all-reduce per scan per iteration"),
+    # config 4: the offline sequence (10 000 scans of config 1's shape against the 5M-point map); scans are
+    # independent, so ranks take disjoint scans and the sequence time is 10 000 / (scans/s over all ranks)
+    "c4": dict(map_points=5_000_000, beams=32, azimuths=1024, leaf=0.0, mode="reference", max_range=100.0,
+               scans_per_step=128,
+               desc="offline reprocessing: 32-beam scans (~30k pts) reference point-to-point ICP (10 it, thr 0.5) vs "
+                    "5M-point map, scans sharded across ranks, no communication"),
     # config 5 per GPU: 62.5M map points per rank (500M on 8), dense scans, tight leaf, 30 iterations.
     # (PCL's index-overflow guard refuses leaf 0.05 on a 100 m scan, SURVEY 7.3-6: range clamped to 40 m.)
     "c5": dict(map_points=62_500_000, per_rank=True, beams=128, azimuths=2048, leaf=0.05, mode="gn_p2p", max_range=40.0,

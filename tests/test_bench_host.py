@@ -40,6 +40,7 @@ def test_workloads_name_the_baseline_configs():
     assert w["c1"]["mode"] == "reference" and w["c1"]["map_points"] == 1_000_000          # configs[0]
     assert w["c2"]["leaf"] == 0.2 and w["c2"]["mode"] == "gn_p2plane" and w["c2"]["map_points"] == 5_000_000  # configs[1]
     assert w["c3"]["sharded"] and w["c3"]["map_points"] == 50_000_000                     # configs[2]
+    assert w["c4"]["mode"] == "reference" and w["c4"]["map_points"] == 5_000_000 and not w["c4"].get("sharded")  # configs[3]
     assert w["c5"]["leaf"] == 0.05 and w["c5"]["iters"] == 30 and w["c5"]["sharded"]      # configs[4], per-GPU scale
 
 
