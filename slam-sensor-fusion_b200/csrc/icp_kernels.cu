@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(kTile)
 }
 
 // ---- ordered float chains (STRICT) ------------------------------------------------------------
-constexpr int kRefThreads = 256;
+constexpr int kRefThreads = 512;  // warp 0 walks the chains, 15 warps stage the next tile's values
 constexpr int kChainTile = 512;
 constexpr int kChainMax = 9;
 
@@ -689,9 +689,10 @@ __device__ void strict_chains(const float4 *P, const float4 *Q, const int32_t *c
             const uint32_t row = t * kChainTile + j;
             float o[kChainMax];
             if (row < n) {
-                const bool alive = corr[base + row] >= 0;
-                float4 p = make_float4(0, 0, 0, 0), q = p;
-                if (alive) { p = P[base + row]; q = Q[base + row]; }
+                // three independent loads (P / Q of a dropped row are stale or unset: never used)
+                const int32_t c = corr[base + row];
+                const float4 p = P[base + row], q = Q[base + row];
+                const bool alive = c >= 0;
                 if (PASS == 1) rowvals_pass1(p, q, alive, o);
                 else rowvals_pass2(p, q, alive, cs, ct, o);
             } else {
