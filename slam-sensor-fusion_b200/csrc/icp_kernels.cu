@@ -637,11 +637,11 @@ __global__ void __launch_bounds__(kTile)
 
 // ---- ordered float chains (STRICT) ------------------------------------------------------------
 constexpr int kRefThreads = 512;  // warp 0 walks the chains, 15 warps stage the next tile's values
-constexpr int kChainTile = 512;
+constexpr int kChainTile = 1024;  // rows staged per buffer: long enough that staging the next one hides behind the chain
 constexpr int kChainMax = 9;
 
 struct ChainBuf {
-    float v[2][kChainMax][kChainTile + 1];
+    float v[2][kChainMax][kChainTile + 4];  // 16-byte aligned columns (the chain warp reads them with 128-bit loads)
 };
 
 // per-row values of the first pass: |p - q| (cpp:166), p (cpp:119), q (cpp:120)
@@ -684,21 +684,33 @@ __device__ void strict_chains(const float4 *P, const float4 *Q, const int32_t *c
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_tiles = (n + kChainTile - 1) / kChainTile;
+    // staging by warps 1..: every thread issues the loads of ALL its rows of the tile first (three
+    // independent loads per row; P / Q of a dropped row are stale or unset and never used), then
+    // computes and stores -- one memory latency per tile instead of one per row
+    constexpr int kFillThreads = kRefThreads - 32;
+    constexpr int kFillRows = (kChainTile + kFillThreads - 1) / kFillThreads;
     auto fill = [&](uint32_t t, int which) {
-        for (uint32_t j = threadIdx.x - 32; j < (uint32_t)kChainTile; j += kRefThreads - 32) {
-            const uint32_t row = t * kChainTile + j;
-            float o[kChainMax];
-            if (row < n) {
-                // three independent loads (P / Q of a dropped row are stale or unset: never used)
-                const int32_t c = corr[base + row];
-                const float4 p = P[base + row], q = Q[base + row];
-                const bool alive = c >= 0;
-                if (PASS == 1) rowvals_pass1(p, q, alive, o);
-                else rowvals_pass2(p, q, alive, cs, ct, o);
-            } else {
+        int32_t c[kFillRows];
+        float4 p[kFillRows], q[kFillRows];
 #pragma unroll
-                for (int i = 0; i < NCH; ++i) o[i] = 0.f;
+        for (int k = 0; k < kFillRows; ++k) {
+            const uint32_t j = threadIdx.x - 32 + (uint32_t)k * kFillThreads, row = t * kChainTile + j;
+            c[k] = -1;
+            p[k] = q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < (uint32_t)kChainTile && row < n) {
+                c[k] = corr[base + row];
+                p[k] = P[base + row];
+                q[k] = Q[base + row];
             }
+        }
+#pragma unroll
+        for (int k = 0; k < kFillRows; ++k) {
+            const uint32_t j = threadIdx.x - 32 + (uint32_t)k * kFillThreads;
+            if (j >= (uint32_t)kChainTile) continue;
+            float o[kChainMax];
+            const bool alive = c[k] >= 0;  // rows past the end of the scan: c = -1 -> exact zeros
+            if (PASS == 1) rowvals_pass1(p[k], q[k], alive, o);
+            else rowvals_pass2(p[k], q[k], alive, cs, ct, o);
 #pragma unroll
             for (int i = 0; i < NCH; ++i) buf.v[which][i][j] = o[i];
         }
@@ -711,19 +723,30 @@ __device__ void strict_chains(const float4 *P, const float4 *Q, const int32_t *c
             if (lane < NCH) {
                 // the adds are one dependent chain (4 cycles each); keep the next 16 values in
                 // registers so the shared-memory loads never sit on the chain
-                const float *col = buf.v[t & 1][lane];
-                float cur[16], nxt[16];
+                // two register sets in alternation: the four 128-bit loads of one are issued before the
+                // 16 dependent adds of the other, so their latency hides behind the chain (measured
+                // 5.3 cycles per row against 4.1 for the adds alone, profiles/exp/mb/chain.cu)
+                const float4 *col = reinterpret_cast<const float4 *>(buf.v[t & 1][lane]);
+                float4 a[4], b[4];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) cur[u] = col[u];
-                for (int j = 0; j < kChainTile; j += 16) {
-                    if (j + 16 < kChainTile) {
+                for (int u = 0; u < 4; ++u) a[u] = col[u];
+                for (int j = 0; j < kChainTile / 4; j += 8) {
 #pragma unroll
-                        for (int u = 0; u < 16; ++u) nxt[u] = col[j + 16 + u];
+                    for (int u = 0; u < 4; ++u) b[u] = col[j + 4 + u];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        acc = __fadd_rn(acc, a[u].x); acc = __fadd_rn(acc, a[u].y);
+                        acc = __fadd_rn(acc, a[u].z); acc = __fadd_rn(acc, a[u].w);
+                    }
+                    if (j + 8 < kChainTile / 4) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) a[u] = col[j + 8 + u];
                     }
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) acc = __fadd_rn(acc, cur[u]);
-#pragma unroll
-                    for (int u = 0; u < 16; ++u) cur[u] = nxt[u];
+                    for (int u = 0; u < 4; ++u) {
+                        acc = __fadd_rn(acc, b[u].x); acc = __fadd_rn(acc, b[u].y);
+                        acc = __fadd_rn(acc, b[u].z); acc = __fadd_rn(acc, b[u].w);
+                    }
                 }
             }
         } else if (t + 1 < n_tiles) {
@@ -787,7 +810,8 @@ __global__ void __launch_bounds__(kRefThreads)
                       const int32_t *__restrict__ corr, int phase, int pass, int reduce, float acc_err, float eps,
                       float *trace_err, int32_t *trace_search, int trace_len)
 {
-    __shared__ ChainBuf buf;
+    extern __shared__ __align__(16) unsigned char ref_dyn_smem[];  // 2 x 9 x 1025 floats: above the static limit
+    ChainBuf &buf = *reinterpret_cast<ChainBuf *>(ref_dyn_smem);
     __shared__ double dscratch[kRefThreads];
     __shared__ uint32_t uscratch[kRefThreads / 32];
     __shared__ float sums1[7], sums2[9], cs[3], ct[3];
@@ -1110,17 +1134,22 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
                       "across ranks); use a GN or O3D mode");
             return SSF_ERR_STATE;
         }
+        static bool ref_attr_set = false;
+        if (!ref_attr_set) {
+            SSF_CUDA(cudaFuncSetAttribute(ref_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainBuf)));
+            ref_attr_set = true;
+        }
         TIMED_SEARCH((ref_search_kernel<<<tiles, kTile, 0, st>>>(map, b.src.p, b.P.p, b.Q.p, b.corr.p, b.tile_scan.p, S,
                                                                 limit, 1)));
         g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
         for (int i = 0; i < cfg.num_iterations; ++i) {
-            ref_reduce_kernel<<<scans, kRefThreads, 0, st>>>(S, b.P.p, b.Q.p, b.corr.p, i == 0 ? 0 : 1, i, cfg.reduce,
+            ref_reduce_kernel<<<scans, kRefThreads, sizeof(ChainBuf), st>>>(S, b.P.p, b.Q.p, b.corr.p, i == 0 ? 0 : 1, i, cfg.reduce,
                                                              cfg.acc_err, cfg.eps, b.trace_err.p, b.trace_search.p,
                                                              b.trace_len);
             SSF_LAUNCHED();
             ref_search_kernel<<<tiles, kTile, 0, st>>>(map, b.src.p, b.P.p, b.Q.p, b.corr.p, b.tile_scan.p, S, limit, 0);
             SSF_LAUNCHED();
-            ref_reduce_kernel<<<scans, kRefThreads, 0, st>>>(S, b.P.p, b.Q.p, b.corr.p, 2, i, cfg.reduce, cfg.acc_err,
+            ref_reduce_kernel<<<scans, kRefThreads, sizeof(ChainBuf), st>>>(S, b.P.p, b.Q.p, b.corr.p, 2, i, cfg.reduce, cfg.acc_err,
                                                              cfg.eps, b.trace_err.p, b.trace_search.p, b.trace_len);
             SSF_LAUNCHED();
             if (i + 1 < cfg.num_iterations) {
