@@ -94,6 +94,26 @@ def test_nn_any_cell_edge_any_threshold(gpu, ora, cell, thr, monkeypatch):
     assert n_in > (1000 if thr >= 0.5 else 100)
 
 
+def test_nn_degenerate_maps(gpu, ora):
+    """Maps the cell-size search has to survive: one point, all points identical, a line, a plane, a cloud
+    far from the origin (large coordinates, small spacing) and a millimetre-scale cloud."""
+    rng = np.random.default_rng(11)
+    line = np.c_[np.linspace(-5, 5, 4001), np.zeros(4001), np.zeros(4001)].astype(np.float32)
+    plane = np.c_[rng.uniform(-4, 4, (20000, 2)), np.zeros(20000)].astype(np.float32)
+    far = (rng.uniform(-3, 3, (30000, 3)) * np.array([1, 1, 0.02]) + np.array([40000.0, -25000.0, 300.0])).astype(np.float32)
+    tiny = (rng.uniform(-1, 1, (20000, 3)) * 1e-3).astype(np.float32)
+    cases = [
+        (np.array([[1.0, 2.0, 3.0]], np.float32), rng.uniform(0, 4, (500, 3)).astype(np.float32), 0.5),
+        (np.tile(np.array([[0.5, -0.25, 2.0]], np.float32), (3000, 1)), rng.uniform(-1, 3, (500, 3)).astype(np.float32), 0.5),
+        (line, np.c_[rng.uniform(-6, 6, 2000), rng.normal(0, 0.2, 2000), rng.normal(0, 0.2, 2000)].astype(np.float32), 0.5),
+        (plane, np.c_[rng.uniform(-5, 5, (3000, 2)), rng.normal(0, 0.3, 3000)].astype(np.float32), 0.5),
+        (far, (far[::13] + rng.normal(0, 0.05, far[::13].shape)).astype(np.float32), 0.5),
+        (tiny, (tiny[::7] + rng.normal(0, 5e-5, tiny[::7].shape)).astype(np.float32), 1e-7),
+    ]
+    for m, q, thr in cases:
+        assert _check_nn(gpu, ora, m, q, thr) > 0
+
+
 def test_nn_synthetic_map(gpu, ora, c1_world):
     w = c1_world
     T0 = w["T0"].astype(np.float32)
@@ -274,6 +294,36 @@ def test_certificates_change_nothing(gpu, c1_world, small_world, mode, monkeypat
             assert (x.iterations, x.n_searches, x.k_final, x.has_converged) == (y.iterations, y.n_searches, y.k_final,
                                                                                 y.has_converged)
             assert np.float32(x.error).view(np.uint32) == np.float32(y.error).view(np.uint32)
+
+
+def test_certificates_with_ties(gpu, monkeypatch):
+    """Lattice map with every point duplicated: nearest and second-nearest distances coincide all over, so
+    certificates must refuse to confirm and the walk must break the ties by index -- same bits either way."""
+    g = np.stack(np.meshgrid(np.arange(-20, 21), np.arange(-20, 21), indexing="ij"), -1).reshape(-1, 2).astype(np.float32) * 0.25
+    floor = np.c_[g, np.zeros(len(g), np.float32)]
+    wall = np.c_[g[:, 0], np.full(len(g), 5.0, np.float32), np.abs(g[:, 1])]
+    m = np.concatenate([floor, wall, floor, wall[::-1]]).astype(np.float32)
+    rng = np.random.default_rng(4)
+    src = np.concatenate([floor[::3], wall[::3]]) + np.float32(0.125) * np.array([1, 1, 0], np.float32)  # on cell mid-points
+    src = np.concatenate([src, src[:200] + rng.normal(0, 0.01, (200, 3)).astype(np.float32)]).astype(np.float32)
+    c, s_ = np.cos(0.02), np.sin(0.02)
+    T0 = np.array([[c, -s_, 0, 0.06], [s_, c, 0, -0.04], [0, 0, 1, 0.03], [0, 0, 0, 1]], np.float64)
+    out = []
+    for no_cert in ("0", "1"):
+        monkeypatch.setenv("SSF_NO_CERT", no_cert)
+        for mode in (gpu.MODE_GN_P2P, gpu.MODE_O3D_P2P):
+            icp = gpu.ICPPointToPoint(0.5, 15, 0.0, 0.0, mode=mode)
+            icp.setTargetPointCloud(m)
+            icp.setSourcePointCloud(src)
+            icp.setInitialTransformation(T0)
+            r = icp.calculateAlignment()
+            out.append((no_cert, mode, r, icp.correspondences().copy()))
+    for (_, _, ra, ca), (_, _, rb, cb) in zip(out[:2], out[2:]):
+        assert np.array_equal(ca, cb)
+        assert np.array_equal(ra.transformation.view(np.uint32), rb.transformation.view(np.uint32))
+        assert (ra.iterations, ra.k_final) == (rb.iterations, rb.k_final)
+        # duplicates: the reported neighbour is always the copy with the lower index
+        assert (ca[ca >= 0] < 2 * len(floor)).all()
 
 
 def test_batched_voxel_stage_matches_oracle(gpu, ora, small_world):
