@@ -18,7 +18,7 @@ for d in range(8):
     v = ssf_gpu.voxel_down_sample(synth.make_scan(T, 64, 2048, scan_id=40 * d), 0.2, ctx)
     scans.append(v); inits.append(synth.perturb_pose(T, d))
 st = (ctypes.c_ulonglong * 8)()
-for iters in (1, 10):
+for iters in (1, 2, 3, 4, 10):
     icp.setNumIterations(iters)
     b = ssf_gpu.Batch(icp, len(scans), sum(s.shape[0] for s in scans) + 1)
     b.upload(scans); b.set_initial(inits)
