@@ -135,6 +135,7 @@ struct MapView {
     int nbx, nty;    // directory: x blocks per row, 4x4 tiles along y
     float bmin[3], bmax[3];  // bounding box of the finite points
     float cert_mu;           // margin of the search certificates (nn_device.cuh), a fraction of the cell edge
+    float cert_step;         // certificates are written once the last pose update was below this (metres)
     // map sharding: this rank owns the queries whose shard column
     // floor((x - shard_ox) * shard_inv_h) lies in [own_lo, own_hi)
     float shard_ox, shard_inv_h;

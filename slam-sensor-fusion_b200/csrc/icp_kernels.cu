@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(THREADS)
         const size_t slot0 = (size_t)z.pt_begin + row0;
         // a certificate only pays off if the next pose update is small: write them once the last
         // update was below a few margins (the updates shrink fast)
-        const bool make_cert = z.last_step < 4.0f * map.cert_mu && pass < kCertHist;
+        const bool make_cert = z.last_step < map.cert_step && pass < kCertHist;
         const float *hist = pose_hist + (size_t)scan * kCertHist * 16;
         if (threadIdx.x == 0) tile_load_issue(s_q, &s_bar, src + slot0, n_here * (uint32_t)sizeof(float4));
         if (threadIdx.x < 16) sT[threadIdx.x] = z.T[threadIdx.x];
