@@ -37,6 +37,7 @@ sys.path.insert(0, os.path.join(ROOT, "slam-sensor-fusion_b200"))
 WORKLOADS = {
     # name: (map points, beams, azimuths, leaf, mode, max_range)
     "c2": dict(map_points=5_000_000, beams=64, azimuths=2048, leaf=0.2, mode="gn_p2plane", max_range=100.0,
+               scans_per_step=256,
                desc="64-beam scan (~130k pts) voxel 0.2 m + point-to-plane GN ICP (10 it, thr 0.5) vs 5M-point map"),
     "c1": dict(map_points=1_000_000, beams=32, azimuths=1024, leaf=0.0, mode="reference", max_range=100.0,
                desc="32-beam scan (~30k pts) reference point-to-point ICP (10 it, thr 0.5) vs 1M-point map"),

@@ -46,5 +46,5 @@ def test_workloads_name_the_baseline_configs():
 
 def test_traffic_record_matches_the_bench_workload():
     t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-    assert t["workload"] == "c2" and t["scans_per_step"] == bench.WORKLOADS["c2"].get("scans_per_step", 64)
+    assert t["workload"] == "c2" and t["scans_per_step"] == bench.WORKLOADS["c2"]["scans_per_step"]
     assert 1e6 < t["dram_bytes_per_launch"] < 1e9 and os.path.exists(os.path.join(ROOT, t["source"].split(":")[0]))
