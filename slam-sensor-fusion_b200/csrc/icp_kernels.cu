@@ -7,11 +7,16 @@
 // per-scan device state, and every kernel of the fixed launch sequence exits early for
 // scans that are done.
 //
-//   search_accum_kernel<GN|KABSCH>  transform + exact NN + rejection + per-block partial sums
-//   rowsum_solve_kernel (rowsum_kernel + solve_kernel when map-sharded)   ordered sum of the partial rows + 6x6 Cholesky or
-//                                         3x3 SVD + pose update + stop rules
-//   ref_search_kernel / ref_reduce_kernel / ref_step_kernel   the reference's own state
-//                                         machine, STRICT (sequential float chains) or FAST
+//   search_accum_kernel<KIND, THREADS>   persistent blocks over the tiles that hold points: TMA tile load,
+//                                         transform, certificate check or exact walk (near part, then the
+//                                         far rings packed densely), residual / Jacobian partial sums
+//   rowsum_solve_kernel                   ordered sum of a scan's partial rows + 6x6 Cholesky or 3x3 SVD +
+//                                         pose update + stop rules (map-sharded: rowsum_xchg / solve_xchg
+//                                         exchange the rows across ranks over peer memory, or rowsum_kernel
+//                                         + the caller's all-reduce hook + solve_kernel)
+//   ref_search_kernel / ref_reduce_kernel / ref_step_kernel   the reference's own state machine, STRICT
+//                                         (sequential float chains) or FAST
+//   run_batch                             the launch sequence; the GN / Open3D-flow loop as one CUDA graph
 #include <climits>
 #include <cmath>
 #include <cstdlib>
