@@ -245,6 +245,9 @@ int ssf_icp_exchange_close(ssf_icp *icp);
  * the elapsed times up and clears the list: *ms = total, *launches = how many. */
 int ssf_ctx_time_searches(ssf_ctx *ctx, int enable);
 int ssf_ctx_search_time(ssf_ctx *ctx, double *ms, uint64_t *launches);
+/* Per-launch elapsed times (ms) of the recorded launches, in launch order, without clearing the
+ * list: at most cap values are written, *launches = how many were recorded. */
+int ssf_ctx_search_times(ssf_ctx *ctx, float *ms_out, uint64_t cap, uint64_t *launches);
 
 /* ---- counters ------------------------------------------------------------------------- */
 /* Kernels launched by this library since process start (all contexts). */

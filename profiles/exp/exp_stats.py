@@ -27,5 +27,5 @@ for iters in (1, 2, 3, 4, 10):
     L.ssf_debug_nn_stats(st, 1)
     q = st[3]
     print(f"iters={iters}: queries {q}  eval4/query {st[0]/q:.2f}  dir loads/query {st[1]/q:.2f}  rows/query {st[2]/q:.2f} "
-          f"runs/query {st[6]/q:.2f}  past-ring-1 {st[4]/q:.4f}  matched {st[5]/q:.3f}")
+          f"runs/query {st[6]/q:.2f}  past-ring-1 {st[4]/q:.4f}  matched {st[5]/q:.3f}  reach-mask exits {st[7]/q:.4f}")
     b.close()

@@ -228,6 +228,20 @@ extern "C" int ssf_ctx_search_time(ssf_ctx *ctx, double *ms, uint64_t *launches)
     return SSF_OK;
 }
 
+extern "C" int ssf_ctx_search_times(ssf_ctx *ctx, float *ms_out, uint64_t cap, uint64_t *launches)
+{
+    SSF_ARG(ctx && launches && (ms_out || cap == 0), "ssf_ctx_search_times: NULL argument");
+    SSF_TRY(use_device(ctx));
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    uint64_t n = 0;
+    for (size_t i = 0; i + 1 < ctx->timer.used; i += 2, ++n) {
+        if (n >= cap) continue;
+        SSF_CUDA(cudaEventElapsedTime(&ms_out[n], ctx->timer.pool[i], ctx->timer.pool[i + 1]));
+    }
+    *launches = n;
+    return SSF_OK;
+}
+
 // ---- helpers ------------------------------------------------------------------------------------
 static int check_params(const ssf_icp_params *p)
 {
@@ -940,6 +954,7 @@ extern "C" int ssf_batch_run(ssf_batch *b)
             icp->xch.epoch += (unsigned long long)p.num_iterations + 2;  // one epoch per pass (O3D runs one more)
         }
     }
+    SSF_TRY(ensure_reach_mask(icp->map, cfg.max_corr, ctx->stream));
     SSF_TRY(run_batch(icp->map.view, cfg, buf, b->T_init_pinned.p, ctx->stream, &ctx->timer));
     SSF_CUDA(cudaEventRecord(b->ev1, ctx->stream));
     SSF_CUDA(cudaEventRecord(b->ran_ev, ctx->stream));

@@ -134,6 +134,11 @@ struct MapView {
     int nx, ny, nz;  // grid extent in cells
     int nbx, nty;    // directory: x blocks per row, 4x4 tiles along y
     float bmin[3], bmax[3];  // bounding box of the finite points
+    // reach mask (map_build.cu, build_reach_mask): one bit per cell, laid out like dir[].x; a CLEAR bit
+    // says that no target point lies within sqrt(reach2) of ANY position binned into that cell, so a
+    // search whose bound is below reach2 ends there.  nullptr when not built.
+    const uint32_t *reach;
+    float reach2;
     float cert_mu;           // margin of the search certificates (nn_device.cuh), a fraction of the cell edge
     float cert_step;         // certificates are written once the last pose update was below this (metres)
     // map sharding: this rank owns the queries whose shard column

@@ -40,7 +40,7 @@ struct BatchBuffers {
     DevBuf<uint2> cert;        // search certificates: (radius | issuing iteration, neighbour position), nn_device.cuh
     DevBuf<float> pose_hist;   // [scan][kCertHist][16]: pose used by search launch i (certificates refer to it)
     DevBuf<uint32_t> tile_scan;
-    DevBuf<uint32_t> active;     // tiles that hold points (search kernel work list)
+    DevBuf<uint4> active;        // tiles that hold points (search kernel work list): (tile, scan, first slot, points)
     DevBuf<uint32_t> counters;   // [0] number of active tiles, [1 + i] tile fetch counter of search launch i
     DevBuf<double> partials;   // [tile][kAccum]
     DevBuf<double> sums;       // [scan][kAccum]: per-scan totals (all-reduced across ranks when sharded)

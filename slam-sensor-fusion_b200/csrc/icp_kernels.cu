@@ -159,9 +159,10 @@ __global__ void zero_u32_kernel(uint32_t *p, uint32_t n)
 }
 
 // list of the tiles that hold points (a scan's slots are sized for its RAW points; after the voxel
-// stage only the first ceil(n_pts / kTile) tiles of each scan are in use)
+// stage only the first ceil(n_pts / kTile) tiles of each scan are in use).  One 16-byte record per
+// tile -- (tile, scan, first slot, points) -- so the search kernel reaches its data in one hop.
 __global__ void __launch_bounds__(128)
-    active_tiles_kernel(const ScanState *__restrict__ states, uint32_t n_scans, uint32_t *__restrict__ active,
+    active_tiles_kernel(const ScanState *__restrict__ states, uint32_t n_scans, uint4 *__restrict__ active,
                         uint32_t *__restrict__ n_active)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,7 +171,65 @@ __global__ void __launch_bounds__(128)
     const uint32_t n = (z.n_pts + kTile - 1) / kTile;
     if (n == 0) return;
     const uint32_t base = atomicAdd(n_active, n);
-    for (uint32_t k = 0; k < n; ++k) active[base + k] = z.tile_begin + k;
+    for (uint32_t k = 0; k < n; ++k)
+        active[base + k] = make_uint4(z.tile_begin + k, s, z.pt_begin + k * kTile, min((uint32_t)kTile, z.n_pts - k * kTile));
+}
+
+// One half (values 16*HALF .. 16*HALF+15 of the partial row) of the Gauss-Newton sums over this
+// thread's queries of the tile, reduced over the warp: lane l returns the warp-wide sum of value
+// 16*HALF + (l & 15).  Row layout: [0..20] J^T J upper triangle, [21..26] J^T r, [27] sum r^2, [28] K.
+template <int KIND, int HALF, int THREADS>
+__device__ __forceinline__ double gn_half(const MapView &map, const float4 *s_q, const uint32_t *s_pos, uint32_t n_here)
+{
+    constexpr int kQ_ = kTile / THREADS;
+    constexpr int lo = 16 * HALF;
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.0;
+    for (int k = 0; k < kQ_; ++k) {
+        const uint32_t r = (uint32_t)k * THREADS + threadIdx.x;
+        if (r >= n_here) break;
+        const uint32_t pos = s_pos[r];
+        if (pos == kNoPos) continue;
+        const float4 p = s_q[r];
+        const float4 q = __ldg(&map.pts[pos]);
+        const double px = p.x, py = p.y, pz = p.z;
+        const double e[3] = {px - (double)q.x, py - (double)q.y, pz - (double)q.z};
+        if (KIND == ACC_GN_P2PLANE) {
+            const float4 nf = __ldg(&map.nrm[pos]);
+            const double n[3] = {nf.x, nf.y, nf.z};
+            const double a[6] = {fma(py, n[2], -(pz * n[1])), fma(pz, n[0], -(px * n[2])),
+                                 fma(px, n[1], -(py * n[0])), n[0], n[1], n[2]};
+            int t = 0;
+#pragma unroll
+            for (int u = 0; u < 6; ++u)
+#pragma unroll
+                for (int w = u; w < 6; ++w, ++t)
+                    if (t >= lo && t < lo + 16) v[t - lo] = fma(a[u], a[w], v[t - lo]);
+            if (HALF == 1) {
+                const double rs = fma(n[0], e[0], fma(n[1], e[1], n[2] * e[2]));
+#pragma unroll
+                for (int u = 0; u < 6; ++u) v[21 - lo + u] = fma(a[u], rs, v[21 - lo + u]);
+                v[27 - lo] = fma(rs, rs, v[27 - lo]);
+            }
+        } else {
+            // J = [-[p]x | I]; J^T J = [[ -[p]x^T -[p]x , [p]x ], [ -[p]x , I ]]
+            const double J[3][6] = {{0, pz, -py, 1, 0, 0}, {-pz, 0, px, 0, 1, 0}, {py, -px, 0, 0, 0, 1}};
+            int t = 0;
+#pragma unroll
+            for (int u = 0; u < 6; ++u)
+#pragma unroll
+                for (int w = u; w < 6; ++w, ++t)
+                    if (t >= lo && t < lo + 16) v[t - lo] += J[0][u] * J[0][w] + J[1][u] * J[1][w] + J[2][u] * J[2][w];
+            if (HALF == 1) {
+#pragma unroll
+                for (int u = 0; u < 6; ++u) v[21 - lo + u] += J[0][u] * e[0] + J[1][u] * e[1] + J[2][u] * e[2];
+                v[27 - lo] += e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+            }
+        }
+        if (HALF == 1) v[28 - lo] += 1.0;
+    }
+    return warp_transpose_reduce16(v);
 }
 
 // Persistent blocks fetch tiles (kTile consecutive queries of one scan) from a shared counter;
@@ -180,12 +239,15 @@ __global__ void __launch_bounds__(128)
 //   S  the queries that could not be confirmed, packed densely over the threads: full exact walk,
 //      new certificate;
 //   K4 residual / Jacobian terms of the matched queries, 32-value warp reduction paid once per kQ.
+#ifndef SSF_MINB
+#define SSF_MINB 8
+#endif
 template <int KIND, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 1)
     search_accum_kernel(MapView map, const float4 *__restrict__ src, const uint32_t *__restrict__ tile_scan,
                         const ScanState *__restrict__ states, float limit, int32_t *__restrict__ corr,
                         double *__restrict__ partials, uint2 *__restrict__ cert, const float *__restrict__ pose_hist,
-                        int use_cert, int pass, const uint32_t *__restrict__ active,
+                        int use_cert, int pass, const uint4 *__restrict__ active,
                         const uint32_t *__restrict__ n_active, uint32_t *__restrict__ fetch)
 {
     __shared__ __align__(128) float4 s_q[kTile];  // TMA destination; transformed in place, w = owned by this rank
@@ -202,11 +264,17 @@ __global__ void __launch_bounds__(THREADS)
     const uint32_t none_hi = __float_as_uint(limit);
     const bool searchable = limit > 0.f && map.n_pts > 0;
     const uint32_t n_tiles = *n_active;
-    if (threadIdx.x == 0) tile_bar_init(&s_bar);
+    // the next tile is claimed while this tile's sums are taken (late, so that a block in a long
+    // walk does not sit on a tile another block could start): the atomic's round trip is hidden
+    uint32_t nxt = 0;
+    if (threadIdx.x == 0) {
+        tile_bar_init(&s_bar);
+        nxt = atomicAdd(fetch, 1u);
+    }
     uint32_t phase = 0;
     while (true) {
         if (threadIdx.x == 0) {
-            s_next = atomicAdd(fetch, 1u);
+            s_next = nxt;
             s_nq = 0;
             s_nfar = 0;
             s_nfar_none = 0;
@@ -214,21 +282,17 @@ __global__ void __launch_bounds__(THREADS)
         __syncthreads();
         const uint32_t ti = s_next;
         if (ti >= n_tiles) break;
-        const uint32_t tile = active[ti];
-        const uint32_t scan = tile_scan[tile];
+        const uint4 rec = active[ti];  // (tile, scan, first slot, points)
+        const uint32_t tile = rec.x, scan = rec.y, n_here = rec.w;
+        const size_t slot0 = rec.z;
+        if (threadIdx.x == 0) tile_load_issue(s_q, &s_bar, src + slot0, n_here * (uint32_t)sizeof(float4));
         const ScanState &z = states[scan];
-        const uint32_t row0 = (tile - z.tile_begin) * kTile;
-        if (z.done || row0 >= z.n_pts) {
-            __syncthreads();  // s_next is rewritten at the top
-            continue;
-        }
-        const uint32_t n_here = min((uint32_t)kTile, z.n_pts - row0);
-        const size_t slot0 = (size_t)z.pt_begin + row0;
+        SSF_CHECK(n_here > 0 && n_here <= kTile && slot0 == (size_t)z.pt_begin + (size_t)(tile - z.tile_begin) * kTile);
+        const bool done = z.done != 0;
         // a certificate only pays off if the next pose update is small: write them once the last
         // update was below a few margins (the updates shrink fast)
         const bool make_cert = z.last_step < map.cert_step && pass < kCertHist;
         const float *hist = pose_hist + (size_t)scan * kCertHist * 16;
-        if (threadIdx.x == 0) tile_load_issue(s_q, &s_bar, src + slot0, n_here * (uint32_t)sizeof(float4));
         if (threadIdx.x < 16) sT[threadIdx.x] = z.T[threadIdx.x];
         // certificates of this thread's queries: issue the loads before waiting for the tile
         uint2 crt[kQ_];
@@ -241,6 +305,11 @@ __global__ void __launch_bounds__(THREADS)
         __syncthreads();
         tile_bar_wait(&s_bar, phase);
         phase ^= 1u;
+        if (done) {
+            if (threadIdx.x == 0) nxt = atomicAdd(fetch, 1u);
+            __syncthreads();  // s_next is rewritten at the top
+            continue;
+        }
         // ---- V ----
 #pragma unroll
         for (int k = 0; k < kQ_; ++k) {
@@ -348,17 +417,19 @@ __global__ void __launch_bounds__(THREADS)
         }
         __syncthreads();
         // ---- K4: residual / Jacobian terms of the matched queries ----
-        double v[kAccum];
+        if (threadIdx.x == 0) nxt = atomicAdd(fetch, 1u);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if constexpr (KIND == ACC_KABSCH) {
+            double v[kAccum];
 #pragma unroll
-        for (int i = 0; i < kAccum; ++i) v[i] = 0.0;
-        for (int k = 0; k < kQ_; ++k) {
-            const uint32_t r = (uint32_t)k * THREADS + threadIdx.x;
-            if (r >= n_here) break;
-            const uint32_t pos = s_pos[r];
-            if (pos == kNoPos) continue;
-            const float4 p = s_q[r];
-            const float4 q = __ldg(&map.pts[pos]);
-            if (KIND == ACC_KABSCH) {
+            for (int i = 0; i < kAccum; ++i) v[i] = 0.0;
+            for (int k = 0; k < kQ_; ++k) {
+                const uint32_t r = (uint32_t)k * THREADS + threadIdx.x;
+                if (r >= n_here) break;
+                const uint32_t pos = s_pos[r];
+                if (pos == kNoPos) continue;
+                const float4 p = s_q[r];
+                const float4 q = __ldg(&map.pts[pos]);
                 const double cx = z.T_init[12], cy = z.T_init[13], cz = z.T_init[14];
                 const double a[3] = {(double)p.x - cx, (double)p.y - cy, (double)p.z - cz};
                 const double b[3] = {(double)q.x - cx, (double)q.y - cy, (double)q.z - cz};
@@ -374,42 +445,18 @@ __global__ void __launch_bounds__(THREADS)
                     for (int c = 0; c < 3; ++c) v[7 + 3 * rr + c] = fma(a[rr], b[c], v[7 + 3 * rr + c]);
                 const double ex = (double)p.x - q.x, ey = (double)p.y - q.y, ez = (double)p.z - q.z;
                 v[16] += fma(ex, ex, fma(ey, ey, ez * ez));
-            } else {
-                const double px = p.x, py = p.y, pz = p.z;
-                const double e[3] = {px - (double)q.x, py - (double)q.y, pz - (double)q.z};
-                if (KIND == ACC_GN_P2PLANE) {
-                    const float4 nf = __ldg(&map.nrm[pos]);
-                    const double n[3] = {nf.x, nf.y, nf.z};
-                    const double a[6] = {fma(py, n[2], -(pz * n[1])), fma(pz, n[0], -(px * n[2])),
-                                         fma(px, n[1], -(py * n[0])), n[0], n[1], n[2]};
-                    const double rs = fma(n[0], e[0], fma(n[1], e[1], n[2] * e[2]));
-                    int t = 0;
-#pragma unroll
-                    for (int u = 0; u < 6; ++u)
-#pragma unroll
-                        for (int w = u; w < 6; ++w, ++t) v[t] = fma(a[u], a[w], v[t]);
-#pragma unroll
-                    for (int u = 0; u < 6; ++u) v[21 + u] = fma(a[u], rs, v[21 + u]);
-                    v[27] = fma(rs, rs, v[27]);
-                } else {
-                    // J = [-[p]x | I]; J^T J = [[ -[p]x^T -[p]x , [p]x ], [ -[p]x , I ]]
-                    const double J[3][6] = {{0, pz, -py, 1, 0, 0}, {-pz, 0, px, 0, 1, 0}, {py, -px, 0, 0, 0, 1}};
-                    int t = 0;
-#pragma unroll
-                    for (int u = 0; u < 6; ++u)
-#pragma unroll
-                        for (int w = u; w < 6; ++w)
-                            v[t++] += J[0][u] * J[0][w] + J[1][u] * J[1][w] + J[2][u] * J[2][w];
-#pragma unroll
-                    for (int u = 0; u < 6; ++u) v[21 + u] += J[0][u] * e[0] + J[1][u] * e[1] + J[2][u] * e[2];
-                    v[27] += e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
-                }
-                v[28] += 1.0;
+            }
+            sred[warp][lane] = warp_transpose_reduce32(v);
+        } else {
+            // the 29 sums are taken in two halves of 16 accumulators (32 registers each instead of
+            // 64): the second half re-reads the neighbour (an L1 hit) and recomputes the six-vector
+            const double lo = gn_half<KIND, 0, THREADS>(map, s_q, s_pos, n_here);
+            const double hi = gn_half<KIND, 1, THREADS>(map, s_q, s_pos, n_here);
+            if (lane < 16) {
+                sred[warp][lane] = lo;
+                sred[warp][16 + lane] = hi;
             }
         }
-        const double w = warp_transpose_reduce32(v);
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        sred[warp][lane] = w;
         __syncthreads();
         if (threadIdx.x < kAccum) {
             double sum = 0.0;

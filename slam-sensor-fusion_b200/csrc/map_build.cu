@@ -140,6 +140,7 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
         return SSF_ERR_INVALID;
     }
     m.view = MapView{};
+    m.reach_limit = -1.f;
     m.cell_size = 0.f;
     m.n_cells = m.n_dir = 0;
     m.build_passes = 0;
@@ -264,6 +265,75 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
     m.n_cells = n_cells;
     m.n_dir = (uint32_t)g.n_dir;
     m.cell_size = h;
+    return SSF_OK;
+}
+
+// ---- reach mask ------------------------------------------------------------------------------------
+// bit (cx & 31) of out[dir_index(cx >> 5, cy, cz)] is set iff some occupied cell c' can hold a point
+// within `reach` of a position binned into cell c.  Lower bound of that distance along one axis for
+// a cell offset D: (|D| - 1 - slack) cells of edge hq (slack covers the rounding of the binning
+// expression for both points, hq under-estimates the edge); the three axes add in squares.  A set
+// bit promises nothing (the walk runs as usual); a clear bit is a proof of emptiness.
+__global__ void __launch_bounds__(256)
+    reach_mask_kernel(const uint2 *__restrict__ dir, uint32_t n_dir, int ny, int nz, int nbx, int nty, int K, float slack,
+                      float hq, float reach2, uint32_t *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_dir) return;
+    const uint32_t t = i >> 4;
+    const int bx = (int)(t % (uint32_t)nbx);
+    const int cy = (int)((t / (uint32_t)nbx) % (uint32_t)nty) * 4 + (int)(i & 3u);
+    const int cz = (int)(t / ((uint32_t)nbx * (uint32_t)nty)) * 4 + (int)((i >> 2) & 3u);
+    uint32_t res = 0;
+    if (cy < ny && cz < nz) {
+        for (int dz = -K; dz <= K; ++dz) {
+            const int rz = cz + dz;
+            if (rz < 0 || rz >= nz) continue;
+            const float gz = fmaxf((float)abs(dz) - 1.0f - slack, 0.f) * hq;
+            for (int dy = -K; dy <= K; ++dy) {
+                const int ry = cy + dy;
+                if (ry < 0 || ry >= ny) continue;
+                const float gy = fmaxf((float)abs(dy) - 1.0f - slack, 0.f) * hq;
+                const float rem = __fmul_ru(__fsub_ru(reach2, __fadd_rd(__fmul_rd(gy, gy), __fmul_rd(gz, gz))), 1.00001f);
+                if (!(rem > 0.f)) continue;
+                const int dxmax = min((int)floorf(1.0f + slack + __fdiv_ru(__fsqrt_ru(rem), hq) + 1e-3f), 31);
+                const uint32_t cur = dir[dir_index(nbx, nty, bx, ry, rz)].x;
+                const uint32_t prev = bx > 0 ? dir[dir_index(nbx, nty, bx - 1, ry, rz)].x : 0u;
+                const uint32_t next = bx + 1 < nbx ? dir[dir_index(nbx, nty, bx + 1, ry, rz)].x : 0u;
+                if (!(cur | prev | next)) continue;
+                const unsigned long long lo = ((unsigned long long)cur << 32) | prev, hi = ((unsigned long long)next << 32) | cur;
+                res |= cur;
+                for (int sft = 1; sft <= dxmax; ++sft) res |= (uint32_t)(lo >> (32 - sft)) | (uint32_t)(hi >> sft);
+            }
+        }
+    }
+    out[i] = res;
+}
+
+int ensure_reach_mask(MapIndex &m, float limit, cudaStream_t st)
+{
+    const char *off = getenv("SSF_NO_REACH");
+    if (m.view.n_pts == 0 || !(limit > 0.f) || !std::isfinite(limit) || m.n_dir == 0 || (off && atoi(off) != 0)) {
+        m.view.reach = nullptr;
+        m.reach_limit = -1.f;
+        return SSF_OK;
+    }
+    if (m.reach_limit == limit) return SSF_OK;
+    // what a walk prunes with: (sqrt(limit) + mu)^2 in certificate mode, limit otherwise
+    const double reach = (sqrt((double)limit) * (1.0 + 2e-6) + (double)m.view.cert_mu) * (1.0 + 1e-5);
+    const double slack = 8e-7 * (double)(std::max(m.view.nx, std::max(m.view.ny, m.view.nz)) + 4);
+    const int K = (int)ceil(1.0 + slack + reach / (double)m.view.hq);
+    m.reach_limit = limit;
+    if (K > 6) {  // (2K+1)^2 rows per cell: the mask would clear too few bits to pay for itself
+        m.view.reach = nullptr;
+        return SSF_OK;
+    }
+    SSF_TRY(m.reach.reserve(m.n_dir));
+    reach_mask_kernel<<<(m.n_dir + 255) / 256, 256, 0, st>>>(m.dir.p, m.n_dir, m.view.ny, m.view.nz, m.view.nbx, m.view.nty, K,
+                                                              (float)slack, m.view.hq, (float)(reach * reach), m.reach.p);
+    SSF_LAUNCHED();
+    m.view.reach = m.reach.p;
+    m.view.reach2 = nextafterf((float)(reach * reach * (1.0 - 1e-5)), 0.f);
     return SSF_OK;
 }
 

@@ -24,6 +24,8 @@ struct MapIndex {
     DevBuf<uint32_t> cell_start;
     DevBuf<uint2> dir;
     DevBuf<float> small;  // bbox (6 floats) + counters
+    DevBuf<uint32_t> reach;     // reach mask of view.reach, built for reach_limit
+    float reach_limit = -1.f;   // the rejection threshold the mask was built for (< 0: none)
     MapView view{};
     size_t n_raw = 0;       // points given to set_target
     bool has_normals = false;
@@ -37,5 +39,10 @@ struct MapIndex {
 // cell_size > 0 fixes the cell edge; cell_size <= 0 picks it from the measured occupancy
 // (target: a few points per occupied cell).
 int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st);
+
+// Make m.view.reach valid for searches with the rejection threshold `limit` (squared distance) and the
+// map's certificate margin: (re)built when the threshold changes, dropped (nullptr) when the reach
+// spans too many cells to pay off.  Stream-ordered; never call inside a graph capture.
+int ensure_reach_mask(MapIndex &m, float limit, cudaStream_t st);
 
 }  // namespace ssf

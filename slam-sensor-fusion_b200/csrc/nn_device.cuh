@@ -296,6 +296,15 @@ __device__ __forceinline__ bool nn_walk_near(const MapView &m, float px, float p
     q.xdn2 = gap_sq(ax.dn);
     q.xup2 = gap_sq(ax.up);
     q.xlim2 = gap_sq(__fadd_rd(fminf(ax.dn, ax.up), m.hq));
+    // reach mask: a clear bit proves that nothing lies within sqrt(reach2) of this cell
+    if (!seeded && m.reach != nullptr && B.prune() < m.reach2 && q.cx >= 0 && q.cx < m.nx && q.cy >= 0 && q.cy < m.ny &&
+        q.cz >= 0 && q.cz < m.nz) {
+        const uint32_t w = __ldg(&m.reach[dir_index(m.nbx, m.nty, q.cx >> 5, q.cy, q.cz)]);
+        if (!((w >> (q.cx & 31)) & 1u)) {
+            NN_STAT(7, 1);
+            return false;
+        }
+    }
     // own row: with a seed, just the cells its distance reaches; else start with the cells
     // cx-1..cx+1, then whatever else of the row is still in reach
     if (q.cy >= 0 && q.cy < m.ny && q.cz >= 0 && q.cz < m.nz) {
@@ -467,6 +476,23 @@ __device__ __forceinline__ double warp_transpose_reduce32(double (&v)[32])
         }
     }
     return v[0];
+}
+
+// 16 doubles per thread: after the call lane l holds the warp-wide sum of v[l & 15]
+__device__ __forceinline__ double warp_transpose_reduce16(double (&v)[16])
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int half = 8; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const double send = up ? v[i] : v[i + half];
+            const double keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
 }  // namespace ssf

@@ -69,6 +69,12 @@ class Context:
         capi.check(capi.lib().ssf_ctx_search_time(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, int(n.value)
 
+    def search_times(self, cap: int = 4096):
+        """Per-launch times (ms) of the NN-search kernels recorded so far (list not cleared)."""
+        buf, n = (ctypes.c_float * cap)(), ctypes.c_uint64(0)
+        capi.check(capi.lib().ssf_ctx_search_times(self._h, buf, cap, ctypes.byref(n)))
+        return [float(buf[i]) for i in range(min(cap, int(n.value)))]
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             capi.lib().ssf_ctx_destroy(self._h)

@@ -13,7 +13,7 @@ MODE_REFERENCE, MODE_GN_P2P, MODE_GN_P2PLANE, MODE_O3D_P2P = 0, 1, 2, 3
 REDUCE_STRICT, REDUCE_FAST = 0, 1
 
 EXPORTS = [
-    "ssf_last_error", "ssf_version", "ssf_ctx_create", "ssf_ctx_destroy", "ssf_ctx_synchronize", "ssf_ctx_stream", "ssf_ctx_time_searches", "ssf_ctx_search_time",
+    "ssf_last_error", "ssf_version", "ssf_ctx_create", "ssf_ctx_destroy", "ssf_ctx_synchronize", "ssf_ctx_stream", "ssf_ctx_time_searches", "ssf_ctx_search_time", "ssf_ctx_search_times",
     "ssf_icp_create", "ssf_icp_destroy", "ssf_icp_set_params", "ssf_icp_get_params", "ssf_icp_set_target",
     "ssf_icp_set_source", "ssf_icp_set_initial", "ssf_icp_align", "ssf_icp_get_correspondences", "ssf_icp_get_trace",
     "ssf_icp_target_size", "ssf_icp_set_target_shard", "ssf_icp_set_allreduce", "ssf_icp_exchange_create", "ssf_icp_exchange_open", "ssf_icp_exchange_close", "ssf_nn_search", "ssf_nn_search_bench", "ssf_voxel_downsample", "ssf_cloud_subsample", "ssf_cloud_remove_floor", "ssf_cloud_crop_radius", "ssf_bfa_pose_count", "ssf_bfa_align", "ssf_batch_create", "ssf_batch_destroy",
@@ -69,6 +69,7 @@ def lib() -> ctypes.CDLL:
     L.ssf_ctx_stream.restype = vp
     L.ssf_ctx_time_searches.argtypes = [vp, i32]
     L.ssf_ctx_search_time.argtypes = [vp, P(ctypes.c_double), P(ctypes.c_uint64)]
+    L.ssf_ctx_search_times.argtypes = [vp, P(ctypes.c_float), ctypes.c_uint64, P(ctypes.c_uint64)]
     L.ssf_icp_create.argtypes = [vp, P(IcpParams), P(vp)]
     L.ssf_icp_destroy.argtypes = [vp]
     L.ssf_icp_destroy.restype = None
