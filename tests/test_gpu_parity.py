@@ -296,6 +296,54 @@ def test_certificates_change_nothing(gpu, c1_world, small_world, mode, monkeypat
             assert np.float32(x.error).view(np.uint32) == np.float32(y.error).view(np.uint32)
 
 
+@pytest.mark.parametrize("mode", ["p2p", "p2plane"])
+def test_reach_mask_changes_nothing(gpu, ora, c1_world, mode, monkeypatch):
+    """The reach mask (one bit per map cell: "no target point within the rejection radius of any
+    position in this cell") only ends walks that could not have found anything.  The target is the
+    10 m crop of the map around the pose -- the reference's own usage (localization_node.cpp:302) --
+    so most of the scan lies in cleared cells; with the mask switched off (SSF_NO_REACH=1) every
+    pose, error, count and correspondence must be bit-identical.  Also against the oracle's NN."""
+    w = c1_world
+    c = w["T_gt"][:3, 3].astype(np.float32)
+    keep = np.linalg.norm(w["map"][:, :3] - c, axis=1) < 10.0
+    tgt, nrm = np.ascontiguousarray(w["map"][keep]), np.ascontiguousarray(w["normals"][keep])
+    assert 1000 < tgt.shape[0] < w["map"].shape[0] // 2
+    out = []
+    for off in ("0", "1"):
+        monkeypatch.setenv("SSF_NO_REACH", off)
+        m = {"p2p": gpu.MODE_GN_P2P, "p2plane": gpu.MODE_GN_P2PLANE}[mode]
+        icp = gpu.ICPPointToPoint(0.5, 8, 0.0, 0.0, mode=m)
+        icp.setTargetPointCloud(tgt, nrm)
+        icp.setSourcePointCloud(w["scan"])
+        icp.setInitialTransformation(w["T0"])
+        r = icp.calculateAlignment()
+        out.append((r, icp.correspondences().copy()))
+        # the threshold changes: the mask is rebuilt for it (coarse parameter set of the node)
+        icp.setMaxCorrespondenceDist(5.0)
+        r2 = icp.calculateAlignment()
+        out[-1] += (r2, icp.correspondences().copy())
+    (ra, ca, ra2, ca2), (rb, cb, rb2, cb2) = out
+    assert np.array_equal(ca, cb) and np.array_equal(ca2, cb2)
+    assert (ca >= 0).sum() > 100 and (ca < 0).sum() > 100  # both kinds of query are present
+    for x, y in ((ra, rb), (ra2, rb2)):
+        assert np.array_equal(x.transformation.view(np.uint32), y.transformation.view(np.uint32))
+        assert (x.iterations, x.n_searches, x.k_final) == (y.iterations, y.n_searches, y.k_final)
+        assert np.float32(x.error).view(np.uint32) == np.float32(y.error).view(np.uint32)
+    # the parity entry point walks the same index: with the mask in place (built by the run above
+    # for thr 5.0, rebuilt here for 0.5) its answers must still be the oracle's exact NN
+    monkeypatch.setenv("SSF_NO_REACH", "0")
+    icp.setMaxCorrespondenceDist(0.5)
+    icp.calculateAlignment()
+    q = (w["scan"][:, :3].astype(np.float64) @ w["T0"][:3, :3].T + w["T0"][:3, 3]).astype(np.float32)
+    for thr in (0.5, 0.05):
+        gi, gd = icp.nearest(q, thr)
+        oi, od = ora.KdTree(tgt).nn(q, threads=8)
+        inside = od < np.float32(thr)
+        assert np.array_equal(gi[inside], oi[inside])
+        assert np.array_equal(gd[inside].view(np.uint32), od[inside].view(np.uint32))
+        assert (gi[~inside] == -1).all() and inside.sum() > 100 and (~inside).sum() > 100
+
+
 def test_certificates_with_ties(gpu, monkeypatch):
     """Lattice map with every point duplicated: nearest and second-nearest distances coincide all over, so
     certificates must refuse to confirm and the walk must break the ties by index -- same bits either way."""
@@ -389,3 +437,30 @@ def test_golden_fixture(gpu):
     assert dt < TOL_T and dr < TOL_R and abs(r.iterations - int(g["gn_p2plane_iterations"])) <= 1
     v = gpu.voxel_down_sample(g["scan"], 0.2)
     assert np.array_equal(v.view(np.uint32), g["vox_02"][:, :3].copy().view(np.uint32))
+
+
+def test_search_timer(gpu, small_world):
+    """ssf_ctx_time_searches / ssf_ctx_search_times / ssf_ctx_search_time: one event pair per K3 launch,
+    per-launch read-out in launch order, the total equals their sum and clears the list."""
+    w = small_world
+    ctx = gpu.default_context()
+    icp = gpu.ICPPointToPoint(0.5, 6, 0.0, 0.0, mode=gpu.MODE_GN_P2PLANE)
+    icp.setTargetPointCloud(w["map"], w["normals"])
+    b = gpu.Batch(icp, 2, 2 * w["scan"].shape[0] + 1)
+    b.upload([w["scan"], w["scan"]])
+    b.set_initial([w["T0"], w["T_gt"]])
+    b.run()
+    ref = b.results()
+    ctx.time_searches(True)
+    b.run()
+    b.run()
+    t = ctx.search_times()
+    assert len(t) == 12 and all(x > 0.0 for x in t)
+    assert len(ctx.search_times(cap=5)) == 5
+    total, n = ctx.search_time()
+    assert n == 12 and abs(total - sum(t)) < 1e-3 * max(total, 1e-3)
+    assert ctx.search_time()[1] == 0
+    ctx.time_searches(False)
+    # the timed (non-graph) path gives the same results as the graph replay
+    for x, y in zip(ref, b.results()):
+        assert np.array_equal(x.transformation.view(np.uint32), y.transformation.view(np.uint32))
