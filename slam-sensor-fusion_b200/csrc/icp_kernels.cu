@@ -232,6 +232,95 @@ __device__ __forceinline__ double gn_half(const MapView &map, const float4 *s_q,
     return warp_transpose_reduce16(v);
 }
 
+// ---- Gauss-Newton sums as a Gram matrix on the FP64 tensor core ------------------------------------
+// The 29 sums of a partial row are the upper triangle of F F^T, F = one 8-vector of features per
+// residual: (a0..a5, r, 1) with a = J^T row and r the residual -- J^T J = sum a a^T, J^T r = sum a r,
+// sum r^2 and the count K all fall out of one 8x8 product.  mma.sync m8n8k4 (f64) adds four
+// residuals per instruction into an accumulator of two doubles per lane, so a thread keeps 2
+// accumulators instead of 29 and the warp needs no shuffle reduction at all.
+// Fragment layout (PTX ISA, mma.m8n8k4 .f64): lane l holds A[l >> 2][l & 3], B[l & 3][l >> 2] and
+// C[l >> 2][2 (l & 3) + {0, 1}]; with A = F (feature x residual) and B = F^T both operands of a
+// lane are the same value F[l >> 2][4 j + (l & 3)].
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// one feature vector per lane -> F F^T added to (c0, c1).  F is staged in the warp's 2 KB tile,
+// [feature][lane ^ (feature << 2)]: the swizzle makes the stores and the fragment loads free of
+// bank conflicts (a fragment load touches columns 4 (j ^ g) + t: all 32 of a row pair).
+__device__ __forceinline__ void gram_round(double *F, const double (&f)[8], double &c0, double &c1)
+{
+    const uint32_t lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    __syncwarp();  // the previous round's fragment loads are done
+#pragma unroll
+    for (uint32_t i = 0; i < 8; ++i) F[i * 32 + (lane ^ (i << 2))] = f[i];
+    __syncwarp();
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j) {
+        const double x = F[g * 32 + (((j ^ g) << 2) | t)];
+        dmma_m8n8k4(c0, c1, x, x);
+    }
+}
+
+// partial-row index of Gram entry (R, col), R <= col; -1 for entries the row does not keep.
+// Row layout: [0..20] J^T J upper triangle (row-major), [21..26] J^T r, [27] sum r^2, [28] K.
+__device__ __forceinline__ int gram_slot(int R, int col)
+{
+    if (R > col) return -1;
+    if (col <= 5) return R * 6 - R * (R - 1) / 2 + (col - R);
+    if (col == 6) return R <= 5 ? 21 + R : 27;
+    return R == 7 ? 28 : -1;
+}
+
+// the Gauss-Newton sums of this warp's queries of the tile -> row[0..31] (shared memory)
+template <int KIND, int THREADS>
+__device__ __forceinline__ void gn_gram(const MapView &map, const float4 *s_q, const uint32_t *s_pos, uint32_t n_here,
+                                        double *F, double *row)
+{
+    constexpr int kQ_ = kTile / THREADS;
+    const uint32_t lane = threadIdx.x & 31;
+    double c0 = 0.0, c1 = 0.0;
+    // (loading the gathers of all four queries up front was measured slower: 132 -> 143 us per
+    // converged launch)
+    for (int k = 0; k < kQ_; ++k) {
+        const uint32_t r = (uint32_t)k * THREADS + threadIdx.x;
+        const uint32_t pos = r < n_here ? s_pos[r] : kNoPos;
+        const bool hit = pos != kNoPos;
+        if (!__any_sync(0xffffffffu, hit)) continue;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = p, nf = p;
+        if (hit) {
+            p = s_q[r];
+            q = __ldg(&map.pts[pos]);
+            if (KIND == ACC_GN_P2PLANE) nf = __ldg(&map.nrm[pos]);
+        }
+        const double px = p.x, py = p.y, pz = p.z;
+        const double e[3] = {px - (double)q.x, py - (double)q.y, pz - (double)q.z};
+        const double one = hit ? 1.0 : 0.0;
+        if (KIND == ACC_GN_P2PLANE) {
+            const double n[3] = {nf.x, nf.y, nf.z};
+            const double f[8] = {fma(py, n[2], -(pz * n[1])), fma(pz, n[0], -(px * n[2])), fma(px, n[1], -(py * n[0])),
+                                 n[0], n[1], n[2], fma(n[0], e[0], fma(n[1], e[1], n[2] * e[2])), one};
+            gram_round(F, f, c0, c1);
+        } else {
+            // J = [-[p]x | I]: three residual rows per query; the count rides on the first
+            const double f0[8] = {0.0, pz, -py, one, 0.0, 0.0, e[0], one};
+            const double f1[8] = {-pz, 0.0, px, 0.0, one, 0.0, e[1], 0.0};
+            const double f2[8] = {py, -px, 0.0, 0.0, 0.0, one, e[2], 0.0};
+            gram_round(F, f0, c0, c1);
+            gram_round(F, f1, c0, c1);
+            gram_round(F, f2, c0, c1);
+        }
+    }
+    const int R = (int)(lane >> 2), col = 2 * (int)(lane & 3);
+    if (lane < 3) row[29 + lane] = 0.0;
+    const int s0 = gram_slot(R, col), s1 = gram_slot(R, col + 1);
+    if (s0 >= 0) row[s0] = c0;
+    if (s1 >= 0) row[s1] = c1;
+}
+
 // Persistent blocks fetch tiles (kTile consecutive queries of one scan) from a shared counter;
 // every thread takes kQ queries of a tile.
 //   V  transform; with use_cert, try to confirm last iteration's neighbour from its certificate
@@ -254,9 +343,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 1)
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_pos[kTile];
     __shared__ unsigned short s_queue[kTile], s_far[kTile];
-    __shared__ unsigned long long s_key[kTile];
-    __shared__ float s_b2[kTile];
-    __shared__ uint32_t s_skip[kTile];
+    // walk state per query; dead once the correspondences are written, when the same 8 KB hold the
+    // feature tiles of the Gauss-Newton Gram matrix (gram_round)
+    __shared__ __align__(16) unsigned char s_raw[kTile * 16];
+    unsigned long long *const s_key = reinterpret_cast<unsigned long long *>(s_raw);
+    float *const s_b2 = reinterpret_cast<float *>(s_raw + kTile * 8);
+    uint32_t *const s_skip = reinterpret_cast<uint32_t *>(s_raw + kTile * 12);
     __shared__ uint32_t s_nq, s_nfar, s_nfar_none, s_next;
     __shared__ float sT[16];
     constexpr int kQ_ = kTile / THREADS;  // queries per thread
@@ -450,11 +542,15 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 1)
         } else {
             // the 29 sums are taken in two halves of 16 accumulators (32 registers each instead of
             // 64): the second half re-reads the neighbour (an L1 hit) and recomputes the six-vector
-            const double lo = gn_half<KIND, 0, THREADS>(map, s_q, s_pos, n_here);
-            const double hi = gn_half<KIND, 1, THREADS>(map, s_q, s_pos, n_here);
-            if (lane < 16) {
-                sred[warp][lane] = lo;
-                sred[warp][16 + lane] = hi;
+            if constexpr (THREADS == kThreads) {
+                gn_gram<KIND, THREADS>(map, s_q, s_pos, n_here, reinterpret_cast<double *>(s_raw) + warp * 256, sred[warp]);
+            } else {
+                const double lo = gn_half<KIND, 0, THREADS>(map, s_q, s_pos, n_here);
+                const double hi = gn_half<KIND, 1, THREADS>(map, s_q, s_pos, n_here);
+                if (lane < 16) {
+                    sred[warp][lane] = lo;
+                    sred[warp][16 + lane] = hi;
+                }
             }
         }
         __syncthreads();
