@@ -26,8 +26,18 @@ for _ in range(reps):
     batch.run()
 t = np.array(ctx.search_times()).reshape(reps, -1) * 1e3
 ctx.time_searches(False)
+import time
+for _ in range(2):
+    batch.run()
+ctx.synchronize()
+t0 = time.perf_counter()
+for _ in range(10):
+    batch.run()
+ctx.synchronize()
+step_us = (time.perf_counter() - t0) / 10 * 1e6
 res = batch.results()
 err = [bench.pose_delta(r.transformation, T)[0] for r, T in zip(res, gts)]
 print("per-launch us (median over reps):", " ".join(f"{x:.0f}" for x in np.median(t, axis=0)))
+print(f"step {step_us:.0f} us (graph replay, wall clock over 10 steps); rest of step {step_us - np.median(t.sum(axis=1)):.0f} us")
 print(f"search total {np.median(t.sum(axis=1)):.0f} us/step; median pose error {np.median(err):.4f} m; "
       f"checksum {sum(float(np.abs(np.asarray(r.transformation, np.float64)).sum()) for r in res):.9f} k_final {sum(r.k_final for r in res)}")

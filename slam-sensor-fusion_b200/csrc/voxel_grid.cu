@@ -325,8 +325,13 @@ __global__ void __launch_bounds__(256)
                        float4 *__restrict__ src)
 {
     constexpr int kPerThread = kSlotAlign / 256;
-    __shared__ uint32_t s_key[kSlotAlign];
-    __shared__ float s_x[kSlotAlign], s_y[kSlotAlign], s_z[kSlotAlign];
+    // element l lives at l + (l >> 5): a thread owns kPerThread CONSECUTIVE elements, so without the
+    // padding the lanes of a warp would sit kPerThread words apart -- an 8-way bank conflict on every
+    // access of the head scan and the run sums
+    constexpr int kPadded = kSlotAlign + kSlotAlign / 32;
+    __shared__ uint32_t s_key[kPadded];
+    __shared__ float s_x[kPadded], s_y[kPadded], s_z[kPadded];
+    auto pad = [](uint32_t l) { return l + (l >> 5); };
     __shared__ uint32_t s_warp[8];
     const uint32_t base = blockIdx.x * kSlotAlign;
     const uint32_t s = tile_scan[base / kTile];
@@ -344,8 +349,8 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int i = 0; i < kPerThread; ++i) {
             const uint32_t l = i * 256 + threadIdx.x;
-            s_key[l] = kk[i];
-            s_x[l] = pp[i].x; s_y[l] = pp[i].y; s_z[l] = pp[i].z;
+            s_key[pad(l)] = kk[i];
+            s_x[pad(l)] = pp[i].x; s_y[pad(l)] = pp[i].y; s_z[pad(l)] = pp[i].z;
         }
     }
     __syncthreads();
@@ -354,8 +359,8 @@ __global__ void __launch_bounds__(256)
     uint32_t heads = 0, cnt = 0;
 #pragma unroll
     for (int i = 0; i < kPerThread; ++i) {
-        const uint32_t l = l0 + i, k = s_key[l];
-        const bool h = k != kDeadKey && (base + l == seg_begin || (l ? s_key[l - 1] : keys[base - 1]) != k);
+        const uint32_t l = l0 + i, k = s_key[pad(l)];
+        const bool h = k != kDeadKey && (base + l == seg_begin || (l ? s_key[pad(l - 1)] : keys[base - 1]) != k);
         heads |= h ? (1u << i) : 0u;
         cnt += h ? 1u : 0u;
     }
@@ -374,13 +379,13 @@ __global__ void __launch_bounds__(256)
     for (int i = 0; i < kPerThread; ++i) {
         if (!(heads & (1u << i))) continue;
         uint32_t l = l0 + i;
-        const uint32_t k = s_key[l];
+        const uint32_t k = s_key[pad(l)];
         float cx = 0.f, cy = 0.f, cz = 0.f;
         uint32_t n = 0;
-        for (; l < (uint32_t)kSlotAlign && s_key[l] == k; ++l, ++n) {
-            cx = __fadd_rn(cx, s_x[l]);
-            cy = __fadd_rn(cy, s_y[l]);
-            cz = __fadd_rn(cz, s_z[l]);
+        for (; l < (uint32_t)kSlotAlign && s_key[pad(l)] == k; ++l, ++n) {
+            cx = __fadd_rn(cx, s_x[pad(l)]);
+            cy = __fadd_rn(cy, s_y[pad(l)]);
+            cz = __fadd_rn(cz, s_z[pad(l)]);
         }
         if (l == (uint32_t)kSlotAlign) {  // the run goes on in the next tile(s) of the same scan
             for (uint32_t e = base + kSlotAlign; e < seg_end && keys[e] == k; ++e, ++n) {
