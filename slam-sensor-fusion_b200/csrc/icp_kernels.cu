@@ -332,7 +332,7 @@ __device__ __forceinline__ void gn_gram(const MapView &map, const float4 *s_q, c
 #define SSF_MINB 8
 #endif
 template <int KIND, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 1)
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
     search_accum_kernel(MapView map, const float4 *__restrict__ src, const uint32_t *__restrict__ tile_scan,
                         const ScanState *__restrict__ states, float limit, int32_t *__restrict__ corr,
                         double *__restrict__ partials, uint2 *__restrict__ cert, const float *__restrict__ pose_hist,
