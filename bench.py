@@ -376,8 +376,6 @@ def run_gpu(args, rank, world, local_rank):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = capi.lib().ssf_kernel_launches()
-    ctx.time_searches(True)
     # inputs of one step: raw scans + map (+ normals).  Smaller than the 126 MB L2 -> flush L2 between
     # timed steps (write a 256 MB buffer); larger -> the step itself streams them
     input_bytes = total * 16 + xyz.shape[0] * 16 * (2 if w["mode"] == "gn_p2plane" else 1)
@@ -385,20 +383,40 @@ def run_gpu(args, rank, world, local_rank):
         input_bytes = total * 16 + sh["points"].shape[0] * 16 * (2 if w["mode"] == "gn_p2plane" else 1)
     flush = input_bytes < 126e6
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}") if flush else None
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for e0, e1 in evs:
-        if flush:
-            with torch.cuda.stream(stream):
-                flush_buf.zero_()
-        e0.record(stream)
-        batch.run()
-        e1.record(stream)
-    ctx.synchronize()
-    evs[-1][1].synchronize()
-    dev_ms = float(sum(e0.elapsed_time(e1) for e0, e1 in evs))
+
+    def timed_steps():
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for e0, e1 in evs:
+            if flush:
+                with torch.cuda.stream(stream):
+                    flush_buf.zero_()
+            e0.record(stream)
+            batch.run()
+            e1.record(stream)
+        ctx.synchronize()
+        evs[-1][1].synchronize()
+        return float(sum(e0.elapsed_time(e1) for e0, e1 in evs))
+
+    # timed region 1 -> `value`: K steps of the product path (ssf_batch_run as a user calls it: the
+    # GN loop replays its CUDA graph where the launch sequence can be captured)
+    launches0 = capi.lib().ssf_kernel_launches()
+    dev_ms = timed_steps()
+    launches = int(capi.lib().ssf_kernel_launches() - launches0)
+    barrier()
+    # timed region 2 -> `roofline`: the same K steps with every K3 launch bracketed by a pair of CUDA
+    # events on the library's stream (plain launches -- a host-side event cannot sit inside the graph).
+    # One untimed step first, so that the event pool exists before the region starts (creating 2 x K x
+    # iterations events inside it cost the map-sharded workload a quarter of its step).
+    ctx.time_searches(True)
+    batch.run()
+    ctx.search_time()
+    barrier()
+    dev_ms_timed = timed_steps()
     search_ms, search_launches = ctx.search_time()
     ctx.time_searches(False)
-    launches = int(capi.lib().ssf_kernel_launches() - launches0)
+    if os.environ.get("SSF_BENCH_DEBUG"):
+        log(f"[bench r{rank}] debug: {dev_ms / args.steps:.3f} ms/step; with search events {dev_ms_timed / args.steps:.3f} ms/step, "
+            f"search {search_ms / max(1, search_launches) * 1e3:.1f} us/launch ({search_launches} launches)")
     batch.results_into(res)
     queries_per_step = int(sum(int(r.n_source) * int(r.n_searches) for r in res))
     barrier()
@@ -470,7 +488,8 @@ def run_gpu(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "kernel": "search_accum_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
                 "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_search_ms,
-                "share_of_step": search_ms / dev_ms, "queries_per_launch": q_per_launch,
+                "share_of_step": search_ms / dev_ms_timed, "ms_per_step_with_events": dev_ms_timed / args.steps,
+                "queries_per_launch": q_per_launch,
                 "bytes_per_query": alg_bytes / max(1.0, q_per_launch)}
     args.l2_note = (f"per-step inputs {input_bytes / 1e6:.0f} MB " +
                     ("< 126 MB L2: L2 flushed (256 MB write) between timed steps" if flush

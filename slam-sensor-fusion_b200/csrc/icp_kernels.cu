@@ -10,6 +10,7 @@
 //   search_accum_kernel<KIND, THREADS>   persistent blocks over the tiles that hold points: TMA tile load,
 //                                         transform, certificate check or exact walk (near part, then the
 //                                         far rings packed densely), residual / Jacobian partial sums
+//                                         (Gauss-Newton: an 8x8 Gram matrix on the FP64 tensor core, gn_gram)
 //   rowsum_solve_kernel                   ordered sum of a scan's partial rows + 6x6 Cholesky or 3x3 SVD +
 //                                         pose update + stop rules (map-sharded: rowsum_xchg / solve_xchg
 //                                         exchange the rows across ranks over peer memory, or rowsum_kernel
@@ -327,7 +328,8 @@ __device__ __forceinline__ void gn_gram(const MapView &map, const float4 *s_q, c
 //      (nn_verify) -- a handful of flops and one gather instead of a search;
 //   S  the queries that could not be confirmed, packed densely over the threads: full exact walk,
 //      new certificate;
-//   K4 residual / Jacobian terms of the matched queries, 32-value warp reduction paid once per kQ.
+//   K4 residual / Jacobian terms of the matched queries: gn_gram (128-thread blocks, tensor core),
+//      gn_half x 2 (512-thread blocks) or the Kabsch moments with a 32-value warp transpose.
 #ifndef SSF_MINB
 #define SSF_MINB 8
 #endif
