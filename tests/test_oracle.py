@@ -214,3 +214,102 @@ def test_golden_fixture_c1_mini():
     assert np.array_equal(corr, g["ref_corr"])
     vox, _ = oracle.voxel_grid(g["scan"], 0.2)
     assert np.array_equal(vox.view(np.uint32), g["vox_02"].view(np.uint32))
+
+
+# ---- independent restatements of the oracle-defined solver modes (numpy / scipy, float64) -------------
+def _f32_transform(T, xyz):
+    """applyTransformation in the reference's float32 expression order ((T0*x + T1*y) + T2*z) + T3."""
+    T = np.asarray(T, np.float32)
+    x, y, z = (np.ascontiguousarray(xyz[:, k], np.float32) for k in range(3))
+    return np.stack([((T[r, 0] * x + T[r, 1] * y) + T[r, 2] * z) + T[r, 3] for r in range(3)], axis=1).astype(np.float32)
+
+
+def _nn_f32(tree, map_xyz, P):
+    """cKDTree neighbour + flann::L2_Simple distance in float32, ((dx*dx + dy*dy) + dz*dz)."""
+    _, idx = tree.query(P.astype(np.float64))
+    d = P - map_xyz[idx]
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    return idx, d2.astype(np.float32)
+
+
+@pytest.mark.parametrize("mode", ["p2p", "p2plane"])
+def test_gn_steps_vs_numpy_restatement(small_world, mode):
+    """The Gauss-Newton modes have no counterpart in the reference: the oracle defines
+    them, so the oracle itself is pinned against an independent float64 numpy / scipy restatement --
+    J^T J and J^T r by matrix products, numpy.linalg.solve, scipy.linalg.expm of the twist -- over three
+    chained iterations.  Poses agree to float32 rounding; correspondences are identical."""
+    from scipy.linalg import expm
+    from scipy.spatial import cKDTree
+    w = small_world
+    m = np.ascontiguousarray(w["map"][:, :3], np.float32)
+    nrm = np.ascontiguousarray(w["normals"][:, :3], np.float64)
+    ck = cKDTree(m.astype(np.float64))
+    T = np.asarray(w["T0"], np.float32).copy()
+    tree = oracle.KdTree(w["map"])
+    for it in range(1, 4):
+        P = _f32_transform(T, w["scan"])
+        idx, d2 = _nn_f32(ck, m, P)
+        ok = d2 < np.float32(0.5)
+        p = P[ok].astype(np.float64)
+        q = m[idx[ok]].astype(np.float64)
+        e = p - q
+        if mode == "p2plane":
+            n = nrm[idx[ok]]
+            A = np.concatenate([np.cross(p, n), n], axis=1)      # K x 6
+            r = np.einsum("ij,ij->i", n, e)
+            H, g = A.T @ A, A.T @ r
+        else:
+            H, g = np.zeros((6, 6)), np.zeros(6)
+            for k in range(3):                                      # the three rows of [-[p]x | I]
+                ek = np.zeros(3); ek[k] = 1.0
+                Jk = np.concatenate([np.cross(p, np.broadcast_to(ek, p.shape)), np.broadcast_to(ek, p.shape)], axis=1)  # row k of -[p]x is p x e_k
+                H += Jk.T @ Jk
+                g += Jk.T @ e[:, k]
+        x = np.linalg.solve(H, -g)
+        tw = np.zeros((4, 4))
+        tw[:3, :3] = np.array([[0, -x[2], x[1]], [x[2], 0, -x[0]], [-x[1], x[0], 0]])
+        tw[:3, 3] = x[3:]
+        step = expm(tw)
+        step[:3, 3] = x[3:]   # the oracle's update is [exp([w]x) | t], not the full SE(3) exponential
+        T = (step @ T.astype(np.float64)).astype(np.float32)
+        res, corr = oracle.icp_gn(tree, w["scan"], w["T0"], mode=mode, normals=w["normals"], num_iterations=it)
+        assert res.iterations == it and res.k_final == int(ok.sum())
+        if it == 1:
+            assert np.array_equal(corr, np.where(ok, idx, -1))
+        assert np.allclose(res.T, T, rtol=0, atol=2e-6 * it), (it, np.abs(res.T - T).max())
+    assert pose_delta(T, w["T_gt"])[0] < pose_delta(w["T0"], w["T_gt"])[0]
+
+
+def test_o3d_flow_vs_numpy_restatement(small_world):
+    """Open3D's registration_icp control flow restated with numpy: true-distance
+    threshold, every source point every iteration, Kabsch/Umeyama step from numpy.linalg.svd in float64,
+    T <- step * T; three chained iterations against the oracle."""
+    from scipy.spatial import cKDTree
+    w = small_world
+    m = np.ascontiguousarray(w["map"][:, :3], np.float32)
+    ck = cKDTree(m.astype(np.float64))
+    T = np.asarray(w["T0"], np.float32).copy()
+    tree = oracle.KdTree(w["map"])
+    thr = np.float32(0.5) * np.float32(0.5)
+    for it in range(1, 4):
+        P = _f32_transform(T, w["scan"])
+        idx, d2 = _nn_f32(ck, m, P)
+        ok = d2 < thr
+        p, q = P[ok].astype(np.float64), m[idx[ok]].astype(np.float64)
+        pb, qb = p.mean(0), q.mean(0)
+        U, S, Vt = np.linalg.svd((p - pb).T @ (q - qb))
+        D = np.diag([1.0, 1.0, np.sign(np.linalg.det(Vt.T @ U.T))])
+        R = Vt.T @ D @ U.T
+        step = np.eye(4)
+        step[:3, :3], step[:3, 3] = R, qb - R @ pb
+        T = (step @ T.astype(np.float64)).astype(np.float32)
+        res, fit, corr = oracle.icp_o3d(tree, w["scan"], w["T0"], 0.5, max_iteration=it)
+        assert res.iterations == it
+        assert np.allclose(res.T, T, rtol=0, atol=2e-6 * it), (it, np.abs(res.T - T).max())
+    # fitness / rmse of the last pass are those of the pose after the last step
+    P = _f32_transform(T, w["scan"])
+    idx, d2 = _nn_f32(ck, m, P)
+    ok = d2 < thr
+    assert abs(fit - ok.mean()) < 1e-6
+    e = P[ok].astype(np.float64) - m[idx[ok]]
+    assert abs(res.error - np.sqrt((e * e).sum() / ok.sum())) < 1e-6
