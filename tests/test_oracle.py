@@ -313,3 +313,76 @@ def test_o3d_flow_vs_numpy_restatement(small_world):
     assert abs(fit - ok.mean()) < 1e-6
     e = P[ok].astype(np.float64) - m[idx[ok]]
     assert abs(res.error - np.sqrt((e * e).sum() / ok.sum())) < 1e-6
+
+
+def _reference_loop_numpy(m, scan, T0, thr, n_iter, acc, eps):
+    """calculateAlignment restated line by line from icp_point_to_point.cpp:185-254 (and :57-84, :99-170)
+    with numpy float32 -- written against the reference file, not against oracle/ssf_oracle.c.  The 3x3
+    SVD is LAPACK's (float32), the covariance a BLAS product: low-order bits differ from Eigen's."""
+    from scipy.spatial import cKDTree
+    f32 = np.float32
+    ck = cKDTree(m.astype(np.float64))
+    margins = []
+
+    def correspondences(P):                                   # :57-84, d2 against the UNSQUARED threshold (:70)
+        idx, d2 = _nn_f32(ck, m, P)
+        ok = d2 < f32(thr)
+        return P[ok], m[idx[ok]]
+
+    T = np.asarray(T0, f32).copy()
+    P = _f32_transform(T, scan)                               # :191-192
+    P, Q = correspondences(P)                                 # :195
+    searches = 1
+    if P.shape[0] < 10:                                       # :196-200
+        return np.asarray(T0, f32), f32(1e6), 0, False, searches, margins
+    its, last = 0, np.finfo(f32).max                          # :203-205
+    for _ in range(n_iter):
+        d = P - Q
+        norms = np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]).astype(f32)
+        err = f32(np.add.accumulate(norms, dtype=f32)[-1] / f32(P.shape[0]))   # :161-170, sequential float sum
+        margins.append(abs(float(err) - acc))
+        if err < f32(acc):                                    # :215-219
+            last = err
+            break
+        margins.append(abs(abs(float(last) - float(err)) - eps))
+        if abs(f32(last - err)) < f32(eps):                   # :221-224, lazy re-search on the SHRUNK cloud
+            P, Q = correspondences(P)
+            searches += 1
+        K = f32(P.shape[0])
+        cs = np.add.accumulate(P, axis=0, dtype=f32)[-1] / K  # :116-123
+        ct = np.add.accumulate(Q, axis=0, dtype=f32)[-1] / K
+        H = ((P - cs).T @ (Q - ct)).astype(f32)               # :126-134
+        U, _, Vt = np.linalg.svd(H)                           # :137-139
+        V = Vt.T.copy()
+        R = V @ U.T
+        if np.linalg.det(R.astype(np.float64)) < 0:           # :142-149
+            V[:, 2] *= -1
+            R = V @ U.T
+        Ts = np.eye(4, dtype=f32)
+        Ts[:3, :3] = R
+        Ts[:3, 3] = ct - R @ cs                               # :152
+        T = (Ts @ T).astype(f32)                              # :228, left-multiplied
+        P = _f32_transform(Ts, P)                             # :230, points advanced by the STEP
+        last = err                                            # :232
+        its += 1
+    return T, f32(last), its, bool(last < f32(acc)), searches, margins
+
+
+@pytest.mark.parametrize("params", [(0.5, 10, 0.05, 1e-5), (5.0, 12, 0.4, 1e-2), (0.5, 6, 0.0, 1.0)])
+def test_reference_loop_vs_numpy_restatement(small_world, params):
+    """The oracle's restatement of calculateAlignment against a second, independent one written from the
+    reference source with numpy (fine and coarse parameter sets of localization_node.cpp:24-27,226-229,
+    and an eps so large that every pass re-searches).  Control flow -- iterations, searches, the
+    surviving-correspondence count, has_converged -- must be identical; pose and error agree to the
+    float32 noise of LAPACK-vs-Jacobi SVD and BLAS-vs-sequential covariance."""
+    w = small_world
+    thr, n_iter, acc, eps = params
+    m = np.ascontiguousarray(w["map"][:, :3], np.float32)
+    T, err, its, conv, searches, margins = _reference_loop_numpy(m, w["scan"], w["T0"], thr, n_iter, acc, eps)
+    res, corr, _ = oracle.icp_reference(oracle.KdTree(w["map"]), w["scan"], w["T0"], thr, n_iter, acc, eps)
+    if min(margins) < 5e-6:
+        pytest.skip("a stop / re-search decision sits within float noise of its threshold")
+    assert (res.iterations, res.n_searches, bool(res.has_converged)) == (its, searches, conv)
+    assert abs(res.error - err) < 2e-5
+    dt, dr = pose_delta(res.T, T)
+    assert dt < 1e-4 and dr < 1e-5, (dt, dr)
