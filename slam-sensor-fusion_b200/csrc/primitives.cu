@@ -270,7 +270,14 @@ __global__ void __launch_bounds__(kSortThreads)
                        uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int shift,
                        const uint2 *__restrict__ seg, const uint32_t *__restrict__ ghist_scanned)
 {
+    // The tile is first ordered by digit in shared memory (stable: warp slices in input order, ranks
+    // within a warp in round and lane order), then written out in that order: the lanes of a store
+    // cover a few digit runs -- a few sectors -- instead of 32 scattered 4-byte targets (the
+    // low-digit passes, where every lane of a warp drew a different digit, took twice the time of
+    // the high-digit ones).
     __shared__ uint32_t wh[kSortThreads / 32][256];
+    __shared__ uint32_t s_k[kSortTile], s_v[kSortTile];
+    __shared__ uint32_t s_gbase[256], s_dstart[256], s_wsum[kSortThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < (kSortThreads / 32) * 256; i += kSortThreads) (&wh[0][0])[i] = 0;
     __syncthreads();
@@ -295,24 +302,43 @@ __global__ void __launch_bounds__(kSortThreads)
     }
     __syncthreads();
     {
-        // thread d owns digit d: turn per-warp counts into global output offsets
+        // thread d owns digit d: per-warp counts -> offsets of the warps inside the digit's run; the
+        // tile's digit totals -> start of each run in the tile (block exclusive scan)
+        static_assert(kSortThreads == 256, "one thread per digit");
         const uint2 sg = seg[blockIdx.x];
         const int d = threadIdx.x;
-        uint32_t run = ghist_scanned[(size_t)256 * sg.x + (size_t)d * sg.y + (blockIdx.x - sg.x)];
+        s_gbase[d] = ghist_scanned[(size_t)256 * sg.x + (size_t)d * sg.y + (blockIdx.x - sg.x)];
+        uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < kSortThreads / 32; ++w) {
             const uint32_t c = wh[w][d];
             wh[w][d] = run;
             run += c;
         }
+        const uint32_t incl = warp_incl_scan(run);
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+#pragma unroll
+        for (int w = 0; w < kSortThreads / 32; ++w) before += w < warp ? s_wsum[w] : 0u;
+        s_dstart[d] = before + incl - run;
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const uint32_t pos = wh[warp][(k[r] >> shift) & 255u] + rank[r];
+        const uint32_t digit = (k[r] >> shift) & 255u;
+        const uint32_t lp = s_dstart[digit] + wh[warp][digit] + rank[r];
+        SSF_CHECK(lp < (uint32_t)kSortTile);
+        s_k[lp] = k[r];
+        s_v[lp] = v[r];
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < (uint32_t)kSortTile; i += kSortThreads) {
+        const uint32_t key = s_k[i], digit = (key >> shift) & 255u;
+        const uint32_t pos = s_gbase[digit] + (i - s_dstart[digit]);
         SSF_CHECK(pos >= seg[blockIdx.x].x * kSortTile && pos < (seg[blockIdx.x].x + seg[blockIdx.x].y) * kSortTile);
-        keys_out[pos] = k[r];
-        vals_out[pos] = v[r];
+        keys_out[pos] = key;
+        vals_out[pos] = s_v[i];
     }
 }
 
