@@ -2,9 +2,10 @@
 
 TEST INFRASTRUCTURE ONLY -- see the header of ``ssf_oracle.c``.  Imported by ``tests/``,
 ``__graft_entry__.smoke()`` and the CPU-baseline legs of ``bench.py``; never by the product
-package.  PARITY UNPINNED by the reference (it has no behavioural tests and cannot be built
-here); ``tests/test_oracle.py`` pins this restatement against brute force, cv2.flann,
-scipy and numpy instead.
+package.  The reference has no behavioural tests; ``tests/test_ref_pin.py`` pins this restatement
+bit for bit to the reference's own sources compiled unmodified (``oracle/_ref``, see ``ref.py``),
+and ``tests/test_oracle.py`` pins the third-party pieces (FLANN k=1, Jacobi SVD, VoxelGrid)
+against brute force, cv2.flann, scipy and numpy.
 """
 from __future__ import annotations
 

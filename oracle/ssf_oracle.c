@@ -6,22 +6,31 @@
  * cpu_baseline / --impl reference legs of bench.py use it, and only as the checker or the
  * reported CPU baseline.
  *
- * PARITY UNPINNED BY THE REFERENCE: the reference (viniciusvidal2/slam-sensor-fusion) has
- * no behavioural tests, golden vectors or fixtures (only three ament lint stubs under
- * localization_python/test/), and its own code cannot be compiled here because PCL, FLANN,
- * Eigen and ROS 2 are not installed.  This file is therefore a restatement, function by
- * function, of reference localization/src/icp_point_to_point.cpp (cited per function
- * below), with the published algorithms of the absent third-party pieces restated from
- * their public sources (versions unpinned in the reference's CMakeLists.txt:14-26):
+ * PINNING.  The reference (viniciusvidal2/slam-sensor-fusion) ships no behavioural tests, golden
+ * vectors or fixtures (only three ament lint stubs under localization_python/test/), and its
+ * build needs PCL, FLANN, Eigen and ROS 2, none of which is installed here.  So:
+ *   (1) oracle/_ref/libssf_ref.so is the reference's OWN icp_point_to_point.cpp,
+ *       brute_force_alignment.cpp and point_cloud_processing.hpp compiled UNMODIFIED against
+ *       stand-in Eigen/PCL headers (oracle/ref_stubs/, recipe in oracle/Makefile), and
+ *       tests/test_ref_pin.py requires this file to agree with it BIT FOR BIT (pose, error,
+ *       iterations, convergence flag, abort sentinel, debug text; fine / coarse / re-search-
+ *       every-pass / abort cases, config 1 at full size; the pose-grid scorer; the three
+ *       pre-processing functions).  Everything the reference spells out in its own text is
+ *       therefore pinned to that text.
+ *   (2) What stays restated from published algorithms, in the stand-ins as well as here  [ext]
+ *       (versions unpinned in the reference's CMakeLists.txt:14-26):
  *   - pcl::KdTreeFLANN<PointXYZ>::nearestKSearch(k=1): exact 1-NN, squared L2 distance
- *     accumulated left to right in float without FMA (flann::L2_Simple).  FLANN's tie
- *     order is traversal order; the contract here is "lowest target index wins".
- *   - Eigen::JacobiSVD<Matrix3f>: two-sided Jacobi with the real 2x2 kernel.
+ *     accumulated left to right in float without FMA (flann::L2_Simple; pinned bit-equal
+ *     against cv2.flann, the same FLANN lineage).  FLANN's tie order is traversal order; the
+ *     contract here is "lowest target index wins".
+ *   - Eigen::JacobiSVD<Matrix3f>: two-sided Jacobi with the real 2x2 kernel; the summation
+ *     order of Eigen's blocked GEMM for the 3x3 cross-covariance (host-cache dependent).
  *   - pcl::VoxelGrid<PointXYZ>::applyFilter: see ssf_oracle_voxel_grid.
- * What pins it instead (tests/test_oracle.py): O(N*M) brute force, cv2.flann
- * KDTREE_SINGLE (same FLANN lineage) and scipy cKDTree for the NN; numpy.linalg.svd for
- * the Kabsch step; a numpy group-by for the voxel grid; analytic ground-truth poses of the
- * synthetic world for the whole loop.
+ *       These are pinned by tests/test_oracle.py: O(N*M) brute force, cv2.flann KDTREE_SINGLE
+ *       and scipy cKDTree for the NN; numpy.linalg.svd for the Kabsch step; a numpy group-by
+ *       for the voxel grid; analytic ground-truth poses of the synthetic world for the loop.
+ *   (3) The GN / Open3D-flow modes have no reference counterpart in C++ (Open3D is absent and
+ *       unpinned): this file defines them; numpy/scipy restatements pin them (test_oracle.py).
  *
  * Build (oracle/Makefile): gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC
  * -ffp-contract=off mirrors the reference build, which passes no -march/-ffast-math flag
