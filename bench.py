@@ -2,20 +2,22 @@
 """bench.py -- scan-to-map registration throughput on B200 (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement (oracle)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU
 
 Workload (BASELINE.json configs[1], "c2"): 64-beam x 2048-azimuth synthetic LiDAR scans
 (~130k points) -> voxel-grid downsample, 0.2 m leaf -> point-to-plane Gauss-Newton ICP, 10
 iterations, threshold 0.5, against a 5M-point synthetic map with analytic normals.
-A step registers one batch of `--scans-per-step` scans (distinct poses); N ranks each take
+A step registers one batch of `--scans-per-step` DISTINCT scans (distinct poses); N ranks each take
 their own batch against their own replica of the map (no collective on the data path: the
 work shards by scan, "weak" scaling).
 
 Printed keys: value = scans/s with the raw scans already resident in HBM (CUDA events on the
-library's stream); e2e = the same through the host-buffer API (pinned host scans -> H2D ->
-align -> D2H results inside the timed region); roofline = the NN-search kernel's algorithmic
-bytes / its CUDA-event time against the measured HBM copy bandwidth; cpu_baseline = the CPU
-oracle on a bounded sample of the same workload on this box's host cores.
+library's stream); e2e = the same through the host-buffer API (pinned host scans, packed 12-byte xyz
+-> H2D -> align -> D2H results inside the timed region); roofline = the dominant kernel's algorithmic
+bytes / its CUDA-event time against the measured HBM copy bandwidth; cpu_baseline = the CPU oracle on
+a bounded sample of the same workload on this box's host cores; latency = single-scan device times;
+map_sharded (N > 1) = the 50M-point map split across the N ranks with the per-iteration exchange
+(BASELINE.json configs[2]), measured in the same run so the collective path is on record at every N.
 """
 from __future__ import annotations
 
@@ -35,16 +37,16 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "slam-sensor-fusion_b200"))
 
 WORKLOADS = {
-    # name: (map points, beams, azimuths, leaf, mode, max_range)
     "c2": dict(map_points=5_000_000, beams=64, azimuths=2048, leaf=0.2, mode="gn_p2plane", max_range=100.0,
                scans_per_step=256,
                desc="64-beam scan (~130k pts) voxel 0.2 m + point-to-plane GN ICP (10 it, thr 0.5) vs 5M-point map"),
     "c1": dict(map_points=1_000_000, beams=32, azimuths=1024, leaf=0.0, mode="reference", max_range=100.0,
+               scans_per_step=64,
                desc="32-beam scan (~30k pts) reference point-to-point ICP (10 it, thr 0.5) vs 1M-point map"),
     "c3": dict(map_points=50_000_000, beams=32, azimuths=1024, leaf=0.0, mode="gn_p2plane", max_range=100.0,
-               sharded=True, scans_per_step=16,
+               sharded=True, scans_per_step=64,
                desc="32-beam scans (~30k pts) point-to-plane GN ICP (10 it, thr 0.5) vs 50M-point map, "
-                    "map sharded by cell columns across ranks, one 32-double all-reduce per scan per iteration"),
+                    "map sharded by cell columns across ranks, one 32-double sum per scan per iteration"),
     # config 4: the offline sequence (10 000 scans of config 1's shape against the 5M-point map); scans are
     # independent, so ranks take disjoint scans and the sequence time is 10 000 / (scans/s over all ranks)
     "c4": dict(map_points=5_000_000, beams=32, azimuths=1024, leaf=0.0, mode="reference", max_range=100.0,
@@ -58,9 +60,10 @@ WORKLOADS = {
                desc="128-beam dense scans (~260k rays) voxel 0.05 m + point-to-point GN ICP (30 it, thr 0.5) vs "
                     "62.5M map points per rank, map sharded by columns across ranks"),
     "mini": dict(map_points=200_000, beams=16, azimuths=512, leaf=0.2, mode="gn_p2plane", max_range=60.0,
-                 desc="smoke-size variant of c2"),
+                 scans_per_step=16, desc="smoke-size variant of c2"),
 }
 THR, ITERS = 0.5, 10
+L2_BYTES = 126e6
 
 
 def log(*a):
@@ -70,41 +73,39 @@ def log(*a):
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return float(json.load(open(p))["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_workload(name: str, n_scans: int, rank: int, distinct: int = 16, world: int = 1):
-    """Map + a batch of raw scans with perturbed initial poses (all seeded)."""
+def make_workload(name: str, n_scans: int, rank: int, world: int = 1, with_map: bool = True):
+    """Map + a batch of n_scans DISTINCT raw scans (distinct poses) with perturbed initial poses, all seeded."""
     from ssf_gpu import synth
     w = WORKLOADS[name]
-    if w.get("sharded"):
-        rank = 0  # map-sharded workloads: every rank registers the SAME scans against its map shard
+    seed_rank = 0 if w.get("sharded") else rank  # map-sharded: every rank registers the SAME scans against its shard
     t0 = time.time()
     m_points = w["map_points"] * (world if w.get("per_rank") else 1)
-    xyz, nrm, half = synth.make_map(m_points, normals=w.get("normals", True))
-    log(f"[bench r{rank}] map {xyz.shape[0]} pts, half extent {half} m, {time.time() - t0:.1f}s")
+    if with_map:
+        xyz, nrm, half = synth.make_map(m_points, normals=w.get("normals", True))
+    else:
+        xyz, nrm, half = None, None, synth.map_half_extent(m_points)[0]
+    log(f"[bench r{rank}] {name}: map {m_points} pts, half extent {half} m, {time.time() - t0:.1f}s")
     t0 = time.time()
-    distinct = min(distinct, n_scans)
-    base, scans, inits, gts = [], [], [], []
-    for d in range(distinct):
-        k = 1000 * rank + 40 * d + (int(half / 0.15) - 320 if w.get("sharded") else 0)  # sharded: map centre
-        T = synth.street_pose(k, half=half)
-        base.append((T, synth.make_scan(T, w["beams"], w["azimuths"], scan_id=k, max_range=w["max_range"])))
+    scans, inits, gts = [], [], []
+    per = int(4 * max(2.0, half - 15.0) / 0.15)  # poses of one lap of the route
     for s in range(n_scans):
-        T, sc = base[s % distinct]
-        scans.append(sc)
+        # poses spread over the whole route, a different stretch per rank
+        k = (seed_rank * 7919 + s * max(1, per // max(1, n_scans)) + (per // 2 if w.get("sharded") else 0)) % per
+        T = synth.street_pose(k, half=half)
+        scans.append(synth.make_scan(T, w["beams"], w["azimuths"], scan_id=100000 * seed_rank + s, max_range=w["max_range"]))
         gts.append(T)
-        inits.append(synth.perturb_pose(T, 100000 * rank + s))
-    log(f"[bench r{rank}] {distinct} distinct scans of ~{scans[0].shape[0]} pts, {time.time() - t0:.1f}s")
+        inits.append(synth.perturb_pose(T, 100000 * seed_rank + s))
+    log(f"[bench r{rank}] {name}: {n_scans} distinct scans of ~{scans[0].shape[0]} pts, {time.time() - t0:.1f}s")
     return w, xyz, nrm, half, scans, inits, gts
 
 
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
-    In-process NVML from a thread, every 2 ms -- the timed region of a default run lasts tens of
-    milliseconds, too short for an `nvidia-smi -lms` child to report even once; nvidia-smi is the
-    fallback when NVML cannot be loaded."""
+    In-process NVML from a thread, every 2 ms; nvidia-smi is the fallback when NVML cannot be loaded."""
 
     def __init__(self, gpu_index: int):
         self.idx, self.rows, self.proc, self.thread, self.stop_flag = gpu_index, [], None, None, False
@@ -201,11 +202,9 @@ def pose_delta(Ta, Tb):
 
 
 def nn_footprint_bytes(map_xyz, queries_world, cell):
-    """SURVEY 8(d) algorithmic bytes of one search launch: every distinct map point (16 B) and
-    cell entry (8 B) in the 3x3x3 neighbourhood of a query-occupied cell, counted once, plus
-    20 B per query (16 B read, 4 B correspondence written)."""
+    """distinct map points (16 B) and cell entries (8 B) in the 3x3x3 neighbourhood (cell edge
+    1.01 sqrt(thr)) of the query-occupied cells, each counted once.  Returns (points, cells)."""
     o = map_xyz[:, :3].min(0)
-    # only map points near the queries can lie in a query cell's neighbourhood: drop the rest first
     qlo, qhi = queries_world.min(0) - 2 * cell, queries_world.max(0) + 2 * cell
     near = ((map_xyz[:, :3] >= qlo) & (map_xyz[:, :3] <= qhi)).all(1)
     map_xyz = map_xyz[near]
@@ -226,35 +225,67 @@ def nn_footprint_bytes(map_xyz, queries_world, cell):
     pos = np.searchsorted(ukeys, nk)
     pos[pos >= len(ukeys)] = len(ukeys) - 1
     hit = ukeys[pos] == nk
-    n_pts, n_cells = int(counts[pos[hit]].sum()), int(hit.sum())
-    return 20 * queries_world.shape[0] + 16 * n_pts + 8 * n_cells, n_pts, n_cells
+    return int(counts[pos[hit]].sum()), int(hit.sum())
+
+
+def config_of(args, w):
+    """Identical in both arms (ours / reference): the workload, nothing about how an arm sampled it."""
+    return {"workload": f"{args.workload}: {w['desc']}", "scans_per_step": args.scans_per_step,
+            "map_points": w["map_points"], "scan_rays": w["beams"] * w["azimuths"], "voxel_leaf": w["leaf"],
+            "mode": w["mode"], "max_correspondence_dist": THR, "iterations": w.get("iters", ITERS),
+            "parallelism": (f"map-sharded x{args.gpus} (scans replicated, per-iteration sum of 32 doubles per scan)"
+                            if w.get("sharded") else f"scan-sharded x{args.gpus} (map replicated)")}
+
+
+def host_threads():
+    from oracle import oracle
+    return max(oracle.max_threads(), len(os.sched_getaffinity(0)))
+
+
+def oracle_scan(oracle, w, tree, nrm, sc, T0, threads):
+    src = oracle.voxel_grid(sc, w["leaf"])[0] if w["leaf"] > 0 else sc
+    if w["mode"] in ("gn_p2plane", "gn_p2p"):
+        r, _ = oracle.icp_gn(tree, src, T0, mode="p2plane" if w["mode"] == "gn_p2plane" else "p2p", normals=nrm,
+                             max_correspondence_dist=THR, num_iterations=w.get("iters", ITERS), threads=threads)
+    else:
+        r, _, _ = oracle.icp_reference(tree, src, T0, THR, ITERS, 0.05, 1e-5, threads=threads)
+    return src.shape[0] * r.n_searches
 
 
 # ------------------------------------------------------------------------------------------------
 def run_cpu(args, rank, world):
-    """--impl reference: the CPU restatement (oracle port) on a bounded sample, all host threads."""
+    """--impl reference: the reference's algorithm on the host CPU, bounded sample, all host threads.
+    Reference-loop workloads (c1, c4) run oracle/_ref -- the reference's own icp_point_to_point.cpp compiled
+    unmodified (single-threaded, like the node) -- when it was shipped; the Gauss-Newton workloads have no
+    counterpart in the reference and run the oracle port with OpenMP over the queries."""
     if rank != 0:
         return
-    from oracle import oracle
+    from oracle import oracle, ref
+    w = WORKLOADS[args.workload]
     sample = max(1, min(args.cpu_scans, args.scans_per_step))
-    w, xyz, nrm, half, scans, inits, gts = make_workload(args.workload, sample, 0, distinct=sample)
-    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: the oracle takes
-    # its thread count per call, so the environment default does not cap it)
-    threads = max(oracle.max_threads(), len(os.sched_getaffinity(0)))
+    w, xyz, nrm, half, scans, inits, gts = make_workload(args.workload, sample, 0)
+    threads = host_threads()
+    use_ref = w["mode"] == "reference" and ref.available()
     t0 = time.time()
-    tree = oracle.KdTree(xyz)
+    if use_ref:
+        icp = ref.ICPPointToPoint(THR, ITERS, 0.05, 1e-5)
+        icp.setDebugMode(False)
+        icp.setTargetPointCloud(xyz)
+        tree = None
+    else:
+        tree = oracle.KdTree(xyz)
     build_s = time.time() - t0
 
     def step():
         q = 0
         for sc, T0 in zip(scans, inits):
-            src = oracle.voxel_grid(sc, w["leaf"])[0] if w["leaf"] > 0 else sc
-            if w["mode"] in ("gn_p2plane", "gn_p2p"):
-                r, _ = oracle.icp_gn(tree, src, T0, mode="p2plane" if w["mode"] == "gn_p2plane" else "p2p", normals=nrm,
-                                     max_correspondence_dist=THR, num_iterations=w.get("iters", ITERS), threads=threads)
+            if use_ref:
+                icp.setSourcePointCloud(sc)
+                icp.setInitialTransformation(T0)
+                icp.calculateAlignment()
+                q += sc.shape[0] * 5
             else:
-                r, _, _ = oracle.icp_reference(tree, src, T0, THR, ITERS, 0.05, 1e-5, threads=threads)
-            q += src.shape[0] * r.n_searches
+                q += oracle_scan(oracle, w, tree, nrm, sc, T0, threads)
         return q
 
     for _ in range(min(args.warmup, 1)):
@@ -271,21 +302,80 @@ def run_cpu(args, rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_of(args, w),
             "nn_queries_per_sec": queries / dt,
-            "cpu_baseline": {"value": val, "unit": "scans/s", "cores": threads, "kind": "port",
-                             "sample": f"{sample} scans/step x {steps} steps, KD-tree build {build_s:.1f}s excluded"},
+            "cpu_baseline": {"value": val, "unit": "scans/s", "cores": 1 if use_ref else threads,
+                             "kind": "reference" if use_ref else "port",
+                             "sample": f"{sample} scans/step x {steps} steps of the same workload, index build "
+                                       f"({build_s:.1f}s) excluded"},
             "e2e": {"value": val, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def config_of(args, w):
-    return {"workload": f"{args.workload}: {w['desc']}", "scans_per_step": args.scans_per_step,
-            "map_points": w["map_points"], "scan_rays": w["beams"] * w["azimuths"], "voxel_leaf": w["leaf"],
-            "mode": w["mode"], "max_correspondence_dist": THR, "iterations": w.get("iters", ITERS),
-            "parallelism": (f"map-sharded x{args.gpus} (scans replicated, per-iteration sum of 32 doubles per scan: " +
-                            ("in-kernel exchange over peer memory" if args.exchange == "peer" else "NCCL all-reduce hook") + ")"
-                            if w.get("sharded")
-                            else f"scan-sharded x{args.gpus} (map replicated)"),
-            "l2": args.l2_note}
+def cpu_baseline(args, w, xyz, nrm, scans, inits):
+    """The oracle port on this box's host cores, bounded sample (rank 0, N = 1 only), plus the same-lineage
+    FLANN index (cv2.flann KDTREE_SINGLE) timed on one search pass of the sample's queries."""
+    from oracle import oracle
+    threads = host_threads()
+    t0 = time.time()
+    tree = oracle.KdTree(xyz)
+    build_s = time.time() - t0
+    n = max(1, min(args.cpu_scans, len(scans)))
+
+    def run(th):
+        t0 = time.time()
+        for sc, T0 in zip(scans[:n], inits[:n]):
+            oracle_scan(oracle, w, tree, nrm, sc, T0, th)
+        return n / (time.time() - t0)
+
+    v_all = run(threads)
+    v_one = run(1) if n <= 8 else None
+    out = {"value": v_all, "unit": "scans/s", "cores": threads, "kind": "port",
+           "sample": f"{n} scans of the same workload, KD-tree build ({build_s:.1f}s) excluded",
+           "value_single_thread": v_one}
+    try:  # BASELINE.md B3: FLANN KDTREE_SINGLE (the index family PCL wraps), one core, one search pass
+        import cv2
+        sub = np.ascontiguousarray(xyz[:, :3])
+        t0 = time.time()
+        idx = cv2.flann_Index(sub, dict(algorithm=4, leaf_max_size=15))
+        fb = time.time() - t0
+        sc = scans[0]
+        src = oracle.voxel_grid(sc, w["leaf"])[0] if w["leaf"] > 0 else sc
+        T0 = np.asarray(inits[0], np.float32)
+        q = np.ascontiguousarray((src[:, :3] @ T0[:3, :3].T + T0[:3, 3]).astype(np.float32))
+        t0 = time.time()
+        idx.knnSearch(q, 1, params=dict(checks=-1, eps=0.0, sorted=True))
+        fq = time.time() - t0
+        out["flann_kdtree_single"] = {"queries_per_sec": q.shape[0] / fq, "build_s": fb, "cores": 1,
+                                      "queries": int(q.shape[0])}
+    except Exception as e:  # cv2 absent on the box: say so instead of failing the bench
+        out["flann_kdtree_single"] = {"unavailable": repr(e)[:120]}
+    return out
+
+
+def bind_to_gpu_numa(local_rank):
+    """CPU affinity (and with it first-touch placement of the pinned staging buffers) on the NUMA node the
+    rank's GPU hangs off.  Returns a description for the JSON line."""
+    info = {"numa_node": None, "cpus": len(os.sched_getaffinity(0))}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        info["numa_node"] = node
+        if node >= 0:
+            cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+            ids = set()
+            for part in cpus.split(","):
+                a, _, b = part.partition("-")
+                ids.update(range(int(a), int(b or a) + 1))
+            ids &= os.sched_getaffinity(0)
+            if ids:
+                os.sched_setaffinity(0, ids)
+                info["cpus"] = len(ids)
+    except Exception as e:
+        info["note"] = repr(e)[:100]
+    return info
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -294,12 +384,12 @@ def run_gpu(args, rank, world, local_rank):
     from ssf_gpu import capi
 
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        # NCCL prints its version banner on stdout; keep stdout for the one JSON line
-        saved = os.dup(1)
+        saved = os.dup(1)  # NCCL prints its version banner on stdout; keep stdout for the one JSON line
         os.dup2(2, 1)
         try:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -328,14 +418,17 @@ def run_gpu(args, rank, world, local_rank):
         else:
             icp.setAllreduce(shard.torch_allreduce_hook(local_rank))
         log(f"[bench r{rank}] shard {sh['points'].shape[0]} of {xyz.shape[0]} pts, columns {sh['own']}")
+        map_pts_dev = sh["points"].shape[0]
     else:
         icp.setTargetPointCloud(xyz, nrm)
+        map_pts_dev = xyz.shape[0]
     log(f"[bench r{rank}] map index built in {time.time() - t0:.2f}s")
 
     n_pts = [s.shape[0] for s in scans]
     total = int(sum(n_pts))
-    pinned = torch.empty((total, 4), dtype=torch.float32, pin_memory=True)
-    pinned.numpy()[:] = np.concatenate(scans, axis=0)
+    # host staging: PACKED 12-byte xyz (the ABI takes any stride >= 12; the 4th float of pcl::PointXYZ is padding)
+    pinned = torch.empty((total, 3), dtype=torch.float32, pin_memory=True)
+    pinned.numpy()[:] = np.concatenate([s[:, :3] for s in scans], axis=0)
     T_pinned = torch.empty((B, 16), dtype=torch.float32, pin_memory=True)
     T_pinned.numpy()[:] = np.stack([np.asarray(T, np.float32).T.reshape(16) for T in inits])
     res = (capi.IcpResult * B)()
@@ -349,7 +442,7 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
 
     def e2e_step():
-        batch.upload_ptr(pinned.data_ptr(), n_pts, 16)
+        batch.upload_ptr(pinned.data_ptr(), n_pts, 12)
         batch.set_initial_ptr(T_pinned.data_ptr())
         batch.run()
         batch.results_into(res)
@@ -378,14 +471,12 @@ def run_gpu(args, rank, world, local_rank):
     sampler.start()
     # inputs of one step: raw scans + map (+ normals).  Smaller than the 126 MB L2 -> flush L2 between
     # timed steps (write a 256 MB buffer); larger -> the step itself streams them
-    input_bytes = total * 16 + xyz.shape[0] * 16 * (2 if w["mode"] == "gn_p2plane" else 1)
-    if sharded:
-        input_bytes = total * 16 + sh["points"].shape[0] * 16 * (2 if w["mode"] == "gn_p2plane" else 1)
-    flush = input_bytes < 126e6
+    input_bytes = total * 16 + map_pts_dev * 16 * (2 if w["mode"] == "gn_p2plane" else 1)
+    flush = input_bytes < L2_BYTES
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}") if flush else None
 
-    def timed_steps():
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    def timed_steps(n):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         for e0, e1 in evs:
             if flush:
                 with torch.cuda.stream(stream):
@@ -397,28 +488,27 @@ def run_gpu(args, rank, world, local_rank):
         evs[-1][1].synchronize()
         return float(sum(e0.elapsed_time(e1) for e0, e1 in evs))
 
-    # timed region 1 -> `value`: K steps of the product path (ssf_batch_run as a user calls it: the
-    # GN loop replays its CUDA graph where the launch sequence can be captured)
+    # timed region 1 -> `value`: K steps of the product path (ssf_batch_run as a user calls it)
     launches0 = capi.lib().ssf_kernel_launches()
-    dev_ms = timed_steps()
+    dev_ms = timed_steps(args.steps)
     launches = int(capi.lib().ssf_kernel_launches() - launches0)
     barrier()
-    # timed region 2 -> `roofline`: the same K steps with every K3 launch bracketed by a pair of CUDA
-    # events on the library's stream (plain launches -- a host-side event cannot sit inside the graph).
-    # One untimed step first, so that the event pool exists before the region starts (creating 2 x K x
-    # iterations events inside it cost the map-sharded workload a quarter of its step).
+    # timed region 2 -> `roofline`: steps with every K3 launch bracketed by a pair of CUDA events on the
+    # library's stream (plain launches -- a host-side event cannot sit inside the graph).  One untimed
+    # step first, so that the event pool exists before the region starts.
+    k2 = max(1, min(args.steps, 20))
     ctx.time_searches(True)
     batch.run()
     ctx.search_time()
     barrier()
-    dev_ms_timed = timed_steps()
+    dev_ms_timed = timed_steps(k2)
+    per_launch = ctx.search_times(cap=8192)
     search_ms, search_launches = ctx.search_time()
     ctx.time_searches(False)
-    if os.environ.get("SSF_BENCH_DEBUG"):
-        log(f"[bench r{rank}] debug: {dev_ms / args.steps:.3f} ms/step; with search events {dev_ms_timed / args.steps:.3f} ms/step, "
-            f"search {search_ms / max(1, search_launches) * 1e3:.1f} us/launch ({search_launches} launches)")
     batch.results_into(res)
-    queries_per_step = int(sum(int(r.n_source) * int(r.n_searches) for r in res))
+    answered, walked = batch.search_stats() if w["mode"] != "reference" else (np.zeros(0), np.zeros(0))
+    queries_per_step = int(answered.sum()) if answered.size else int(sum(int(r.n_source) * int(r.n_searches) for r in res))
+    walked_per_step = int(walked.sum()) if walked.size else None
     barrier()
 
     # ---- e2e: host buffers in, host results out ---------------------------------------------------
@@ -432,7 +522,7 @@ def run_gpu(args, rank, world, local_rank):
         pending = None
         for i in range(steps):
             b = pair[i % 2]
-            b.upload_ptr(pinned.data_ptr(), n_pts, 16, wait=False)
+            b.upload_ptr(pinned.data_ptr(), n_pts, 12, wait=False)
             b.set_initial_ptr(T_pinned.data_ptr())
             b.run()
             if pending is not None:
@@ -454,11 +544,41 @@ def run_gpu(args, rank, world, local_rank):
     e2e_s = max(ee0.elapsed_time(ee1) * 1e-3, time.perf_counter() - t0)
     clocks = sampler.stop()
     barrier()
+    # what the host->device link gives this rank while every rank copies at once (pinned -> device, 5 x 256 MB)
+    probe_src = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+    probe_dst = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    probe_dst.copy_(probe_src, non_blocking=True)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(5):
+        probe_dst.copy_(probe_src, non_blocking=True)
+    p1.record()
+    p1.synchronize()
+    h2d_gbs = 5 * (256 << 20) / (p0.elapsed_time(p1) * 1e-3) / 1e9
+    del probe_src, probe_dst
+    barrier()
 
-    t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local_rank}")
+    # ---- latency of the live-node case (config 1: one 32x1024 scan vs the 1M-point map) -----------------
+    latency = {f"{args.workload}_single_scan_ms": single_ms}
+    if rank == 0 and world == 1 and args.workload != "c1" and not args.no_latency:
+        latency.update(c1_latency(ssf_gpu, ctx))
+
+    # ---- the communicating multi-GPU path, on record at every N > 1 -------------------------------------
+    map_sharded = None
+    if world > 1 and not w.get("sharded") and not args.no_map_sharded:
+        del batch2
+        try:
+            map_sharded = run_map_sharded(args, ssf_gpu, capi, torch, dist, ctx, rank, world, local_rank)
+        except Exception as e:  # the headline line must still be printed
+            map_sharded = {"error": repr(e)[:300]}
+
+    t_dev = torch.tensor([dev_ms, e2e_s * 1e3, -h2d_gbs], dtype=torch.float64, device=f"cuda:{local_rank}")
+    t_sum = torch.tensor([h2d_gbs], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = [float(x) for x in t_dev.cpu()]
+        dist.all_reduce(t_sum, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max, neg_min_h2d = [float(x) for x in t_dev.cpu()]
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -467,42 +587,55 @@ def run_gpu(args, rank, world, local_rank):
     job_scans = B if sharded else world * B  # map-sharded ranks cooperate on the same B scans
     value = job_scans * args.steps / (dev_ms_max * 1e-3)
     e2e_val = job_scans * args.steps / (e2e_ms_max * 1e-3)
-    # roofline of the dominant kernel (search_accum): algorithmic bytes of ONE launch over the batch
     peak, peak_kind = peaks()
-    cell = float(np.sqrt(np.float32(THR)) * np.float32(1.01))
-    down = [ssf_gpu.voxel_down_sample(s, w["leaf"], ctx) if w["leaf"] > 0 else s[:, :3] for s in scans[:16]]
-    qw = np.concatenate([d @ np.asarray(T, np.float64)[:3, :3].T + np.asarray(T, np.float64)[:3, 3]
-                         for d, T in zip(down, inits[:16])])
-    fp16, n_pts_fp, n_cells_fp = nn_footprint_bytes(xyz, qw, cell)
-    # 16 of the B scans are distinct; the other scans revisit the same neighbourhoods
-    q_per_launch = queries_per_step / max(1, int(np.median(searches)))
-    alg_bytes = 20.0 * q_per_launch + 16.0 * n_pts_fp + 8.0 * n_cells_fp
-    avg_search_ms = search_ms / max(1, search_launches)
-    achieved = alg_bytes / (avg_search_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
-    if os.path.exists(tp):
-        tj = json.load(open(tp))
-        if tj.get("workload") == args.workload and tj.get("scans_per_step") == B:
-            traffic = tj.get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "search_accum_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_search_ms,
-                "share_of_step": search_ms / dev_ms_timed, "ms_per_step_with_events": dev_ms_timed / args.steps,
-                "queries_per_launch": q_per_launch,
-                "bytes_per_query": alg_bytes / max(1.0, q_per_launch)}
-    args.l2_note = (f"per-step inputs {input_bytes / 1e6:.0f} MB " +
-                    ("< 126 MB L2: L2 flushed (256 MB write) between timed steps" if flush
-                     else "exceed the 126 MB L2: no flush needed"))
+    n_search = max(1, int(np.median(searches)))
+    if w["mode"] == "reference":
+        roofline = reference_roofline(peak, peak_kind, search_ms, search_launches, dev_ms_timed, k2, res, clocks, B)
+    else:
+        # roofline of the dominant kernel (search_accum): algorithmic bytes of ONE launch over the batch
+        cell = float(np.sqrt(np.float32(THR)) * np.float32(1.01))
+        down = [ssf_gpu.voxel_down_sample(s, w["leaf"], ctx) if w["leaf"] > 0 else s[:, :3] for s in scans]
+        qw = np.concatenate([d @ np.asarray(T, np.float64)[:3, :3].T + np.asarray(T, np.float64)[:3, 3]
+                             for d, T in zip(down, inits)])
+        n_pts_fp, n_cells_fp = nn_footprint_bytes(xyz, qw, cell)
+        q_per_launch = queries_per_step / n_search
+        alg_bytes = 20.0 * q_per_launch + 16.0 * n_pts_fp + 8.0 * n_cells_fp
+        avg_search_ms = search_ms / max(1, search_launches)
+        achieved = alg_bytes / (avg_search_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("workload") == args.workload and tj.get("scans_per_step") == B:
+                traffic = tj.get("dram_bytes_per_launch")
+        per_pos = [float(np.mean(per_launch[i::n_search])) for i in range(n_search)] if len(per_launch) >= n_search else []
+        roofline = {"bound": "hbm", "kernel": "search_accum_kernel<GN_P2PLANE,128>" if w["mode"] == "gn_p2plane"
+                    else "search_accum_kernel<GN_P2P,128>",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "peak_kind": peak_kind, "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_search_ms,
+                    "launch_ms_by_iteration": per_pos,
+                    "share_of_step": search_ms / dev_ms_timed, "ms_per_step_with_events": dev_ms_timed / k2,
+                    "queries_per_launch": q_per_launch, "bytes_per_query": alg_bytes / max(1.0, q_per_launch),
+                    "footprint_points": n_pts_fp, "footprint_cells": n_cells_fp}
+    l2_note = (f"per-step inputs {input_bytes / 1e6:.0f} MB " +
+               ("< 126 MB L2: L2 flushed (256 MB write) between timed steps" if flush
+                else "exceed the 126 MB L2: no flush needed"))
+    dev_s = dev_ms_max * 1e-3
+    scale = 1 if sharded else world
     line = {"metric": "icp_scans_per_sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong" if w.get("sharded") else "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": config_of(args, w),
-            "nn_queries_per_sec": (1 if sharded else world) * queries_per_step * args.steps / (dev_ms_max * 1e-3),
+            "data": "synthetic", "config": config_of(args, w), "l2": l2_note,
+            "nn_queries_per_sec": scale * queries_per_step * args.steps / dev_s,
+            "nn_queries_walked_per_sec": (scale * walked_per_step * args.steps / dev_s) if walked_per_step is not None else None,
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": "scans/s", "h2d_bytes_per_step": total * 16 + B * 64,
-                    "d2h_bytes_per_step": B * ctypes.sizeof(capi.IcpResult)},
-            "gpu_launches": launches, "single_scan_ms": single_ms, "roofline": roofline}
+            "e2e": {"value": e2e_val, "unit": "scans/s", "h2d_bytes_per_step": total * 12 + B * 64,
+                    "d2h_bytes_per_step": B * ctypes.sizeof(capi.IcpResult), "point_stride_bytes": 12,
+                    "h2d_probe_gbs_min_rank": -neg_min_h2d, "h2d_probe_gbs_sum": float(t_sum.cpu()[0]),
+                    "rank0_numa": numa},
+            "gpu_launches": launches, "single_scan_ms": single_ms, "latency": latency, "roofline": roofline}
+    if map_sharded is not None:
+        line["map_sharded"] = map_sharded
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, w, xyz, nrm, scans, inits)
     print(json.dumps(line), flush=True)
@@ -510,47 +643,163 @@ def run_gpu(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, w, xyz, nrm, scans, inits):
-    """The oracle port on this box's host cores, bounded sample (rank 0, N = 1 only)."""
-    from oracle import oracle
-    threads = max(oracle.max_threads(), len(os.sched_getaffinity(0)))
+def reference_roofline(peak, peak_kind, search_ms, search_launches, dev_ms_timed, k2, res, clocks, B):
+    """REFERENCE-mode workloads (c1, c4): the dominant kernel is ref_reduce_kernel, a LATENCY-bound chain of
+    dependent float adds in source-row order (what makes the result bit-identical to the reference), one
+    block per scan.  Its roofline is the 4.1-cycle FADD dependency floor per row and pass, not HBM bytes:
+    `achieved`/`peak` are rows per second per scan against that floor; the HBM fraction is reported beside."""
+    k_final = float(np.median([int(r.k_final) for r in res]))
+    n_src = float(np.median([int(r.n_source) for r in res]))
+    its = float(np.median([int(r.iterations) for r in res]))
+    srch = float(np.median([int(r.n_searches) for r in res]))
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    reduce_ms = (dev_ms_timed - search_ms) / k2          # per step: everything but the first search launch
+    chain_rows = n_src * (2.0 * its + (srch - 1.0))      # chain passes over the scan's rows: 2 per iteration + 1 per re-search
+    cyc_per_row = reduce_ms * 1e-3 * mhz * 1e6 / max(1.0, chain_rows)
+    alg_bytes = B * its * 48.0 * k_final                  # SURVEY 8(d): 48 K bytes per loop iteration
+    return {"bound": "latency (dependent FADD chain)", "kernel": "ref_reduce_kernel", "achieved": 1.0 / max(cyc_per_row, 1e-9),
+            "peak": 1.0 / 4.1, "unit": "rows/cycle/scan", "frac": 4.1 / max(cyc_per_row, 1e-9), "traffic": None,
+            "peak_kind": "4.1-cycle dependent FADD (profiles/exp/mb/chain.cu)", "cycles_per_row": cyc_per_row,
+            "note": "cycles_per_row is an upper bound: it charges the whole non-search part of the step (chains of all scans run "
+                    "concurrently, one block per scan) to the chain rows of the median scan",
+            "hbm_frac_of_loop_bytes": alg_bytes / max(reduce_ms * 1e-3, 1e-12) / 1e9 / peak, "hbm_peak_kind": peak_kind,
+            "first_search_ms": search_ms / max(1, search_launches),
+            "share_of_step": 1.0 - search_ms / dev_ms_timed, "ms_per_step_with_events": dev_ms_timed / k2}
+
+
+def c1_latency(ssf_gpu, ctx):
+    """Single-scan device latency of the live node's case (10 Hz budget, stochastic_filter.cpp:41): one 32x1024
+    scan against the 1M-point map, in the reference's own loop (STRICT = bit-identical, FAST) and GN."""
+    from ssf_gpu import synth
+    xyz, nrm, half = synth.make_map(1_000_000, normals=True)
+    T = synth.street_pose(100, half=half)
+    scan = synth.make_scan(T, 32, 1024, scan_id=100)
+    T0 = synth.perturb_pose(T, 100)
+    out = {}
+    icp = ssf_gpu.ICPPointToPoint(THR, ITERS, 0.05, 1e-5, context=ctx)
+    icp.setTargetPointCloud(xyz, nrm)
+    icp.setSourcePointCloud(scan)
+    icp.setInitialTransformation(T0)
+    for name, mode, red, acc, eps in (("c1_reference_strict_ms", ssf_gpu.MODE_REFERENCE, ssf_gpu.REDUCE_STRICT, 0.05, 1e-5),
+                                      ("c1_reference_fast_ms", ssf_gpu.MODE_REFERENCE, ssf_gpu.REDUCE_FAST, 0.05, 1e-5),
+                                      ("c1_gn_p2plane_ms", ssf_gpu.MODE_GN_P2PLANE, ssf_gpu.REDUCE_STRICT, 0.0, 0.0)):
+        icp.setMode(mode, red)
+        icp.setAcceptableMeanError(acc)
+        icp.setTransformationEpsilon(eps)
+        out[name] = float(np.median([icp.calculateAlignment().device_ms for _ in range(7)]))
+    icp.close()
+    return out
+
+
+def run_map_sharded(args, ssf_gpu, capi, torch, dist, ctx, rank, world, local_rank):
+    """BASELINE.json configs[2] in the same run: the 50M-point map split into `world` column shards (one-cell
+    halo), the same scans on every rank, one exchange of 32 doubles per scan per iteration.  Strong scaling:
+    reported next to the same scans against the unsharded map on one GPU would need 1.6 GB of map per rank,
+    which fits -- so rank 0 also measures that (`one_gpu_value`) as the denominator."""
+    from ssf_gpu import shard
+    name = "c3"
+    w = WORKLOADS[name]
+    B = w["scans_per_step"]
+    w, xyz, nrm, half, scans, inits, gts = make_workload(name, B, rank, world=world)
+    icp = ssf_gpu.ICPPointToPoint(THR, ITERS, 0.0, 0.0, mode=ssf_gpu.MODE_GN_P2PLANE, context=ctx)
     t0 = time.time()
-    tree = oracle.KdTree(xyz)
+    sh = shard.shard_map(xyz, nrm, rank, world, THR)
+    icp.setTargetShard(sh)
+    if args.exchange == "peer":
+        shard.setup_peer_exchange(icp, rank, world, max_scans=B)
+    else:
+        icp.setAllreduce(shard.torch_allreduce_hook(local_rank))
     build_s = time.time() - t0
-    n = max(1, min(args.cpu_scans, len(scans)))
+    n_pts = [s.shape[0] for s in scans]
+    total = int(sum(n_pts))
+    cat = np.ascontiguousarray(np.concatenate([s[:, :3] for s in scans], axis=0))
+    T0 = np.ascontiguousarray(np.stack([np.asarray(T, np.float32).T.reshape(16) for T in inits]))
+    res = (capi.IcpResult * B)()
+    batch = ssf_gpu.Batch(icp, B, total + 1)
+    batch.upload_ptr(cat.ctypes.data, n_pts, 12)
+    batch.set_initial_ptr(T0.ctypes.data)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
 
-    def run(th):
-        t0 = time.time()
-        for sc, T0 in zip(scans[:n], inits[:n]):
-            src = oracle.voxel_grid(sc, w["leaf"])[0] if w["leaf"] > 0 else sc
-            if w["mode"] in ("gn_p2plane", "gn_p2p"):
-                oracle.icp_gn(tree, src, T0, mode="p2plane" if w["mode"] == "gn_p2plane" else "p2p", normals=nrm,
-                              max_correspondence_dist=THR, num_iterations=w.get("iters", ITERS), threads=th)
-            else:
-                oracle.icp_reference(tree, src, T0, THR, ITERS, 0.05, 1e-5, threads=th)
-        return n / (time.time() - t0)
+    def sync():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
 
-    v_all = run(threads)
-    v_one = run(1) if n <= 8 else None
-    return {"value": v_all, "unit": "scans/s", "cores": threads, "kind": "port",
-            "sample": f"{n} scans of the same workload, KD-tree build ({build_s:.1f}s) excluded",
-            "value_single_thread": v_one}
+    def timed(n):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            batch.run()
+        e1.record(stream)
+        ctx.synchronize()
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+
+    for _ in range(3):
+        batch.run()
+    steps = max(5, min(args.steps, 30))
+    ms = timed(steps)
+    batch.results_into(res)
+    errs = [pose_delta(ssf_gpu._rowmajor(r.transformation), T)[0] for r, T in zip(res, gts)]
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.cpu()[0])
+    # the exchange alone: the same alignment with the per-scan work taken out is not available, so time the
+    # step with searches bracketed and subtract: (step - searches) / iterations = row-sum + exchange + solve
+    ctx.time_searches(True)
+    batch.run()
+    ctx.search_time()
+    ms_ev = timed(3)
+    s_ms, s_n = ctx.search_time()
+    ctx.time_searches(False)
+    sync()
+    out = {"workload": f"c3: {w['desc']}", "n_ranks": world, "scans_per_step": B, "exchange": args.exchange,
+           "value": B * steps / (ms_max * 1e-3), "unit": "scans/s", "ms_per_step": ms_max / steps,
+           "exchange_us_per_iter": 1e3 * (ms_ev - s_ms) / 3 / ITERS, "search_us_per_iter": 1e3 * s_ms / max(1, s_n),
+           "shard_points_rank0": int(sh["points"].shape[0]), "map_points": int(xyz.shape[0]),
+           "shard_build_s_rank0": build_s, "median_pose_error_m": float(np.median(errs))}
+    batch.close()
+    icp.close()
+    if rank == 0:  # the denominator: the same scans against the whole map on one GPU
+        one = ssf_gpu.ICPPointToPoint(THR, ITERS, 0.0, 0.0, mode=ssf_gpu.MODE_GN_P2PLANE, context=ctx)
+        one.setTargetPointCloud(xyz, nrm)
+        b1 = ssf_gpu.Batch(one, B, total + 1)
+        b1.upload_ptr(cat.ctypes.data, n_pts, 12)
+        b1.set_initial_ptr(T0.ctypes.data)
+        for _ in range(3):
+            b1.run()
+        ctx.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            b1.run()
+        e1.record(stream)
+        ctx.synchronize()
+        e1.synchronize()
+        out["one_gpu_value"] = B * steps / (e0.elapsed_time(e1) * 1e-3)
+        out["speedup_vs_one_gpu"] = out["value"] / out["one_gpu_value"]
+        b1.close()
+        one.close()
+    dist.barrier()
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--scans-per-step", type=int, default=0, help="default: 64 (16 for c3)")
+    ap.add_argument("--scans-per-step", type=int, default=0, help="default: the workload's (256 for c2)")
     ap.add_argument("--cpu-scans", type=int, default=8, help="scans in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the config-1 single-scan latency block")
+    ap.add_argument("--no-map-sharded", action="store_true", help="N > 1: skip the map-sharded (c3) block")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="map-sharded workloads: in-kernel exchange over peer memory (default) or the NCCL all-reduce hook")
     args = ap.parse_args()
-    args.l2_note = "n/a (CPU run)"
     if args.scans_per_step <= 0:
         args.scans_per_step = WORKLOADS[args.workload].get("scans_per_step", 64)
     rank = int(os.environ.get("RANK", "0"))

@@ -86,7 +86,7 @@ typedef struct {
     int32_t has_converged;
     int32_t n_searches;       /* correspondence searches run                               */
     int32_t k_final;          /* correspondences in the last search                        */
-    int32_t aborted;          /* 1: < 10 correspondences on the first search (cpp:196-200) */
+    int32_t aborted;          /* 1: < 10 correspondences on the first search (cpp:196-200); 2: multi-GPU exchange failed */
     float fitness;            /* k_final / n_source                                        */
     int32_t n_source;         /* source points after optional voxel downsample             */
     float device_ms;          /* device time of the call (CUDA events)                     */
@@ -202,6 +202,10 @@ int ssf_batch_set_initial(ssf_batch *b, const float *T_colmajor);
 int ssf_batch_run(ssf_batch *b);
 /* Wait and copy the n_scans results back. */
 int ssf_batch_results(ssf_batch *b, ssf_icp_result *out, size_t n_scans);
+/* Search statistics of the last run (GN / O3D modes): per search launch, the queries it answered and
+ * how many of them needed a walk of the index (the others were confirmed by their search certificate).
+ * At most cap entries are written; *n_launches = launches of the run. */
+int ssf_batch_search_stats(ssf_batch *b, uint64_t *answered, uint64_t *walked, size_t cap, size_t *n_launches);
 /* upload + set_initial + run + results in one call (host buffers in, host results out). */
 int ssf_icp_align_batch(ssf_icp *icp, const float *xyz, const size_t *n_pts, size_t n_scans, size_t stride_bytes,
                         const float *T_colmajor, ssf_icp_result *out);
@@ -228,15 +232,20 @@ int ssf_icp_set_target_shard(ssf_icp *icp, const float *xyz, size_t n, size_t st
 typedef int (*ssf_allreduce_fn)(void *user, double *buf, size_t count, void *cuda_stream);
 int ssf_icp_set_allreduce(ssf_icp *icp, ssf_allreduce_fn fn, void *user);
 /* In-kernel exchange instead of the hook (one process per GPU, all on one NVLink box): every rank
- * creates its exchange buffer and gets a 64-byte CUDA IPC handle, the caller gathers the handles of
+ * creates its exchange buffer and gets a handle blob (CUDA IPC handle + identity), the caller gathers the blobs of
  * all ranks (any transport: torch.distributed, MPI, a file) and hands the rank-ordered array
- * (world x 64 bytes) to ssf_icp_exchange_open.  From then on the row-sum kernel stores this rank's
+ * (world x SSF_XCH_HANDLE_BYTES) to ssf_icp_exchange_open.  From then on the row-sum kernel stores this rank's
  * per-scan rows straight into every rank's buffer (peer stores over NVLink) and the solve kernel
  * waits for all ranks' epoch flags and adds the rows in rank order -- no host call and no NCCL
  * collective per iteration.  All ranks must run the same sequence of alignments with the same
  * scans; max_scans bounds the scans per batch.  world <= 32. */
-int ssf_icp_exchange_create(ssf_icp *icp, int rank, int world, size_t max_scans, unsigned char handle_out[64]);
-int ssf_icp_exchange_open(ssf_icp *icp, const unsigned char *handles /* world x 64 bytes, rank order */);
+#define SSF_XCH_HANDLE_BYTES 128 /* CUDA IPC handle + device UUID + (max_scans, world, rank) */
+int ssf_icp_exchange_create(ssf_icp *icp, int rank, int world, size_t max_scans,
+                            unsigned char handle_out[SSF_XCH_HANDLE_BYTES]);
+/* SSF_ERR_COMM when two ranks share a device or the ranks' (world, max_scans) differ.  During a run a rank
+ * waits at most 20 s for a peer's sums, and rejects sums of another batch shape (scans, iterations, mode):
+ * the scan's result then carries aborted == 2 and ssf_batch_results returns SSF_ERR_COMM. */
+int ssf_icp_exchange_open(ssf_icp *icp, const unsigned char *handles /* world x SSF_XCH_HANDLE_BYTES, rank order */);
 int ssf_icp_exchange_close(ssf_icp *icp);
 
 /* ---- profiling hook ------------------------------------------------------------------- */

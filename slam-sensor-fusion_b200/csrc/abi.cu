@@ -393,7 +393,8 @@ static void exchange_release(ssf_icp *icp)
     x.world = 0;
 }
 
-extern "C" int ssf_icp_exchange_create(ssf_icp *icp, int rank, int world, size_t max_scans, unsigned char handle_out[64])
+extern "C" int ssf_icp_exchange_create(ssf_icp *icp, int rank, int world, size_t max_scans,
+                                       unsigned char handle_out[SSF_XCH_HANDLE_BYTES])
 {
     SSF_ARG(icp && handle_out, "ssf_icp_exchange_create: NULL argument");
     SSF_ARG(world >= 1 && world <= 32 && rank >= 0 && rank < world, "ssf_icp_exchange_create: bad rank / world (<= 32)");
@@ -405,7 +406,7 @@ extern "C" int ssf_icp_exchange_create(ssf_icp *icp, int rank, int world, size_t
     x.rank = rank;
     x.world = world;
     x.max_scans = max_scans;
-    x.bytes = (size_t)2 * world * max_scans * kAccum * sizeof(double) + (size_t)2 * world * sizeof(unsigned long long);
+    x.bytes = (size_t)2 * world * max_scans * kAccum * sizeof(double) + (size_t)4 * world * sizeof(unsigned long long);
     SSF_CUDA(cudaMalloc(&x.local, x.bytes));
     SSF_CUDA(cudaMemset(x.local, 0, x.bytes));
     SSF_TRY(x.counter.reserve(1));
@@ -413,7 +414,17 @@ extern "C" int ssf_icp_exchange_create(ssf_icp *icp, int rank, int world, size_t
     SSF_CUDA(cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     SSF_CUDA(cudaIpcGetMemHandle(&h, x.local));
+    // blob: [0..63] IPC handle, [64..79] device UUID, [80..87] max_scans, [88..91] world, [92..95] rank
+    cudaDeviceProp prop;
+    SSF_CUDA(cudaGetDeviceProperties(&prop, icp->ctx->device));
+    memset(handle_out, 0, SSF_XCH_HANDLE_BYTES);
     memcpy(handle_out, &h, 64);
+    memcpy(handle_out + 64, &prop.uuid, 16);
+    const unsigned long long ms64 = max_scans;
+    const int32_t w32 = world, r32 = rank;
+    memcpy(handle_out + 80, &ms64, 8);
+    memcpy(handle_out + 88, &w32, 4);
+    memcpy(handle_out + 92, &r32, 4);
     x.epoch = 1;
     return SSF_OK;
 }
@@ -427,6 +438,27 @@ extern "C" int ssf_icp_exchange_open(ssf_icp *icp, const unsigned char *handles)
         return SSF_ERR_STATE;
     }
     SSF_TRY(use_device(icp->ctx));
+    // every rank must sit on its own device (two ranks on one GPU would be mutually waiting launches)
+    // and must have created the exchange with the same shape
+    for (int r = 0; r < x.world; ++r) {
+        const unsigned char *hr = handles + (size_t)SSF_XCH_HANDLE_BYTES * r;
+        unsigned long long ms64 = 0;
+        int32_t w32 = 0, r32 = -1;
+        memcpy(&ms64, hr + 80, 8);
+        memcpy(&w32, hr + 88, 4);
+        memcpy(&r32, hr + 92, 4);
+        if (ms64 != x.max_scans || w32 != x.world || r32 != r) {
+            set_error("ssf_icp_exchange_open: handle %d was created as rank %d of %d with max_scans %llu (here: world %d, "
+                      "max_scans %zu)", r, (int)r32, (int)w32, ms64, x.world, x.max_scans);
+            return SSF_ERR_COMM;
+        }
+        for (int q = 0; q < r; ++q)
+            if (memcmp(hr + 64, handles + (size_t)SSF_XCH_HANDLE_BYTES * q + 64, 16) == 0) {
+                set_error("ssf_icp_exchange_open: ranks %d and %d are on the same GPU; the in-kernel exchange needs one "
+                          "device per rank", q, r);
+                return SSF_ERR_COMM;
+            }
+    }
     x.peers.assign(x.world, nullptr);
     x.opened.assign(x.world, false);
     for (int r = 0; r < x.world; ++r) {
@@ -435,7 +467,7 @@ extern "C" int ssf_icp_exchange_open(ssf_icp *icp, const unsigned char *handles)
             continue;
         }
         cudaIpcMemHandle_t h;
-        memcpy(&h, handles + (size_t)64 * r, 64);
+        memcpy(&h, handles + (size_t)SSF_XCH_HANDLE_BYTES * r, 64);
         cudaError_t e = cudaIpcOpenMemHandle(&x.peers[r], h, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
             set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
@@ -483,6 +515,44 @@ extern "C" int ssf_icp_set_source(ssf_icp *icp, const float *xyz, size_t n, size
     return SSF_OK;
 }
 
+// setDebugMode(true): the text printStepDebug (cpp:172-183) and the tail of calculateAlignment
+// (cpp:237-246) write to stdout, from the per-pass error trace of the finished alignment.
+static void debug_print(ssf_icp *icp, const ssf_icp_result &out)
+{
+    const ssf_icp_params &p = icp->prm;
+    const size_t n = (size_t)icp->single->buf.trace_len;
+    std::vector<float> err(n ? n : 1);
+    if (n == 0 || ssf_icp_get_trace(icp, err.data(), nullptr, n) != SSF_OK) return;
+    const bool ref = p.mode == SSF_MODE_REFERENCE;
+    float last_error = 3.402823466e+38f;  // cpp:205
+    for (size_t i = 0; i < n; ++i) {
+        if (err[i] != err[i]) break;
+        printf("[ICP INFO] Iteration %zu - Error: %g\n", i, err[i]);
+        if (err[i] < p.acceptable_mean_error) printf("[ICP INFO] Acceptable error reached. Stopping iterations.\n");
+        // REFERENCE: the test of cpp:179 against the previous pass's error; GN: the pose update of this
+        // pass was below the epsilon (the stop rule of those modes)
+        const bool eps_hit = ref ? fabsf(last_error - err[i]) < p.transformation_epsilon
+                                 : (out.has_converged && (int)i + 1 == out.iterations && !(err[i] < p.acceptable_mean_error));
+        if (eps_hit) printf("[ICP INFO] Transformation epsilon reached. Stopping iterations.\n");
+        last_error = err[i];
+    }
+    if (out.iterations == p.num_iterations)
+        printf("[ICP INFO] We reached the maximum number of iterations. Returning best transform found.\n");
+    printf("[ICP INFO] Total iterations taken: %d\n[ICP INFO] Final error: %g\n", out.iterations, out.error);
+    // operator<< of Eigen::Matrix4f (default IOFormat): %g coefficients right-aligned to the widest one
+    char cell[16][32];
+    int wid = 0;
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            const int len = snprintf(cell[r * 4 + c], sizeof(cell[0]), "%g", out.transformation[c * 4 + r]);
+            if (len > wid) wid = len;
+        }
+    printf("[ICP INFO] Final transformation matrix: \n");
+    for (int r = 0; r < 4; ++r)
+        printf("%*s %*s %*s %*s\n", wid, cell[r * 4], wid, cell[r * 4 + 1], wid, cell[r * 4 + 2], wid, cell[r * 4 + 3]);
+    fflush(stdout);
+}
+
 extern "C" int ssf_icp_align(ssf_icp *icp, ssf_icp_result *out)
 {
     SSF_ARG(icp && out, "ssf_icp_align: NULL argument");
@@ -497,24 +567,8 @@ extern "C" int ssf_icp_align(ssf_icp *icp, ssf_icp_result *out)
     SSF_TRY(ssf_batch_set_initial(icp->single, icp->T_init));
     SSF_TRY(ssf_batch_run(icp->single));
     SSF_TRY(ssf_batch_results(icp->single, out, 1));
-    if (out->aborted) fprintf(stderr, "[ICP ERROR] Not enough valid correspondences found. Aborting.\n");  // cpp:198
-    if (icp->prm.debug && icp->prm.mode == SSF_MODE_REFERENCE && !out->aborted) {
-        // printStepDebug / tail of calculateAlignment (cpp:172-183, 237-246)
-        std::vector<float> err(icp->prm.num_iterations);
-        std::vector<int32_t> srch(icp->prm.num_iterations);
-        if (ssf_icp_get_trace(icp, err.data(), srch.data(), err.size()) == SSF_OK) {
-            for (size_t i = 0; i < err.size(); ++i) {
-                if (err[i] != err[i]) break;
-                printf("[ICP INFO] Iteration %zu - Error: %g\n", i, err[i]);
-                if (err[i] < icp->prm.acceptable_mean_error)
-                    printf("[ICP INFO] Acceptable error reached. Stopping iterations.\n");
-                if (srch[i]) printf("[ICP INFO] Transformation epsilon reached. Stopping iterations.\n");
-            }
-        }
-        if (out->iterations == icp->prm.num_iterations)
-            printf("[ICP INFO] We reached the maximum number of iterations. Returning best transform found.\n");
-        printf("[ICP INFO] Total iterations taken: %d\n[ICP INFO] Final error: %g\n", out->iterations, out->error);
-    }
+    if (out->aborted == 1) fprintf(stderr, "[ICP ERROR] Not enough valid correspondences found. Aborting.\n");  // cpp:198
+    if (icp->prm.debug && out->aborted == 0) debug_print(icp, *out);
     return SSF_OK;
 }
 
@@ -919,7 +973,10 @@ extern "C" int ssf_batch_run(ssf_batch *b)
     SSF_TRY(use_device(ctx));
     const ssf_icp_params &p = icp->prm;
     BatchBuffers &buf = b->buf;
-    const int trace_len = p.mode == SSF_MODE_REFERENCE ? p.num_iterations : 0;
+    // per-pass error trace: always in REFERENCE mode (ssf_icp_get_trace), in the other modes only for
+    // the debug print of a single alignment
+    const int trace_len = p.mode == SSF_MODE_REFERENCE ? p.num_iterations
+                                                       : (p.debug && buf.n_scans == 1 ? p.num_iterations + 1 : 0);
     buf.trace_len = trace_len;
     SSF_TRY(buf.trace_err.reserve(buf.n_scans * (size_t)(trace_len ? trace_len : 1)));
     SSF_TRY(buf.trace_search.reserve(buf.n_scans * (size_t)(trace_len ? trace_len : 1)));
@@ -997,6 +1054,35 @@ extern "C" int ssf_batch_results(ssf_batch *b, ssf_icp_result *out, size_t n_sca
                 t2, t3, t4);
     }
     for (size_t s = 0; s < n_scans; ++s) out[s].device_ms = ms;
+    for (size_t s = 0; s < n_scans; ++s)
+        if (out[s].aborted == 2) {
+            set_error("scan %zu: the per-scan sums of a peer rank did not arrive (timeout, or the ranks ran different "
+                      "batch shapes / iteration counts / modes)", s);
+            return SSF_ERR_COMM;
+        }
+    return SSF_OK;
+}
+
+extern "C" int ssf_batch_search_stats(ssf_batch *b, uint64_t *answered, uint64_t *walked, size_t cap, size_t *n_launches)
+{
+    SSF_ARG(b && n_launches, "ssf_batch_search_stats: NULL argument");
+    if (!b->ran) {
+        set_error("ssf_batch_search_stats: the batch has not run");
+        return SSF_ERR_STATE;
+    }
+    ssf_ctx *ctx = b->icp->ctx;
+    SSF_TRY(use_device(ctx));
+    const size_t n = (size_t)b->buf.search_stats_len;
+    *n_launches = n;
+    const size_t m = n < cap ? n : cap;
+    if (m == 0) return SSF_OK;
+    std::vector<unsigned long long> h(2 * m);
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    SSF_CUDA(cudaMemcpy(h.data(), b->buf.search_stats.p, 2 * m * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < m; ++i) {
+        if (answered) answered[i] = h[2 * i];
+        if (walked) walked[i] = h[2 * i + 1];
+    }
     return SSF_OK;
 }
 

@@ -25,7 +25,7 @@ struct ScanState {
     int iterations, done, converged, aborted, n_searches, k_last, need_search, have_step;
     double fitness, rmse;  // O3D
     float last_step;       // size of the last pose update (metres; rotations weighted by a 30 m lever arm)
-    float pad_;
+    int comm_error;        // map sharding: a peer's rows did not arrive in time (solve_xchg_kernel)
     uint32_t pt_begin;     // first slot in the packed arrays (multiple of kTile)
     uint32_t n_pts;        // source points (after optional voxel downsample)
     uint32_t tile_begin, tile_cap;
@@ -42,6 +42,8 @@ struct BatchBuffers {
     DevBuf<uint32_t> tile_scan;
     DevBuf<uint4> active;        // tiles that hold points (search kernel work list): (tile, scan, first slot, points)
     DevBuf<uint32_t> counters;   // [0] number of active tiles, [1 + i] tile fetch counter of search launch i
+    DevBuf<unsigned long long> search_stats;  // per search launch: (queries answered, queries walked)
+    int search_stats_len = 0;
     DevBuf<double> partials;   // [tile][kAccum]
     DevBuf<double> sums;       // [scan][kAccum]: per-scan totals (all-reduced across ranks when sharded)
     DevBuf<ScanState> state;
@@ -93,6 +95,7 @@ struct XchView {
     int rank = 0, world = 0;
     uint32_t max_scans = 0;
     uint32_t *counter = nullptr;   // blocks of the row-sum kernel that have stored their row
+    unsigned long long timeout_ns = 20000000000ull;  // give up waiting for a peer's rows after this long
 };
 
 struct IcpConfig {

@@ -71,6 +71,7 @@ __global__ void init_states_kernel(ScanState *st, const float *T_init, uint32_t 
     z.fitness = 0.0;
     z.rmse = 0.0;
     z.last_step = 3.0e38f;
+    z.comm_error = 0;
     for (int i = 0; i < trace_len; ++i) {
         trace_err[(size_t)s * trace_len + i] = nanf("");
         trace_search[(size_t)s * trace_len + i] = 0;
@@ -87,6 +88,17 @@ int init_states(BatchBuffers &b, const float *T_init_dev, cudaStream_t st)
     return SSF_OK;
 }
 
+__global__ void no_points_kernel(ScanState *st, uint32_t n_scans, int mode)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scans) return;
+    ScanState &z = st[s];
+    z.done = 1;
+    z.n_searches = 1;
+    if (mode == SSF_MODE_O3D_P2P) z.error = 0.f;
+    else z.aborted = 1;
+}
+
 __global__ void results_kernel(ScanState *st, ssf_icp_result *out, uint32_t n_scans, int mode, float acc_err)
 {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,13 +110,14 @@ __global__ void results_kernel(ScanState *st, ssf_icp_result *out, uint32_t n_sc
         z.error = z.last_error;
         z.converged = z.last_error < acc_err ? 1 : 0;
     }
-    for (int i = 0; i < 16; ++i) r.transformation[i] = z.aborted ? z.T_init[i] : z.T[i];
-    r.error = z.aborted ? 1e6f : z.error;
-    r.iterations = z.aborted ? 0 : z.iterations;
-    r.has_converged = z.aborted ? 0 : z.converged;
+    const bool ab = z.aborted || z.comm_error;
+    for (int i = 0; i < 16; ++i) r.transformation[i] = ab ? z.T_init[i] : z.T[i];
+    r.error = ab ? 1e6f : z.error;
+    r.iterations = ab ? 0 : z.iterations;
+    r.has_converged = ab ? 0 : z.converged;
     r.n_searches = z.n_searches;
     r.k_final = z.k_last;
-    r.aborted = z.aborted;
+    r.aborted = z.comm_error ? 2 : z.aborted;  // 2: a peer's sums never arrived (ssf_batch_results -> SSF_ERR_COMM)
     r.n_source = (int32_t)z.n_pts;
     r.fitness = z.n_pts ? (float)((double)z.k_last / (double)z.n_pts) : 0.f;
     r.device_ms = 0.f;
@@ -339,7 +352,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
                         const ScanState *__restrict__ states, float limit, int32_t *__restrict__ corr,
                         double *__restrict__ partials, uint2 *__restrict__ cert, const float *__restrict__ pose_hist,
                         int use_cert, int pass, const uint4 *__restrict__ active,
-                        const uint32_t *__restrict__ n_active, uint32_t *__restrict__ fetch)
+                        const uint32_t *__restrict__ n_active, uint32_t *__restrict__ fetch,
+                        unsigned long long *__restrict__ stats)
 {
     __shared__ __align__(128) float4 s_q[kTile];  // TMA destination; transformed in place, w = owned by this rank
     __shared__ __align__(8) unsigned long long s_bar;
@@ -352,6 +366,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
     float *const s_b2 = reinterpret_cast<float *>(s_raw + kTile * 8);
     uint32_t *const s_skip = reinterpret_cast<uint32_t *>(s_raw + kTile * 12);
     __shared__ uint32_t s_nq, s_nfar, s_nfar_none, s_next;
+    __shared__ uint32_t sred_u[THREADS / 32];
     __shared__ float sT[16];
     constexpr int kQ_ = kTile / THREADS;  // queries per thread
     __shared__ double sred[THREADS / 32][kAccum];
@@ -439,11 +454,53 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
             s_queue[atomicAdd(&s_nq, 1u)] = (unsigned short)r;
         }
         __syncthreads();
+        // First search of an alignment (no previous neighbour to start from): the queries of a tile are
+        // in voxel order, i.e. consecutive ones are neighbours in space, so the queue is put back into
+        // source order and every thread walks kQ_ CONSECUTIVE queries, handing the neighbour it found
+        // to the next one as its seed.  A seed only tightens the bound a walk starts with -- the
+        // result is that of the unseeded walk -- but the walk then prunes from the first row on.
+        // search statistics of this launch: [0] queries answered, [1] queries that needed a walk
+        if (threadIdx.x == 0) {
+            atomicAdd(&stats[0], (unsigned long long)n_here);
+            atomicAdd(&stats[1], (unsigned long long)s_nq);
+        }
+        const bool chain = !use_cert && kQ_ > 1;
+        if (chain) {
+            // s_queue holds an arbitrary order of the walkable rows; s_far (free until the walks) gets
+            // a presence flag per row, then the queue is rebuilt in row order
+            for (uint32_t r = threadIdx.x; r < kTile; r += THREADS) s_far[r] = 0;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < s_nq; i += THREADS) s_far[s_queue[i]] = 1;
+            __syncthreads();
+            // ballot-scan compaction in row order (one pass of kTile / THREADS rounds)
+            uint32_t base = 0;
+            for (uint32_t r0 = 0; r0 < kTile; r0 += THREADS) {
+                const uint32_t r = r0 + threadIdx.x;
+                const bool on = s_far[r] != 0;
+                const uint32_t bal = __ballot_sync(0xffffffffu, on);
+                const uint32_t wpre = __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+                if ((threadIdx.x & 31) == 0) sred_u[threadIdx.x >> 5] = __popc(bal);
+                __syncthreads();
+                uint32_t off = base;
+                for (uint32_t wv = 0; wv < (threadIdx.x >> 5); ++wv) off += sred_u[wv];
+                uint32_t tot = 0;
+                for (uint32_t wv = 0; wv < THREADS / 32; ++wv) tot += sred_u[wv];
+                if (on) s_queue[off + wpre] = (unsigned short)r;
+                base += tot;
+                __syncthreads();
+            }
+        }
         // ---- S: near part of the walk for every queued query; the few that must go on to rings 2..
         // are queued again and finished afterwards, packed densely, so that a warp is not held up
         // by the lanes that drew a far query ----
         const uint32_t nq = s_nq;
-        for (uint32_t i = threadIdx.x; i < nq; i += THREADS) {
+        // chain: thread t takes queue items kQ_ t .. kQ_ t + kQ_ - 1 (consecutive rows); otherwise item
+        // t, t + THREADS, ... (dense packing of the few unconfirmed queries of a certificate launch)
+        const uint32_t i_first = chain ? threadIdx.x * kQ_ : threadIdx.x;
+        const uint32_t i_step = chain ? 1u : (uint32_t)THREADS;
+        const uint32_t i_end = chain ? min(nq, i_first + kQ_) : nq;
+        uint32_t carry = kNoPos;  // chain: the neighbour found for the previous row
+        for (uint32_t i = i_first; i < i_end; i += i_step) {
             const uint32_t r = s_queue[i];
             SSF_CHECK(r < n_here);
             const float4 p = s_q[r];
@@ -451,15 +508,18 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
             uint32_t pos;
             float b2 = 0.f;
             bool far;
+            const uint32_t seed = chain ? carry : s_pos[r];
+            if (chain) s_pos[r] = seed;
             if (make_cert) {
                 NNBest<true> B;
-                far = nn_walk_near<true>(map, p.x, p.y, p.z, limit, map.cert_mu, B, s_pos[r]);
+                far = nn_walk_near<true>(map, p.x, p.y, p.z, limit, map.cert_mu, B, seed);
                 key = B.key; pos = B.pos; b2 = B.b2;
             } else {
                 NNBest<false> B;
-                far = nn_walk_near<false>(map, p.x, p.y, p.z, limit, 0.f, B, s_pos[r]);
+                far = nn_walk_near<false>(map, p.x, p.y, p.z, limit, 0.f, B, seed);
                 key = B.key; pos = B.pos;
             }
+            carry = (uint32_t)(key >> 32) < none_hi ? pos : kNoPos;
             if (far) s_skip[r] = s_pos[r];  // (read before s_pos is overwritten)
             s_key[r] = key;
             s_pos[r] = pos;
@@ -590,7 +650,7 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const ScanState *__restrict
 }
 
 // one thread: normal equations -> Cholesky -> pose update -> stop rules (sv = the scan's kAccum totals)
-__device__ void gn_solve(ScanState &z, const double *sv, int pass, float acc_err, float eps, float *hist)
+__device__ void gn_solve(ScanState &z, const double *sv, int pass, float acc_err, float eps, float *hist, float *trace)
 {
     const long long K = (long long)(sv[28] + 0.5);
     z.n_searches += 1;
@@ -603,6 +663,7 @@ __device__ void gn_solve(ScanState &z, const double *sv, int pass, float acc_err
     if (K < 6) { z.done = 1; return; }
     const float err = (float)sqrt(sv[27] / (double)K);
     z.error = err;
+    if (trace) trace[pass] = err;  // debug trace: error measured by pass `pass`
     if (err < acc_err) { z.converged = 1; z.done = 1; return; }
     double A[36], nb[6], x[6];
     int t = 0;
@@ -627,7 +688,7 @@ __device__ void gn_solve(ScanState &z, const double *sv, int pass, float acc_err
     if (mx < (double)eps) { z.converged = 1; z.done = 1; }
 }
 
-__device__ void o3d_solve(ScanState &z, const double *sv, int pass, int max_iteration, float *hist)
+__device__ void o3d_solve(ScanState &z, const double *sv, int pass, int max_iteration, float *hist, float *trace)
 {
     const long long K = (long long)(sv[0] + 0.5);
     z.n_searches += 1;
@@ -636,6 +697,7 @@ __device__ void o3d_solve(ScanState &z, const double *sv, int pass, int max_iter
     z.fitness = z.n_pts ? (double)K / (double)z.n_pts : 0.0;
     z.rmse = K > 0 ? sqrt(sv[16] / (double)K) : 0.0;
     z.error = (float)z.rmse;
+    if (trace) trace[pass] = z.error;
     if (pass > 0 && fabs(prev_fit - z.fitness) < 1e-6 && fabs(prev_rmse - z.rmse) < 1e-6) {
         z.converged = 1;
         z.done = 1;
@@ -673,7 +735,7 @@ __device__ void o3d_solve(ScanState &z, const double *sv, int pass, int max_iter
 // the sums arrive from outside (map sharding: all-reduced across ranks)
 __global__ void __launch_bounds__(32) solve_kernel(ScanState *states, const double *__restrict__ sums, int pass,
                                                    int o3d, float acc_err, float eps, int max_iteration,
-                                                   float *pose_hist)
+                                                   float *pose_hist, float *trace_err, int trace_len)
 {
     __shared__ double sv[kAccum];
     ScanState &z = states[blockIdx.x];
@@ -682,14 +744,16 @@ __global__ void __launch_bounds__(32) solve_kernel(ScanState *states, const doub
     __syncwarp();
     if (threadIdx.x != 0) return;
     float *hist = pose_hist + (size_t)blockIdx.x * kCertHist * 16;
-    if (o3d) o3d_solve(z, sv, pass, max_iteration, hist);
-    else gn_solve(z, sv, pass, acc_err, eps, hist);
+    float *trace = pass < trace_len ? trace_err + (size_t)blockIdx.x * trace_len : nullptr;
+    if (o3d) o3d_solve(z, sv, pass, max_iteration, hist, trace);
+    else gn_solve(z, sv, pass, acc_err, eps, hist, trace);
 }
 
 // single GPU: ordered sum of the scan's partial rows and the solve in one launch
 __global__ void __launch_bounds__(256)
     rowsum_solve_kernel(ScanState *states, const double *__restrict__ partials, double *__restrict__ sums, int pass,
-                        int o3d, float acc_err, float eps, int max_iteration, float *pose_hist)
+                        int o3d, float acc_err, float eps, int max_iteration, float *pose_hist, float *trace_err,
+                        int trace_len)
 {
     __shared__ double sw[8][kAccum];
     __shared__ double sv[kAccum];
@@ -710,8 +774,9 @@ __global__ void __launch_bounds__(256)
     __syncwarp();
     if (lane != 0) return;
     float *hist = pose_hist + (size_t)blockIdx.x * kCertHist * 16;
-    if (o3d) o3d_solve(z, sv, pass, max_iteration, hist);
-    else gn_solve(z, sv, pass, acc_err, eps, hist);
+    float *trace = pass < trace_len ? trace_err + (size_t)blockIdx.x * trace_len : nullptr;
+    if (o3d) o3d_solve(z, sv, pass, max_iteration, hist, trace);
+    else gn_solve(z, sv, pass, acc_err, eps, hist, trace);
 }
 
 // =========================================================================================
@@ -1093,18 +1158,20 @@ __device__ __forceinline__ double *xch_rows(void *base, const XchView &x, int pa
 {
     return reinterpret_cast<double *>(base) + ((size_t)(par * x.world + r) * x.max_scans) * kAccum;
 }
+// flag record of (parity, rank): [0] epoch, [1] what that rank ran (scans, passes, mode) -- a peer whose
+// batch shape differs is reported instead of summed
 __device__ __forceinline__ unsigned long long *xch_flag(void *base, const XchView &x, int par, int r)
 {
     return reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(base) +
                                                   (size_t)2 * x.world * x.max_scans * kAccum) +
-           par * x.world + r;
+           2 * (par * x.world + r);
 }
 
 // ordered sum of a scan's partial rows, stored into EVERY rank's buffer (peer stores over NVLink);
 // the last block to finish publishes the epoch to every rank
 __global__ void __launch_bounds__(256)
     rowsum_xchg_kernel(const ScanState *__restrict__ states, const double *__restrict__ partials, XchView x,
-                       unsigned long long epoch)
+                       unsigned long long epoch, unsigned long long shape)
 {
     __shared__ double sw[8][kAccum];
     const ScanState &z = states[blockIdx.x];
@@ -1130,6 +1197,7 @@ __global__ void __launch_bounds__(256)
         __threadfence_system();
         for (int r = 0; r < x.world; ++r) {
             unsigned long long *f = xch_flag(x.peers[r], x, par, x.rank);
+            f[1] = shape;
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
         }
     }
@@ -1137,22 +1205,38 @@ __global__ void __launch_bounds__(256)
 
 // wait for every rank's rows of this epoch, add them in rank order (identical on all ranks), solve
 __global__ void __launch_bounds__(32)
-    solve_xchg_kernel(ScanState *states, XchView x, unsigned long long epoch, double *__restrict__ sums, int pass, int o3d,
-                      float acc_err, float eps, int max_iteration, float *pose_hist)
+    solve_xchg_kernel(ScanState *states, XchView x, unsigned long long epoch, unsigned long long shape,
+                      double *__restrict__ sums, int pass, int o3d, float acc_err, float eps, int max_iteration,
+                      float *pose_hist, float *trace_err, int trace_len)
 {
     __shared__ double sv[kAccum];
     ScanState &z = states[blockIdx.x];
     if (z.done) return;
     const int lane = threadIdx.x, par = (int)(epoch & 1ull);
     void *mine = x.peers[x.rank];
+    bool late = false;
     if (lane < x.world) {
+        // bounded wait: a peer that failed before its row-sum, or whose epochs drifted (different batch
+        // size / iteration count / mode), must not leave this GPU spinning for ever
         const unsigned long long *f = xch_flag(mine, x, par, lane);
-        unsigned long long v;
+        unsigned long long v, t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-        } while (v < epoch);
+            if (v >= epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            late = t1 - t0 > x.timeout_ns;
+        } while (!late);
+        // epochs drifted (v > epoch) or the peer ran another batch shape: its rows are not this pass's
+        if (!late && (v != epoch || __ldcg(f + 1) != shape)) late = true;
     }
-    __syncwarp();
+    if (__any_sync(0xffffffffu, late)) {  // give up on this scan: flagged in the result, ssf_batch_results -> SSF_ERR_COMM
+        if (lane == 0) {
+            z.comm_error = 1;
+            z.done = 1;
+        }
+        return;
+    }
     double tot = 0.0;
     for (int r = 0; r < x.world; ++r) tot += __ldcg(xch_rows(mine, x, par, r) + (size_t)blockIdx.x * kAccum + lane);
     sums[(size_t)blockIdx.x * kAccum + lane] = tot;
@@ -1160,8 +1244,9 @@ __global__ void __launch_bounds__(32)
     __syncwarp();
     if (lane != 0) return;
     float *hist = pose_hist + (size_t)blockIdx.x * kCertHist * 16;
-    if (o3d) o3d_solve(z, sv, pass, max_iteration, hist);
-    else gn_solve(z, sv, pass, acc_err, eps, hist);
+    float *trace = pass < trace_len ? trace_err + (size_t)blockIdx.x * trace_len : nullptr;
+    if (o3d) o3d_solve(z, sv, pass, max_iteration, hist, trace);
+    else gn_solve(z, sv, pass, acc_err, eps, hist, trace);
 }
 
 // per-scan totals of the partial rows and the solve.  Map sharding: the totals are summed across
@@ -1171,16 +1256,21 @@ static int reduce_and_solve(const IcpConfig &cfg, BatchBuffers &b, int pass, int
 {
     if (cfg.xch.world > 0) {  // in-kernel exchange over peer memory
         const unsigned long long epoch = cfg.xch_epoch + (unsigned long long)pass;
-        rowsum_xchg_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, cfg.xch, epoch);
+        const unsigned long long shape = ((unsigned long long)b.n_scans << 32) |
+                                         ((unsigned long long)(cfg.num_iterations & 0xFFFFF) << 8) |
+                                         (unsigned long long)(cfg.mode & 0xFF);
+        rowsum_xchg_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, cfg.xch, epoch, shape);
         SSF_LAUNCHED();
-        solve_xchg_kernel<<<(unsigned)b.n_scans, 32, 0, st>>>(b.state.p, cfg.xch, epoch, b.sums.p, pass, o3d, cfg.acc_err,
-                                                              cfg.eps, cfg.num_iterations, b.pose_hist.p);
+        solve_xchg_kernel<<<(unsigned)b.n_scans, 32, 0, st>>>(b.state.p, cfg.xch, epoch, shape, b.sums.p, pass, o3d,
+                                                              cfg.acc_err, cfg.eps, cfg.num_iterations, b.pose_hist.p,
+                                                              b.trace_err.p, b.trace_len);
         SSF_LAUNCHED();
         return SSF_OK;
     }
     if (!cfg.allreduce) {
         rowsum_solve_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, b.sums.p, pass, o3d,
-                                                                 cfg.acc_err, cfg.eps, cfg.num_iterations, b.pose_hist.p);
+                                                                 cfg.acc_err, cfg.eps, cfg.num_iterations, b.pose_hist.p,
+                                                              b.trace_err.p, b.trace_len);
         SSF_LAUNCHED();
         return SSF_OK;
     }
@@ -1191,7 +1281,7 @@ static int reduce_and_solve(const IcpConfig &cfg, BatchBuffers &b, int pass, int
         return SSF_ERR_COMM;
     }
     solve_kernel<<<(unsigned)b.n_scans, 32, 0, st>>>(b.state.p, b.sums.p, pass, o3d, cfg.acc_err, cfg.eps,
-                                                     cfg.num_iterations, b.pose_hist.p);
+                                                     cfg.num_iterations, b.pose_hist.p, b.trace_err.p, b.trace_len);
     SSF_LAUNCHED();
     return SSF_OK;
 }
@@ -1213,21 +1303,21 @@ static void launch_search(bool wide, unsigned grid, cudaStream_t st, const MapVi
     if (wide)
         search_accum_kernel<KIND, kWideThreads><<<grid, kWideThreads, 0, st>>>(map, b.src.p, b.tile_scan.p, b.state.p, limit, b.corr.p,
                                                                  b.partials.p, b.cert.p, b.pose_hist.p, use_cert, pass,
-                                                                 b.active.p, b.counters.p, fetch);
+                                                                 b.active.p, b.counters.p, fetch, b.search_stats.p + 2 * pass);
     else
         search_accum_kernel<KIND, kThreads><<<grid, kThreads, 0, st>>>(map, b.src.p, b.tile_scan.p, b.state.p, limit,
                                                                        b.corr.p, b.partials.p, b.cert.p, b.pose_hist.p,
-                                                                       use_cert, pass, b.active.p, b.counters.p, fetch);
+                                                                       use_cert, pass, b.active.p, b.counters.p, fetch,
+                                                                       b.search_stats.p + 2 * pass);
 }
 
 static int search_grid(const BatchBuffers &b, unsigned *grid, bool *wide)
 {
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        SSF_CUDA(cudaGetDevice(&dev));
-        SSF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    }
+    // queried per call: contexts on different devices share this code (a process-wide cache would
+    // pin the first device's count), and the attribute read costs well under a microsecond
+    int n_sm = 0, dev = 0;
+    SSF_CUDA(cudaGetDevice(&dev));
+    SSF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     // persistent blocks; sized by the batch CAPACITY so that the launch shape (and a captured graph)
     // does not change with the number of points of an upload -- surplus blocks fetch once and exit
     size_t g = (size_t)n_sm * 8u;
@@ -1247,6 +1337,10 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
     const float limit = cfg.max_corr;
     ScanState *S = b.state.p;
     if (tiles == 0) {
+        // no source point at all: the first search finds 0 (< 10) correspondences -- the reference's
+        // abort sentinel (cpp:196-200); the Open3D flow ends with nothing matched (rmse 0)
+        no_points_kernel<<<(scans + 127) / 128, 128, 0, st>>>(S, scans, cfg.mode);
+        SSF_LAUNCHED();
         results_kernel<<<(scans + 127) / 128, 128, 0, st>>>(S, b.results.p, scans, cfg.mode, cfg.acc_err);
         SSF_LAUNCHED();
         return SSF_OK;
@@ -1257,6 +1351,9 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
         // batch's H2D copy on a copy engine and stall the pipeline)
         zero_u32_kernel<<<(unsigned)((cfg.num_iterations + 3 + 255) / 256), 256, 0, st>>>(b.counters.p,
                                                                                           (uint32_t)cfg.num_iterations + 3);
+        SSF_LAUNCHED();
+        zero_u32_kernel<<<(unsigned)((4 * (cfg.num_iterations + 1) + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<uint32_t *>(b.search_stats.p), 4u * (uint32_t)(cfg.num_iterations + 1));
         SSF_LAUNCHED();
         active_tiles_kernel<<<(scans + 127) / 128, 128, 0, st>>>(S, scans, b.active.p, b.counters.p);
         SSF_LAUNCHED();
@@ -1284,11 +1381,8 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
                       "across ranks); use a GN or O3D mode");
             return SSF_ERR_STATE;
         }
-        static bool ref_attr_set = false;
-        if (!ref_attr_set) {
-            SSF_CUDA(cudaFuncSetAttribute(ref_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainBuf)));
-            ref_attr_set = true;
-        }
+        // function attributes are per device: set on every run (cheap) rather than once per process
+        SSF_CUDA(cudaFuncSetAttribute(ref_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainBuf)));
         TIMED_SEARCH((ref_search_kernel<<<tiles, kTile, 0, st>>>(map, b.src.p, b.P.p, b.Q.p, b.corr.p, b.tile_scan.p, S,
                                                                 limit, 1)));
         g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
@@ -1336,6 +1430,10 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
     if (cfg.mode != SSF_MODE_REFERENCE) {  // allocations happen here, never inside a capture
         SSF_TRY(b.active.reserve(b.max_tiles ? b.max_tiles : 1));
         SSF_TRY(b.counters.reserve((size_t)cfg.num_iterations + 3));
+        SSF_TRY(b.search_stats.reserve(2 * ((size_t)cfg.num_iterations + 1)));
+        b.search_stats_len = cfg.num_iterations + (cfg.mode == SSF_MODE_O3D_P2P ? 1 : 0);
+    } else {
+        b.search_stats_len = 0;
     }
     const char *ng = getenv("SSF_NO_GRAPH");
     const bool graphable = cfg.mode != SSF_MODE_REFERENCE && b.n_tiles > 0 && !cfg.allreduce && cfg.xch.world == 0 &&
@@ -1359,10 +1457,11 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
     put(&cfg.max_corr, sizeof(float)); put(&cfg.acc_err, sizeof(float)); put(&cfg.eps, sizeof(float));
     const unsigned long long scalars[] = {(unsigned long long)cfg.num_iterations, (unsigned long long)cfg.mode,
                                           (unsigned long long)certs, (unsigned long long)grid, (unsigned long long)b.n_scans,
-                                          (unsigned long long)wide};
+                                          (unsigned long long)wide, (unsigned long long)b.trace_len};
     put(scalars, sizeof(scalars));
     const void *ptrs[] = {b.src.p, b.corr.p, b.cert.p, b.pose_hist.p, b.tile_scan.p, b.active.p, b.counters.p,
-                          b.partials.p, b.sums.p, b.state.p, b.results.p, b.trace_err.p, b.trace_search.p, T_init};
+                          b.partials.p, b.sums.p, b.state.p, b.results.p, b.trace_err.p, b.trace_search.p, T_init,
+                          b.search_stats.p};
     put(ptrs, sizeof(ptrs));
     if (!b.graph_exec || key != b.graph_key) {
         if (b.graph_exec) {

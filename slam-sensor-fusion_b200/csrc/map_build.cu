@@ -225,7 +225,9 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
             SSF_TRY(index_pass(m, g, h, org, n_finite, s, st, cnt_dev, &n_cells));
             m.build_passes = pass + 1;
             const float rho = (float)n_finite / (float)(n_cells ? n_cells : 1);
-            if (rho <= 2.0f * target || ext_max == 0.f) break;
+            // h and g must stay the edge / grid the index was built with: only move on to a new
+            // edge when another index_pass follows
+            if (rho <= 2.0f * target || ext_max == 0.f || pass + 1 == 4) break;
             float h_new = h * sqrtf(target / rho);
             if (h_new < h / 16.f) h_new = h / 16.f;
             GridDims g2{};

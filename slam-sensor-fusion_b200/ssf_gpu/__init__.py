@@ -207,14 +207,14 @@ class ICPPointToPoint:
         capi.check(capi.lib().ssf_icp_set_allreduce(self._h, ctypes.cast(hook, ctypes.c_void_p), None))
 
     def exchangeCreate(self, rank: int, world: int, max_scans: int) -> bytes:
-        """This rank's exchange buffer for the in-kernel sum across map shards; returns its 64-byte
-        CUDA IPC handle (gather the handles of all ranks, then ``exchangeOpen``)."""
-        h = (ctypes.c_ubyte * 64)()
+        """This rank's exchange buffer for the in-kernel sum across map shards; returns its handle blob
+        (CUDA IPC handle + device identity; gather the blobs of all ranks, then ``exchangeOpen``)."""
+        h = (ctypes.c_ubyte * capi.XCH_HANDLE_BYTES)()
         capi.check(capi.lib().ssf_icp_exchange_create(self._h, int(rank), int(world), int(max_scans), h))
         return bytes(h)
 
     def exchangeOpen(self, handles) -> None:
-        """``handles``: the 64-byte handles of all ranks, in rank order."""
+        """``handles``: the handle blobs of all ranks, in rank order."""
         blob = b"".join(bytes(x) for x in handles)
         buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
         capi.check(capi.lib().ssf_icp_exchange_open(self._h, buf))
@@ -325,6 +325,15 @@ class Batch:
         res = (IcpResult * self.n_scans)()
         self.results_into(res)
         return [ICPResult.from_c(r) for r in res]
+
+    def search_stats(self):
+        """Per search launch of the last run: (queries answered, queries that needed a walk)."""
+        cap = 128
+        a, w = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+        n = ctypes.c_size_t(0)
+        capi.check(capi.lib().ssf_batch_search_stats(self._h, a.ctypes.data, w.ctypes.data, cap, ctypes.byref(n)))
+        k = min(cap, int(n.value))
+        return a[:k].copy(), w[:k].copy()
 
     def close(self) -> None:
         if getattr(self, "_h", None):

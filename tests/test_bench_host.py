@@ -28,8 +28,8 @@ def test_footprint_matches_the_definition():
     m = np.c_[rng.uniform(-30, 30, (20000, 2)), rng.normal(0, 0.05, 20000)].astype(np.float32)
     q = np.c_[rng.uniform(-5, 8, (500, 2)), rng.normal(0.2, 0.3, 500)].astype(np.float32)
     cell = 0.7142
-    got, n_pts, n_cells = bench.nn_footprint_bytes(np.c_[m, np.ones(len(m), np.float32)], q, cell)
-    assert got == _footprint_reference(m, q, cell)
+    n_pts, n_cells = bench.nn_footprint_bytes(np.c_[m, np.ones(len(m), np.float32)], q, cell)
+    assert 20 * len(q) + 16 * n_pts + 8 * n_cells == _footprint_reference(m, q, cell)
     assert 0 < n_pts < len(m) and n_cells > 0
 
 
@@ -48,3 +48,22 @@ def test_traffic_record_matches_the_bench_workload():
     t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     assert t["workload"] == "c2" and t["scans_per_step"] == bench.WORKLOADS["c2"]["scans_per_step"]
     assert 1e6 < t["dram_bytes_per_launch"] < 1e9 and os.path.exists(os.path.join(ROOT, t["source"].split(":")[0]))
+
+
+def test_both_arms_print_the_same_config():
+    """The driver compares `config` of the two arms: nothing arm-specific (sample sizes, L2 notes) may sit in it."""
+    import argparse
+    a = argparse.Namespace(workload="c2", scans_per_step=256, gpus=1, exchange="peer")
+    c = bench.config_of(a, bench.WORKLOADS["c2"])
+    assert set(c) == {"workload", "scans_per_step", "map_points", "scan_rays", "voxel_leaf", "mode",
+                      "max_correspondence_dist", "iterations", "parallelism"}
+    assert c == bench.config_of(a, bench.WORKLOADS["c2"])
+
+
+def test_distinct_scans_per_step():
+    w, xyz, nrm, half, scans, inits, gts = bench.make_workload("mini", 12, 0)
+    assert len(scans) == 12
+    poses = {tuple(np.round(T[:3, 3], 3)) for T in gts}
+    assert len(poses) == 12          # every scan of a step comes from its own pose
+    w2, *_rest, gts2 = bench.make_workload("mini", 12, 1)
+    assert {tuple(np.round(T[:3, 3], 3)) for T in gts2} != poses   # and every rank from its own stretch
