@@ -415,6 +415,8 @@ def run_gpu(args, rank, world, local_rank):
         icp.setTargetShard(sh)
         if args.exchange == "peer":
             shard.setup_peer_exchange(icp, rank, world, max_scans=B)
+        elif args.exchange == "nccl":
+            shard.setup_nccl(icp, rank, world)
         else:
             icp.setAllreduce(shard.torch_allreduce_hook(local_rank))
         log(f"[bench r{rank}] shard {sh['points'].shape[0]} of {xyz.shape[0]} pts, columns {sh['own']}")
@@ -693,9 +695,9 @@ def c1_latency(ssf_gpu, ctx):
 
 def run_map_sharded(args, ssf_gpu, capi, torch, dist, ctx, rank, world, local_rank):
     """BASELINE.json configs[2] in the same run: the 50M-point map split into `world` column shards (one-cell
-    halo), the same scans on every rank, one exchange of 32 doubles per scan per iteration.  Strong scaling:
-    reported next to the same scans against the unsharded map on one GPU would need 1.6 GB of map per rank,
-    which fits -- so rank 0 also measures that (`one_gpu_value`) as the denominator."""
+    halo), the same scans on every rank, one sum of 32 doubles per scan per iteration -- through the in-kernel
+    exchange over peer memory (`value`) and through ncclAllReduce behind the C ABI (`nccl`).  Strong scaling:
+    rank 0 also registers the same scans against the WHOLE map on one GPU (`one_gpu_value`), the denominator."""
     from ssf_gpu import shard
     name = "c3"
     w = WORKLOADS[name]
@@ -705,61 +707,72 @@ def run_map_sharded(args, ssf_gpu, capi, torch, dist, ctx, rank, world, local_ra
     t0 = time.time()
     sh = shard.shard_map(xyz, nrm, rank, world, THR)
     icp.setTargetShard(sh)
-    if args.exchange == "peer":
-        shard.setup_peer_exchange(icp, rank, world, max_scans=B)
-    else:
-        icp.setAllreduce(shard.torch_allreduce_hook(local_rank))
     build_s = time.time() - t0
     n_pts = [s.shape[0] for s in scans]
     total = int(sum(n_pts))
     cat = np.ascontiguousarray(np.concatenate([s[:, :3] for s in scans], axis=0))
     T0 = np.ascontiguousarray(np.stack([np.asarray(T, np.float32).T.reshape(16) for T in inits]))
     res = (capi.IcpResult * B)()
-    batch = ssf_gpu.Batch(icp, B, total + 1)
-    batch.upload_ptr(cat.ctypes.data, n_pts, 12)
-    batch.set_initial_ptr(T0.ctypes.data)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    steps = max(5, min(args.steps, 30))
 
     def sync():
         ctx.synchronize()
         torch.cuda.synchronize()
         dist.barrier()
 
-    def timed(n):
-        sync()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(n):
-            batch.run()
-        e1.record(stream)
-        ctx.synchronize()
-        e1.synchronize()
-        return e0.elapsed_time(e1)
+    def measure(batch):
+        def timed(n):
+            sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(n):
+                batch.run()
+            e1.record(stream)
+            ctx.synchronize()
+            e1.synchronize()
+            return e0.elapsed_time(e1)
 
-    for _ in range(3):
+        for _ in range(3):
+            batch.run()
+        ms = timed(steps)
+        batch.results_into(res)
+        errs = [pose_delta(ssf_gpu._rowmajor(r.transformation), T)[0] for r, T in zip(res, gts)]
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.cpu()[0])
+        # what an iteration spends outside the search kernel (row sum + exchange + solve + tile list): the
+        # step with every search bracketed by events (plain launches), minus the searches
+        ctx.time_searches(True)
         batch.run()
-    steps = max(5, min(args.steps, 30))
-    ms = timed(steps)
-    batch.results_into(res)
-    errs = [pose_delta(ssf_gpu._rowmajor(r.transformation), T)[0] for r, T in zip(res, gts)]
-    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.cpu()[0])
-    # the exchange alone: the same alignment with the per-scan work taken out is not available, so time the
-    # step with searches bracketed and subtract: (step - searches) / iterations = row-sum + exchange + solve
-    ctx.time_searches(True)
-    batch.run()
-    ctx.search_time()
-    ms_ev = timed(3)
-    s_ms, s_n = ctx.search_time()
-    ctx.time_searches(False)
-    sync()
-    out = {"workload": f"c3: {w['desc']}", "n_ranks": world, "scans_per_step": B, "exchange": args.exchange,
-           "value": B * steps / (ms_max * 1e-3), "unit": "scans/s", "ms_per_step": ms_max / steps,
-           "exchange_us_per_iter": 1e3 * (ms_ev - s_ms) / 3 / ITERS, "search_us_per_iter": 1e3 * s_ms / max(1, s_n),
-           "shard_points_rank0": int(sh["points"].shape[0]), "map_points": int(xyz.shape[0]),
-           "shard_build_s_rank0": build_s, "median_pose_error_m": float(np.median(errs))}
-    batch.close()
+        ctx.search_time()
+        ms_ev = timed(3)
+        s_ms, s_n = ctx.search_time()
+        ctx.time_searches(False)
+        sync()
+        return {"value": B * steps / (ms_max * 1e-3), "unit": "scans/s", "ms_per_step": ms_max / steps,
+                "exchange_us_per_iter": 1e3 * (ms_ev - s_ms) / 3 / ITERS, "search_us_per_iter": 1e3 * s_ms / max(1, s_n),
+                "median_pose_error_m": float(np.median(errs))}
+
+    out = {"workload": f"c3: {w['desc']}", "n_ranks": world, "scans_per_step": B,
+           "shard_points_rank0": int(sh["points"].shape[0]), "map_points": int(xyz.shape[0]), "shard_build_s_rank0": build_s}
+    for ex in ("peer", "nccl"):
+        batch = ssf_gpu.Batch(icp, B, total + 1)
+        batch.upload_ptr(cat.ctypes.data, n_pts, 12)
+        batch.set_initial_ptr(T0.ctypes.data)
+        if ex == "peer":
+            shard.setup_peer_exchange(icp, rank, world, max_scans=B)
+        else:
+            shard.setup_nccl(icp, rank, world)
+        m = measure(batch)
+        batch.close()
+        if ex == "peer":
+            icp.exchangeClose()
+            out.update(m)
+            out["exchange"] = "in-kernel over peer memory (rowsum_xchg_solve_kernel)"
+        else:
+            icp.ncclClose()
+            out["nccl"] = m
     icp.close()
     if rank == 0:  # the denominator: the same scans against the whole map on one GPU
         one = ssf_gpu.ICPPointToPoint(THR, ITERS, 0.0, 0.0, mode=ssf_gpu.MODE_GN_P2PLANE, context=ctx)
@@ -779,6 +792,7 @@ def run_map_sharded(args, ssf_gpu, capi, torch, dist, ctx, rank, world, local_ra
         e1.synchronize()
         out["one_gpu_value"] = B * steps / (e0.elapsed_time(e1) * 1e-3)
         out["speedup_vs_one_gpu"] = out["value"] / out["one_gpu_value"]
+        out["nccl"]["speedup_vs_one_gpu"] = out["nccl"]["value"] / out["one_gpu_value"]
         b1.close()
         one.close()
     dist.barrier()
@@ -797,8 +811,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the config-1 single-scan latency block")
     ap.add_argument("--no-map-sharded", action="store_true", help="N > 1: skip the map-sharded (c3) block")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="map-sharded workloads: in-kernel exchange over peer memory (default) or the NCCL all-reduce hook")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl", "hook"],
+                    help="map-sharded workloads: in-kernel exchange over peer memory (default), ncclAllReduce behind the "
+                         "C ABI, or the caller's all-reduce hook (torch.distributed)")
     args = ap.parse_args()
     if args.scans_per_step <= 0:
         args.scans_per_step = WORKLOADS[args.workload].get("scans_per_step", 64)

@@ -231,13 +231,21 @@ int ssf_icp_set_target_shard(ssf_icp *icp, const float *xyz, size_t n, size_t st
  * Return 0 on success.  (bench.py passes torch.distributed.all_reduce over NCCL.) */
 typedef int (*ssf_allreduce_fn)(void *user, double *buf, size_t count, void *cuda_stream);
 int ssf_icp_set_allreduce(ssf_icp *icp, ssf_allreduce_fn fn, void *user);
+/* The same sum through NCCL, with no callback: ncclAllReduce (n_scans x 32 doubles) on the library's own
+ * stream, inside the CUDA graph of the loop.  libnccl.so.2 is bound at run time.  Rank 0 calls
+ * ssf_nccl_unique_id, the caller carries the 128 bytes to every rank (any transport), and every rank
+ * calls ssf_icp_nccl_init -- collectively, like ncclCommInitRank.  Takes precedence over the hook. */
+#define SSF_NCCL_ID_BYTES 128
+int ssf_nccl_unique_id(unsigned char id_out[SSF_NCCL_ID_BYTES]);
+int ssf_icp_nccl_init(ssf_icp *icp, const unsigned char id[SSF_NCCL_ID_BYTES], int rank, int world);
+int ssf_icp_nccl_close(ssf_icp *icp);
 /* In-kernel exchange instead of the hook (one process per GPU, all on one NVLink box): every rank
  * creates its exchange buffer and gets a handle blob (CUDA IPC handle + identity), the caller gathers the blobs of
  * all ranks (any transport: torch.distributed, MPI, a file) and hands the rank-ordered array
- * (world x SSF_XCH_HANDLE_BYTES) to ssf_icp_exchange_open.  From then on the row-sum kernel stores this rank's
- * per-scan rows straight into every rank's buffer (peer stores over NVLink) and the solve kernel
- * waits for all ranks' epoch flags and adds the rows in rank order -- no host call and no NCCL
- * collective per iteration.  All ranks must run the same sequence of alignments with the same
+ * (world x SSF_XCH_HANDLE_BYTES) to ssf_icp_exchange_open.  From then on ONE kernel per iteration sums a scan's partial rows, stores the row
+ * straight into every rank's buffer (peer stores over NVLink, per-scan release flag), waits for the same
+ * scan's rows of the other ranks, adds them in rank order and solves -- no host call and no NCCL
+ * collective per iteration; the loop stays one CUDA graph.  All ranks must run the same sequence of alignments with the same
  * scans; max_scans bounds the scans per batch.  world <= 32. */
 #define SSF_XCH_HANDLE_BYTES 128 /* CUDA IPC handle + device UUID + (max_scans, world, rank) */
 int ssf_icp_exchange_create(ssf_icp *icp, int rank, int world, size_t max_scans,

@@ -13,6 +13,7 @@
 #include "bfa.cuh"
 #include "icp.cuh"
 #include "map_index.cuh"
+#include "nccl_link.cuh"
 #include "preprocess.cuh"
 #include "voxel_grid.cuh"
 
@@ -85,10 +86,10 @@ struct ssf_icp {
         std::vector<void *> peers;         // every rank's buffer as seen from this device
         std::vector<bool> opened;          // peers[r] came from cudaIpcOpenMemHandle
         DevBuf<void *> peers_dev;
-        DevBuf<uint32_t> counter;
-        unsigned long long epoch = 1;      // next epoch to use (flags start at 0)
+        DevBuf<unsigned long long> epoch_dev;  // epoch of the next run's first pass (flags start at 0); advanced on the device
         bool ready = false;
     } xch;
+    NcclLink *nccl = nullptr;  // map sharding through ncclAllReduce (nccl_link.cu)
     DevBuf<float4> q_dev;  // ssf_nn_search temporaries
     DevBuf<int32_t> q_idx;
     DevBuf<float> q_d2;
@@ -292,6 +293,7 @@ extern "C" void ssf_icp_destroy(ssf_icp *icp)
     cudaStreamSynchronize(icp->ctx->stream);
     if (icp->single) ssf_batch_destroy(icp->single);
     exchange_release(icp);
+    nccl_link_destroy(icp->nccl);
     delete icp;
 }
 
@@ -406,11 +408,12 @@ extern "C" int ssf_icp_exchange_create(ssf_icp *icp, int rank, int world, size_t
     x.rank = rank;
     x.world = world;
     x.max_scans = max_scans;
-    x.bytes = (size_t)2 * world * max_scans * kAccum * sizeof(double) + (size_t)4 * world * sizeof(unsigned long long);
+    x.bytes = (size_t)2 * world * max_scans * kAccum * sizeof(double) + (size_t)4 * world * max_scans * sizeof(unsigned long long);
     SSF_CUDA(cudaMalloc(&x.local, x.bytes));
     SSF_CUDA(cudaMemset(x.local, 0, x.bytes));
-    SSF_TRY(x.counter.reserve(1));
-    SSF_CUDA(cudaMemset(x.counter.p, 0, sizeof(uint32_t)));
+    SSF_TRY(x.epoch_dev.reserve(1));
+    const unsigned long long one = 1;
+    SSF_CUDA(cudaMemcpy(x.epoch_dev.p, &one, sizeof(one), cudaMemcpyHostToDevice));
     SSF_CUDA(cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     SSF_CUDA(cudaIpcGetMemHandle(&h, x.local));
@@ -425,7 +428,6 @@ extern "C" int ssf_icp_exchange_create(ssf_icp *icp, int rank, int world, size_t
     memcpy(handle_out + 80, &ms64, 8);
     memcpy(handle_out + 88, &w32, 4);
     memcpy(handle_out + 92, &r32, 4);
-    x.epoch = 1;
     return SSF_OK;
 }
 
@@ -488,6 +490,32 @@ extern "C" int ssf_icp_exchange_close(ssf_icp *icp)
     SSF_TRY(use_device(icp->ctx));
     cudaStreamSynchronize(icp->ctx->stream);
     exchange_release(icp);
+    return SSF_OK;
+}
+
+extern "C" int ssf_nccl_unique_id(unsigned char id_out[SSF_NCCL_ID_BYTES])
+{
+    SSF_ARG(id_out, "ssf_nccl_unique_id: NULL argument");
+    return nccl_link_unique_id(id_out);
+}
+
+extern "C" int ssf_icp_nccl_init(ssf_icp *icp, const unsigned char id[SSF_NCCL_ID_BYTES], int rank, int world)
+{
+    SSF_ARG(icp && id, "ssf_icp_nccl_init: NULL argument");
+    SSF_ARG(world >= 1 && rank >= 0 && rank < world, "ssf_icp_nccl_init: bad rank / world");
+    SSF_TRY(use_device(icp->ctx));
+    nccl_link_destroy(icp->nccl);
+    icp->nccl = nullptr;
+    return nccl_link_create(id, rank, world, &icp->nccl);
+}
+
+extern "C" int ssf_icp_nccl_close(ssf_icp *icp)
+{
+    SSF_ARG(icp, "ssf_icp_nccl_close: icp == NULL");
+    SSF_TRY(use_device(icp->ctx));
+    cudaStreamSynchronize(icp->ctx->stream);
+    nccl_link_destroy(icp->nccl);
+    icp->nccl = nullptr;
     return SSF_OK;
 }
 
@@ -1006,9 +1034,10 @@ extern "C" int ssf_batch_run(ssf_batch *b)
             cfg.xch.rank = icp->xch.rank;
             cfg.xch.world = icp->xch.world;
             cfg.xch.max_scans = (uint32_t)icp->xch.max_scans;
-            cfg.xch.counter = icp->xch.counter.p;
-            cfg.xch_epoch = icp->xch.epoch;
-            icp->xch.epoch += (unsigned long long)p.num_iterations + 2;  // one epoch per pass (O3D runs one more)
+            cfg.xch.epoch = icp->xch.epoch_dev.p;
+        } else if (icp->nccl) {
+            cfg.nccl_allreduce = nccl_link_allreduce;
+            cfg.nccl_user = icp->nccl;
         }
     }
     SSF_TRY(ensure_reach_mask(icp->map, cfg.max_corr, ctx->stream));

@@ -41,7 +41,9 @@ struct BatchBuffers {
     DevBuf<float> pose_hist;   // [scan][kCertHist][16]: pose used by search launch i (certificates refer to it)
     DevBuf<uint32_t> tile_scan;
     DevBuf<uint4> active;        // tiles that hold points (search kernel work list): (tile, scan, first slot, points)
-    DevBuf<uint32_t> counters;   // [0] number of active tiles, [1 + i] tile fetch counter of search launch i
+    DevBuf<uint32_t> counters;   // [0 .. P]: tiles listed for search launch i (unsharded: [0] serves every launch),
+                                 // [P + 1 .. 2P + 1]: tile fetch counter of launch i; P = num_iterations + 1
+    DevBuf<float4> tile_box;     // map sharding: bounding box of every tile's source points (ShardView)
     DevBuf<unsigned long long> search_stats;  // per search launch: (queries answered, queries walked)
     int search_stats_len = 0;
     DevBuf<double> partials;   // [tile][kAccum]
@@ -94,9 +96,20 @@ struct XchView {
     void *const *peers = nullptr;  // device array [world] of buffer base pointers (own entry included)
     int rank = 0, world = 0;
     uint32_t max_scans = 0;
-    uint32_t *counter = nullptr;   // blocks of the row-sum kernel that have stored their row
+    unsigned long long *epoch = nullptr;  // device: epoch of the current run's first pass (advanced by the run itself)
     unsigned long long timeout_ns = 20000000000ull;  // give up waiting for a peer's rows after this long
 };
+
+// Map sharding: ownership test of whole tiles (icp_kernels.cu, tile_may_own).  enabled == 0: every tile is listed.
+struct ShardView {
+    int enabled = 0;
+    float ox = 0.f, inv_h = 1.f;
+    int own_lo = 0, own_hi = 0;
+    const float4 *tile_box = nullptr;  // [2 * tile]: min / max corner of the tile's source points, sensor frame
+};
+
+// all-reduce behind the C ABI (NCCL, loaded at run time: nccl_link.cu): sum `count` doubles in place on `stream`
+typedef int (*NcclAllreduceFn)(void *user, double *buf, size_t count, cudaStream_t stream);
 
 struct IcpConfig {
     float max_corr;
@@ -108,7 +121,8 @@ struct IcpConfig {
     AllreduceFn allreduce = nullptr;
     void *allreduce_user = nullptr;
     XchView xch;                      // world > 0: exchange in-kernel instead of through the hook
-    unsigned long long xch_epoch = 0; // epoch of the first exchange of this run
+    NcclAllreduceFn nccl_allreduce = nullptr;  // ncclAllReduce on the library's stream (graph-capturable)
+    void *nccl_user = nullptr;
 };
 
 // Enqueue the whole alignment of every scan in the batch on `st` (no host sync inside).

@@ -172,21 +172,105 @@ __global__ void zero_u32_kernel(uint32_t *p, uint32_t n)
     if (i < n) p[i] = 0;
 }
 
-// list of the tiles that hold points (a scan's slots are sized for its RAW points; after the voxel
-// stage only the first ceil(n_pts / kTile) tiles of each scan are in use).  One 16-byte record per
-// tile -- (tile, scan, first slot, points) -- so the search kernel reaches its data in one hop.
+// ---- map sharding: which tiles can hold a query this rank owns ------------------------------------
+// A rank owns the queries whose shard column floor((x' - ox) * inv_h) lies in [own_lo, own_hi), x' being
+// the x coordinate of the TRANSFORMED source point.  tile_box holds the bounding box of every tile's
+// source points in the sensor frame; moved by the scan's current pose it gives an interval of x' that
+// contains every query of the tile (interval arithmetic, widened by the rounding of the per-point
+// transform), hence a column interval (cell_coord is monotone).  A tile whose interval misses the
+// rank's columns is left out of the search kernel's work list: nothing is loaded or transformed for it.
+__device__ __forceinline__ bool tile_may_own(const ShardView &sv, const float *T, uint32_t tile)
+{
+    if (!sv.enabled) return true;
+    const float4 lo = sv.tile_box[2 * (size_t)tile], hi = sv.tile_box[2 * (size_t)tile + 1];
+    const float c[3] = {T[0], T[4], T[8]}, l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
+    float xmin = T[12], xmax = T[12], mag = fabsf(T[12]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float a = c[k] * l[k], b = c[k] * h[k];
+        xmin += fminf(a, b);
+        xmax += fmaxf(a, b);
+        mag += fmaxf(fabsf(a), fabsf(b));
+    }
+    if (!(mag < 3.0e38f)) return true;  // non-finite points in the tile (their rows are answered by the first rank)
+    const float slack = 4e-6f * mag + 1e-5f;
+    const int clo = cell_coord(xmin - slack, sv.ox, sv.inv_h, 1 << 24), chi = cell_coord(xmax + slack, sv.ox, sv.inv_h, 1 << 24);
+    return chi >= sv.own_lo && clo < sv.own_hi;
+}
+
+// bounding box of every tile's source points (sensor frame); a tile with a non-finite point gets an
+// infinite box.  One 128-thread block per tile.
 __global__ void __launch_bounds__(128)
-    active_tiles_kernel(const ScanState *__restrict__ states, uint32_t n_scans, uint4 *__restrict__ active,
+    tile_box_kernel(const float4 *__restrict__ src, const uint32_t *__restrict__ tile_scan,
+                    const ScanState *__restrict__ states, float4 *__restrict__ tile_box)
+{
+    __shared__ float smin[4][3], smax[4][3];
+    const uint32_t tile = blockIdx.x;
+    const ScanState &z = states[tile_scan[tile]];
+    const uint32_t k = tile - z.tile_begin;
+    if ((size_t)k * kTile >= z.n_pts) return;
+    const uint32_t n_here = min((uint32_t)kTile, z.n_pts - k * kTile);
+    const float4 *p = src + (size_t)z.pt_begin + (size_t)k * kTile;
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    bool bad = false;
+    for (uint32_t i = threadIdx.x; i < n_here; i += 128) {
+        const float4 q = p[i];
+        bad |= !(isfinite(q.x) && isfinite(q.y) && isfinite(q.z));
+        mn[0] = fminf(mn[0], q.x); mn[1] = fminf(mn[1], q.y); mn[2] = fminf(mn[2], q.z);
+        mx[0] = fmaxf(mx[0], q.x); mx[1] = fmaxf(mx[1], q.y); mx[2] = fmaxf(mx[2], q.z);
+    }
+    bad = __syncthreads_or(bad);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], d));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], d));
+        }
+    if ((threadIdx.x & 31) == 0)
+        for (int c = 0; c < 3; ++c) { smin[threadIdx.x >> 5][c] = mn[c]; smax[threadIdx.x >> 5][c] = mx[c]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float inf = __int_as_float(0x7f800000);
+        for (int c = 0; c < 3; ++c) {
+            mn[c] = fminf(fminf(smin[0][c], smin[1][c]), fminf(smin[2][c], smin[3][c]));
+            mx[c] = fmaxf(fmaxf(smax[0][c], smax[1][c]), fmaxf(smax[2][c], smax[3][c]));
+            if (bad) { mn[c] = -inf; mx[c] = inf; }
+        }
+        tile_box[2 * (size_t)tile] = make_float4(mn[0], mn[1], mn[2], 0.f);
+        tile_box[2 * (size_t)tile + 1] = make_float4(mx[0], mx[1], mx[2], 0.f);
+    }
+}
+
+// The work list of a search launch: one 16-byte record per tile in use -- (tile, scan, first slot,
+// points) -- so the search kernel reaches its data in one hop.  A scan's slots are sized for its RAW
+// points; after the voxel stage only the first ceil(n_pts / kTile) tiles are in use.  Called by one
+// warp per scan; sharded maps list only the tiles that can hold an owned query at pose T.
+__device__ __forceinline__ void list_scan_tiles(const ScanState &z, uint32_t scan, const float *T, const ShardView &sv,
+                                                uint4 *__restrict__ active, uint32_t *__restrict__ n_active)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n = (z.n_pts + kTile - 1) / kTile;
+    for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        const bool on = k < n && tile_may_own(sv, T, z.tile_begin + k);
+        const uint32_t bal = __ballot_sync(0xffffffffu, on);
+        uint32_t base = 0;
+        if (lane == 0 && bal) base = atomicAdd(n_active, (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (on)
+            active[base + __popc(bal & ((1u << lane) - 1u))] =
+                make_uint4(z.tile_begin + k, scan, z.pt_begin + k * kTile, min((uint32_t)kTile, z.n_pts - k * kTile));
+    }
+}
+
+__global__ void __launch_bounds__(128)
+    active_tiles_kernel(const ScanState *__restrict__ states, uint32_t n_scans, ShardView sv, uint4 *__restrict__ active,
                         uint32_t *__restrict__ n_active)
 {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per scan
     if (s >= n_scans) return;
-    const ScanState &z = states[s];
-    const uint32_t n = (z.n_pts + kTile - 1) / kTile;
-    if (n == 0) return;
-    const uint32_t base = atomicAdd(n_active, n);
-    for (uint32_t k = 0; k < n; ++k)
-        active[base + k] = make_uint4(z.tile_begin + k, s, z.pt_begin + k * kTile, min((uint32_t)kTile, z.n_pts - k * kTile));
+    list_scan_tiles(states[s], s, states[s].T, sv, active, n_active);
 }
 
 // One half (values 16*HALF .. 16*HALF+15 of the partial row) of the Gauss-Newton sums over this
@@ -366,7 +450,6 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
     float *const s_b2 = reinterpret_cast<float *>(s_raw + kTile * 8);
     uint32_t *const s_skip = reinterpret_cast<uint32_t *>(s_raw + kTile * 12);
     __shared__ uint32_t s_nq, s_nfar, s_nfar_none, s_next;
-    __shared__ uint32_t sred_u[THREADS / 32];
     __shared__ float sT[16];
     constexpr int kQ_ = kTile / THREADS;  // queries per thread
     __shared__ double sred[THREADS / 32][kAccum];
@@ -454,53 +537,16 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
             s_queue[atomicAdd(&s_nq, 1u)] = (unsigned short)r;
         }
         __syncthreads();
-        // First search of an alignment (no previous neighbour to start from): the queries of a tile are
-        // in voxel order, i.e. consecutive ones are neighbours in space, so the queue is put back into
-        // source order and every thread walks kQ_ CONSECUTIVE queries, handing the neighbour it found
-        // to the next one as its seed.  A seed only tightens the bound a walk starts with -- the
-        // result is that of the unseeded walk -- but the walk then prunes from the first row on.
         // search statistics of this launch: [0] queries answered, [1] queries that needed a walk
         if (threadIdx.x == 0) {
             atomicAdd(&stats[0], (unsigned long long)n_here);
             atomicAdd(&stats[1], (unsigned long long)s_nq);
         }
-        const bool chain = !use_cert && kQ_ > 1;
-        if (chain) {
-            // s_queue holds an arbitrary order of the walkable rows; s_far (free until the walks) gets
-            // a presence flag per row, then the queue is rebuilt in row order
-            for (uint32_t r = threadIdx.x; r < kTile; r += THREADS) s_far[r] = 0;
-            __syncthreads();
-            for (uint32_t i = threadIdx.x; i < s_nq; i += THREADS) s_far[s_queue[i]] = 1;
-            __syncthreads();
-            // ballot-scan compaction in row order (one pass of kTile / THREADS rounds)
-            uint32_t base = 0;
-            for (uint32_t r0 = 0; r0 < kTile; r0 += THREADS) {
-                const uint32_t r = r0 + threadIdx.x;
-                const bool on = s_far[r] != 0;
-                const uint32_t bal = __ballot_sync(0xffffffffu, on);
-                const uint32_t wpre = __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
-                if ((threadIdx.x & 31) == 0) sred_u[threadIdx.x >> 5] = __popc(bal);
-                __syncthreads();
-                uint32_t off = base;
-                for (uint32_t wv = 0; wv < (threadIdx.x >> 5); ++wv) off += sred_u[wv];
-                uint32_t tot = 0;
-                for (uint32_t wv = 0; wv < THREADS / 32; ++wv) tot += sred_u[wv];
-                if (on) s_queue[off + wpre] = (unsigned short)r;
-                base += tot;
-                __syncthreads();
-            }
-        }
         // ---- S: near part of the walk for every queued query; the few that must go on to rings 2..
         // are queued again and finished afterwards, packed densely, so that a warp is not held up
         // by the lanes that drew a far query ----
         const uint32_t nq = s_nq;
-        // chain: thread t takes queue items kQ_ t .. kQ_ t + kQ_ - 1 (consecutive rows); otherwise item
-        // t, t + THREADS, ... (dense packing of the few unconfirmed queries of a certificate launch)
-        const uint32_t i_first = chain ? threadIdx.x * kQ_ : threadIdx.x;
-        const uint32_t i_step = chain ? 1u : (uint32_t)THREADS;
-        const uint32_t i_end = chain ? min(nq, i_first + kQ_) : nq;
-        uint32_t carry = kNoPos;  // chain: the neighbour found for the previous row
-        for (uint32_t i = i_first; i < i_end; i += i_step) {
+        for (uint32_t i = threadIdx.x; i < nq; i += THREADS) {
             const uint32_t r = s_queue[i];
             SSF_CHECK(r < n_here);
             const float4 p = s_q[r];
@@ -508,18 +554,15 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
             uint32_t pos;
             float b2 = 0.f;
             bool far;
-            const uint32_t seed = chain ? carry : s_pos[r];
-            if (chain) s_pos[r] = seed;
             if (make_cert) {
                 NNBest<true> B;
-                far = nn_walk_near<true>(map, p.x, p.y, p.z, limit, map.cert_mu, B, seed);
+                far = nn_walk_near<true>(map, p.x, p.y, p.z, limit, map.cert_mu, B, s_pos[r]);
                 key = B.key; pos = B.pos; b2 = B.b2;
             } else {
                 NNBest<false> B;
-                far = nn_walk_near<false>(map, p.x, p.y, p.z, limit, 0.f, B, seed);
+                far = nn_walk_near<false>(map, p.x, p.y, p.z, limit, 0.f, B, s_pos[r]);
                 key = B.key; pos = B.pos;
             }
-            carry = (uint32_t)(key >> 32) < none_hi ? pos : kNoPos;
             if (far) s_skip[r] = s_pos[r];  // (read before s_pos is overwritten)
             s_key[r] = key;
             s_pos[r] = pos;
@@ -620,33 +663,47 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
             double sum = 0.0;
 #pragma unroll
             for (int k = 0; k < THREADS / 32; ++k) sum += sred[k][threadIdx.x];
-            partials[(size_t)tile * kAccum + threadIdx.x] = sum;
+            // slot 31 (unused by every mode) carries the pass that wrote the row: a tile left out of a
+            // sharded rank's work list keeps an older stamp and is not added (scan_rowsum)
+            partials[(size_t)tile * kAccum + threadIdx.x] = threadIdx.x == kAccum - 1 ? (double)(pass + 1) : sum;
         }
         // (the barrier at the top of the loop orders these reads before the next tile's writes)
     }
 }
 
-// ordered sum of the partial rows of one scan -> sums[scan][kAccum].  8 warps take interleaved
-// rows, then the 8 partial totals are added in warp order: fixed order, deterministic.
-__global__ void __launch_bounds__(256) rowsum_kernel(const ScanState *__restrict__ states,
-                                                     const double *__restrict__ partials, double *__restrict__ sums)
+// ordered sum of the partial rows of one scan (rows stamped with this pass only).  8 warps take interleaved
+// rows, then the 8 partial totals are added in warp order: fixed order, deterministic.  Returns the total of
+// value `lane` in warp 0 (other warps: undefined).  256 threads.
+__device__ __forceinline__ double scan_rowsum(const ScanState &z, const double *__restrict__ partials, int pass,
+                                              double (*sw)[kAccum])
 {
-    __shared__ double sw[8][kAccum];
-    const ScanState &z = states[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double s = 0.0;
     if (!z.done) {
         const uint32_t n_tiles = (z.n_pts + kTile - 1) / kTile;
-        for (uint32_t t = warp; t < n_tiles; t += 8) s += partials[(size_t)(z.tile_begin + t) * kAccum + lane];
+        const double stamp = (double)(pass + 1);
+        for (uint32_t t = warp; t < n_tiles; t += 8) {
+            const double v = partials[(size_t)(z.tile_begin + t) * kAccum + lane];
+            if (__shfl_sync(0xffffffffu, v, kAccum - 1) == stamp) s += v;
+        }
     }
     sw[warp][lane] = s;
     __syncthreads();
+    double tot = 0.0;
     if (warp == 0) {
-        double tot = 0.0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) tot += sw[w][lane];
-        sums[(size_t)blockIdx.x * kAccum + lane] = tot;
     }
+    return tot;
+}
+
+__global__ void __launch_bounds__(256) rowsum_kernel(const ScanState *__restrict__ states,
+                                                     const double *__restrict__ partials, double *__restrict__ sums,
+                                                     int pass)
+{
+    __shared__ double sw[8][kAccum];
+    const double tot = scan_rowsum(states[blockIdx.x], partials, pass, sw);
+    if (threadIdx.x < 32) sums[(size_t)blockIdx.x * kAccum + threadIdx.x] = tot;
 }
 
 // one thread: normal equations -> Cholesky -> pose update -> stop rules (sv = the scan's kAccum totals)
@@ -732,51 +789,59 @@ __device__ void o3d_solve(ScanState &z, const double *sv, int pass, int max_iter
     z.iterations += 1;
 }
 
-// the sums arrive from outside (map sharding: all-reduced across ranks)
-__global__ void __launch_bounds__(32) solve_kernel(ScanState *states, const double *__restrict__ sums, int pass,
-                                                   int o3d, float acc_err, float eps, int max_iteration,
-                                                   float *pose_hist, float *trace_err, int trace_len)
+// what the solve step needs besides the sums
+struct SolveArgs {
+    int pass, o3d;
+    float acc_err, eps;
+    int max_iteration;
+    float *pose_hist;
+    float *trace_err;
+    int trace_len;
+    ShardView shard;              // sharded maps: rebuild the scan's tile list for the next pass at the new pose
+    uint4 *active;
+    uint32_t *n_active_next;
+};
+
+// warp 0 of a scan's block: sv[] holds the scan's totals; lane 0 solves, then the warp lists the tiles
+// of the next search launch (sharded maps only: the owned columns move with the pose)
+__device__ __forceinline__ void solve_and_list(ScanState &z, uint32_t scan, const double *sv, const SolveArgs &a)
+{
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        float *hist = a.pose_hist + (size_t)scan * kCertHist * 16;
+        float *trace = a.pass < a.trace_len ? a.trace_err + (size_t)scan * a.trace_len : nullptr;
+        if (a.o3d) o3d_solve(z, sv, a.pass, a.max_iteration, hist, trace);
+        else gn_solve(z, sv, a.pass, a.acc_err, a.eps, hist, trace);
+    }
+    __syncwarp();
+    if (a.shard.enabled && !z.done) list_scan_tiles(z, scan, z.T, a.shard, a.active, a.n_active_next);
+}
+
+// the sums arrive from outside (map sharding: all-reduced across ranks by NCCL or the caller's hook)
+__global__ void __launch_bounds__(32) solve_kernel(ScanState *states, const double *__restrict__ sums, SolveArgs a)
 {
     __shared__ double sv[kAccum];
     ScanState &z = states[blockIdx.x];
     if (z.done) return;
     sv[threadIdx.x] = sums[(size_t)blockIdx.x * kAccum + threadIdx.x];
     __syncwarp();
-    if (threadIdx.x != 0) return;
-    float *hist = pose_hist + (size_t)blockIdx.x * kCertHist * 16;
-    float *trace = pass < trace_len ? trace_err + (size_t)blockIdx.x * trace_len : nullptr;
-    if (o3d) o3d_solve(z, sv, pass, max_iteration, hist, trace);
-    else gn_solve(z, sv, pass, acc_err, eps, hist, trace);
+    solve_and_list(z, blockIdx.x, sv, a);
 }
 
 // single GPU: ordered sum of the scan's partial rows and the solve in one launch
 __global__ void __launch_bounds__(256)
-    rowsum_solve_kernel(ScanState *states, const double *__restrict__ partials, double *__restrict__ sums, int pass,
-                        int o3d, float acc_err, float eps, int max_iteration, float *pose_hist, float *trace_err,
-                        int trace_len)
+    rowsum_solve_kernel(ScanState *states, const double *__restrict__ partials, double *__restrict__ sums, SolveArgs a)
 {
     __shared__ double sw[8][kAccum];
     __shared__ double sv[kAccum];
     ScanState &z = states[blockIdx.x];
     if (z.done) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double s = 0.0;
-    const uint32_t n_tiles = (z.n_pts + kTile - 1) / kTile;
-    for (uint32_t t = warp; t < n_tiles; t += 8) s += partials[(size_t)(z.tile_begin + t) * kAccum + lane];
-    sw[warp][lane] = s;
-    __syncthreads();
-    if (warp != 0) return;
-    double tot = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) tot += sw[w][lane];
-    sums[(size_t)blockIdx.x * kAccum + lane] = tot;
-    sv[lane] = tot;
+    const double tot = scan_rowsum(z, partials, a.pass, sw);
+    if (threadIdx.x >= 32) return;
+    sums[(size_t)blockIdx.x * kAccum + threadIdx.x] = tot;
+    sv[threadIdx.x] = tot;
     __syncwarp();
-    if (lane != 0) return;
-    float *hist = pose_hist + (size_t)blockIdx.x * kCertHist * 16;
-    float *trace = pass < trace_len ? trace_err + (size_t)blockIdx.x * trace_len : nullptr;
-    if (o3d) o3d_solve(z, sv, pass, max_iteration, hist, trace);
-    else gn_solve(z, sv, pass, acc_err, eps, hist, trace);
+    solve_and_list(z, blockIdx.x, sv, a);
 }
 
 // =========================================================================================
@@ -1154,71 +1219,54 @@ int SearchTimer::end(cudaStream_t st)
 }
 
 // ---- in-kernel exchange of the per-scan rows across ranks (map sharding) ---------------------------
+// Buffer of one rank: rows[2][world][max_scans][kAccum] doubles, then flags[2][world][max_scans][2] u64
+// ((epoch, shape) per parity, source rank and scan).
 __device__ __forceinline__ double *xch_rows(void *base, const XchView &x, int par, int r)
 {
     return reinterpret_cast<double *>(base) + ((size_t)(par * x.world + r) * x.max_scans) * kAccum;
 }
-// flag record of (parity, rank): [0] epoch, [1] what that rank ran (scans, passes, mode) -- a peer whose
-// batch shape differs is reported instead of summed
-__device__ __forceinline__ unsigned long long *xch_flag(void *base, const XchView &x, int par, int r)
+__device__ __forceinline__ unsigned long long *xch_flag(void *base, const XchView &x, int par, int r, uint32_t scan)
 {
     return reinterpret_cast<unsigned long long *>(reinterpret_cast<double *>(base) +
                                                   (size_t)2 * x.world * x.max_scans * kAccum) +
-           2 * (par * x.world + r);
+           2 * ((size_t)(par * x.world + r) * x.max_scans + scan);
 }
 
-// ordered sum of a scan's partial rows, stored into EVERY rank's buffer (peer stores over NVLink);
-// the last block to finish publishes the epoch to every rank
+// One launch per iteration, one block per scan: ordered sum of the scan's partial rows, STORED into every
+// rank's buffer (peer stores over NVLink) and published with a per-scan release flag; then the block
+// waits for the same scan's rows of every other rank, adds them in rank order (bit-identical on all
+// ranks) and solves.  The compute (row sum, solve) and the collective (all-gather of 32 doubles per scan
+// + ordered reduction) are one kernel; no host call, no NCCL launch, and ranks synchronise per scan, not
+// per batch.  All blocks of the launch are resident at once (n_scans <= a few hundred), and a block only
+// waits for stores its peers issue BEFORE they wait themselves, so there is no cyclic wait.
+// The epoch of the run's first pass lives in device memory (x.epoch): the launch is graph-capturable.
 __global__ void __launch_bounds__(256)
-    rowsum_xchg_kernel(const ScanState *__restrict__ states, const double *__restrict__ partials, XchView x,
-                       unsigned long long epoch, unsigned long long shape)
+    rowsum_xchg_solve_kernel(ScanState *states, const double *__restrict__ partials, double *__restrict__ sums, XchView x,
+                             unsigned long long shape, SolveArgs a)
 {
     __shared__ double sw[8][kAccum];
-    const ScanState &z = states[blockIdx.x];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ double sv[kAccum];
+    ScanState &z = states[blockIdx.x];
+    if (z.done) return;  // identical on every rank: the states are replicas
+    const double tot = scan_rowsum(z, partials, a.pass, sw);
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const unsigned long long epoch = *x.epoch + (unsigned long long)a.pass;
     const int par = (int)(epoch & 1ull);
-    double s = 0.0;
-    if (!z.done) {
-        const uint32_t n_tiles = (z.n_pts + kTile - 1) / kTile;
-        for (uint32_t t = warp; t < n_tiles; t += 8) s += partials[(size_t)(z.tile_begin + t) * kAccum + lane];
-    }
-    sw[warp][lane] = s;
-    __syncthreads();
-    if (warp != 0) return;
-    double tot = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) tot += sw[w][lane];
     for (int r = 0; r < x.world; ++r) xch_rows(x.peers[r], x, par, x.rank)[(size_t)blockIdx.x * kAccum + lane] = tot;
     __threadfence_system();
     __syncwarp();
-    if (lane != 0) return;
-    if (atomicAdd(x.counter, 1u) == gridDim.x - 1) {  // every block's row is out: publish
-        *x.counter = 0;
-        __threadfence_system();
-        for (int r = 0; r < x.world; ++r) {
-            unsigned long long *f = xch_flag(x.peers[r], x, par, x.rank);
-            f[1] = shape;
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
-        }
+    if (lane < x.world) {
+        unsigned long long *f = xch_flag(x.peers[lane], x, par, x.rank, blockIdx.x);
+        f[1] = shape;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
     }
-}
-
-// wait for every rank's rows of this epoch, add them in rank order (identical on all ranks), solve
-__global__ void __launch_bounds__(32)
-    solve_xchg_kernel(ScanState *states, XchView x, unsigned long long epoch, unsigned long long shape,
-                      double *__restrict__ sums, int pass, int o3d, float acc_err, float eps, int max_iteration,
-                      float *pose_hist, float *trace_err, int trace_len)
-{
-    __shared__ double sv[kAccum];
-    ScanState &z = states[blockIdx.x];
-    if (z.done) return;
-    const int lane = threadIdx.x, par = (int)(epoch & 1ull);
     void *mine = x.peers[x.rank];
     bool late = false;
     if (lane < x.world) {
         // bounded wait: a peer that failed before its row-sum, or whose epochs drifted (different batch
         // size / iteration count / mode), must not leave this GPU spinning for ever
-        const unsigned long long *f = xch_flag(mine, x, par, lane);
+        const unsigned long long *f = xch_flag(mine, x, par, lane, blockIdx.x);
         unsigned long long v, t0, t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         do {
@@ -1237,51 +1285,48 @@ __global__ void __launch_bounds__(32)
         }
         return;
     }
-    double tot = 0.0;
-    for (int r = 0; r < x.world; ++r) tot += __ldcg(xch_rows(mine, x, par, r) + (size_t)blockIdx.x * kAccum + lane);
-    sums[(size_t)blockIdx.x * kAccum + lane] = tot;
-    sv[lane] = tot;
+    double all = 0.0;
+    for (int r = 0; r < x.world; ++r) all += __ldcg(xch_rows(mine, x, par, r) + (size_t)blockIdx.x * kAccum + lane);
+    sums[(size_t)blockIdx.x * kAccum + lane] = all;
+    sv[lane] = all;
     __syncwarp();
-    if (lane != 0) return;
-    float *hist = pose_hist + (size_t)blockIdx.x * kCertHist * 16;
-    float *trace = pass < trace_len ? trace_err + (size_t)blockIdx.x * trace_len : nullptr;
-    if (o3d) o3d_solve(z, sv, pass, max_iteration, hist, trace);
-    else gn_solve(z, sv, pass, acc_err, eps, hist, trace);
+    solve_and_list(z, blockIdx.x, sv, a);
 }
 
-// per-scan totals of the partial rows and the solve.  Map sharding: the totals are summed across
-// ranks through the caller's hook (one small all-reduce per iteration: n_scans x 32 doubles) between
-// the two; otherwise both run in one launch.
-static int reduce_and_solve(const IcpConfig &cfg, BatchBuffers &b, int pass, int o3d, cudaStream_t st)
+// the run is over: the next one starts at a fresh epoch (one per pass; O3D runs one more than num_iterations)
+__global__ void xch_advance_kernel(unsigned long long *epoch, unsigned long long by) { *epoch += by; }
+
+// per-scan totals of the partial rows and the solve.  Map sharding: the totals are summed across ranks
+// inside the kernel (peer exchange), by ncclAllReduce on the library's stream, or through the caller's
+// hook; otherwise row sum and solve are one launch.
+static int reduce_and_solve(const IcpConfig &cfg, BatchBuffers &b, int pass, int o3d, const ShardView &shard,
+                            cudaStream_t st)
 {
+    const int n_pass = cfg.num_iterations + 1;
+    SolveArgs a{pass, o3d, cfg.acc_err, cfg.eps, cfg.num_iterations, b.pose_hist.p, b.trace_err.p, b.trace_len,
+                shard, b.active.p, b.counters.p + (pass + 1 < n_pass ? pass + 1 : n_pass)};
     if (cfg.xch.world > 0) {  // in-kernel exchange over peer memory
-        const unsigned long long epoch = cfg.xch_epoch + (unsigned long long)pass;
         const unsigned long long shape = ((unsigned long long)b.n_scans << 32) |
                                          ((unsigned long long)(cfg.num_iterations & 0xFFFFF) << 8) |
                                          (unsigned long long)(cfg.mode & 0xFF);
-        rowsum_xchg_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, cfg.xch, epoch, shape);
-        SSF_LAUNCHED();
-        solve_xchg_kernel<<<(unsigned)b.n_scans, 32, 0, st>>>(b.state.p, cfg.xch, epoch, shape, b.sums.p, pass, o3d,
-                                                              cfg.acc_err, cfg.eps, cfg.num_iterations, b.pose_hist.p,
-                                                              b.trace_err.p, b.trace_len);
+        rowsum_xchg_solve_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, b.sums.p, cfg.xch, shape, a);
         SSF_LAUNCHED();
         return SSF_OK;
     }
-    if (!cfg.allreduce) {
-        rowsum_solve_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, b.sums.p, pass, o3d,
-                                                                 cfg.acc_err, cfg.eps, cfg.num_iterations, b.pose_hist.p,
-                                                              b.trace_err.p, b.trace_len);
+    if (!cfg.allreduce && !cfg.nccl_allreduce) {
+        rowsum_solve_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, b.sums.p, a);
         SSF_LAUNCHED();
         return SSF_OK;
     }
-    rowsum_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, b.sums.p);
+    rowsum_kernel<<<(unsigned)b.n_scans, 256, 0, st>>>(b.state.p, b.partials.p, b.sums.p, pass);
     SSF_LAUNCHED();
-    if (cfg.allreduce(cfg.allreduce_user, b.sums.p, b.n_scans * kAccum, (void *)st) != 0) {
+    if (cfg.nccl_allreduce) {
+        SSF_TRY(cfg.nccl_allreduce(cfg.nccl_user, b.sums.p, b.n_scans * kAccum, st));
+    } else if (cfg.allreduce(cfg.allreduce_user, b.sums.p, b.n_scans * kAccum, (void *)st) != 0) {
         set_error("all-reduce hook failed");
         return SSF_ERR_COMM;
     }
-    solve_kernel<<<(unsigned)b.n_scans, 32, 0, st>>>(b.state.p, b.sums.p, pass, o3d, cfg.acc_err, cfg.eps,
-                                                     cfg.num_iterations, b.pose_hist.p, b.trace_err.p, b.trace_len);
+    solve_kernel<<<(unsigned)b.n_scans, 32, 0, st>>>(b.state.p, b.sums.p, a);
     SSF_LAUNCHED();
     return SSF_OK;
 }
@@ -1298,16 +1343,16 @@ static int reduce_and_solve(const IcpConfig &cfg, BatchBuffers &b, int pass, int
 // blocks -- four times the parallelism per tile, for latency --, large ones four queries per thread
 template <int KIND>
 static void launch_search(bool wide, unsigned grid, cudaStream_t st, const MapView &map, const BatchBuffers &b,
-                          float limit, int use_cert, int pass, uint32_t *fetch)
+                          float limit, int use_cert, int pass, const uint32_t *n_active, uint32_t *fetch)
 {
     if (wide)
         search_accum_kernel<KIND, kWideThreads><<<grid, kWideThreads, 0, st>>>(map, b.src.p, b.tile_scan.p, b.state.p, limit, b.corr.p,
                                                                  b.partials.p, b.cert.p, b.pose_hist.p, use_cert, pass,
-                                                                 b.active.p, b.counters.p, fetch, b.search_stats.p + 2 * pass);
+                                                                 b.active.p, n_active, fetch, b.search_stats.p + 2 * pass);
     else
         search_accum_kernel<KIND, kThreads><<<grid, kThreads, 0, st>>>(map, b.src.p, b.tile_scan.p, b.state.p, limit,
                                                                        b.corr.p, b.partials.p, b.cert.p, b.pose_hist.p,
-                                                                       use_cert, pass, b.active.p, b.counters.p, fetch,
+                                                                       use_cert, pass, b.active.p, n_active, fetch,
                                                                        b.search_stats.p + 2 * pass);
 }
 
@@ -1345,17 +1390,34 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
         SSF_LAUNCHED();
         return SSF_OK;
     }
+    const int n_pass = cfg.num_iterations + 1;  // search launches of the longest flow (O3D runs one more than GN)
+    const bool sharded = map.own_lo != INT32_MIN || map.own_hi != INT32_MAX;
+    ShardView shard;
+    if (sharded) {
+        shard.enabled = 1;
+        shard.ox = map.shard_ox;
+        shard.inv_h = map.shard_inv_h;
+        shard.own_lo = map.own_lo;
+        shard.own_hi = map.own_hi;
+        shard.tile_box = b.tile_box.p;
+    }
+    // sharded: launch i works on the list built for it (counters[i]); else one list serves every launch
+    auto n_active_of = [&](int i) { return b.counters.p + (sharded ? i : 0); };
+    auto fetch_of = [&](int i) { return b.counters.p + n_pass + 1 + i; };
     if (cfg.mode != SSF_MODE_REFERENCE) {
-        // counters[0] = number of active tiles, counters[1 + i] = fetch counter of search launch i
         // (zeroed by a kernel: memsets and copies on the compute stream can queue behind the other
         // batch's H2D copy on a copy engine and stall the pipeline)
-        zero_u32_kernel<<<(unsigned)((cfg.num_iterations + 3 + 255) / 256), 256, 0, st>>>(b.counters.p,
-                                                                                          (uint32_t)cfg.num_iterations + 3);
+        const uint32_t n_cnt = 2u * (uint32_t)n_pass + 2u;
+        zero_u32_kernel<<<(n_cnt + 255) / 256, 256, 0, st>>>(b.counters.p, n_cnt);
         SSF_LAUNCHED();
-        zero_u32_kernel<<<(unsigned)((4 * (cfg.num_iterations + 1) + 255) / 256), 256, 0, st>>>(
-            reinterpret_cast<uint32_t *>(b.search_stats.p), 4u * (uint32_t)(cfg.num_iterations + 1));
+        zero_u32_kernel<<<(unsigned)((4 * n_pass + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<uint32_t *>(b.search_stats.p), 4u * (uint32_t)n_pass);
         SSF_LAUNCHED();
-        active_tiles_kernel<<<(scans + 127) / 128, 128, 0, st>>>(S, scans, b.active.p, b.counters.p);
+        if (sharded) {
+            tile_box_kernel<<<tiles, 128, 0, st>>>(b.src.p, b.tile_scan.p, S, b.tile_box.p);
+            SSF_LAUNCHED();
+        }
+        active_tiles_kernel<<<(scans * 32 + 127) / 128, 128, 0, st>>>(S, scans, shard, b.active.p, b.counters.p);
         SSF_LAUNCHED();
     }
     if (cfg.mode == SSF_MODE_GN_P2P || cfg.mode == SSF_MODE_GN_P2PLANE) {
@@ -1365,15 +1427,15 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
         }
         for (int i = 0; i < cfg.num_iterations; ++i) {
             if (cfg.mode == SSF_MODE_GN_P2PLANE)
-                TIMED_SEARCH(launch_search<ACC_GN_P2PLANE>(wide, grid, st, map, b, limit, certs && i > 0, i, b.counters.p + 1 + i));
+                TIMED_SEARCH(launch_search<ACC_GN_P2PLANE>(wide, grid, st, map, b, limit, certs && i > 0, i, n_active_of(i), fetch_of(i)));
             else
-                TIMED_SEARCH(launch_search<ACC_GN_P2P>(wide, grid, st, map, b, limit, certs && i > 0, i, b.counters.p + 1 + i));
-            SSF_TRY(reduce_and_solve(cfg, b, i, 0, st));
+                TIMED_SEARCH(launch_search<ACC_GN_P2P>(wide, grid, st, map, b, limit, certs && i > 0, i, n_active_of(i), fetch_of(i)));
+            SSF_TRY(reduce_and_solve(cfg, b, i, 0, shard, st));
         }
     } else if (cfg.mode == SSF_MODE_O3D_P2P) {
         for (int i = 0; i <= cfg.num_iterations; ++i) {
-            TIMED_SEARCH(launch_search<ACC_KABSCH>(wide, grid, st, map, b, limit, certs && i > 0, i, b.counters.p + 1 + i));
-            SSF_TRY(reduce_and_solve(cfg, b, i, 1, st));
+            TIMED_SEARCH(launch_search<ACC_KABSCH>(wide, grid, st, map, b, limit, certs && i > 0, i, n_active_of(i), fetch_of(i)));
+            SSF_TRY(reduce_and_solve(cfg, b, i, 1, shard, st));
         }
     } else if (cfg.mode == SSF_MODE_REFERENCE) {
         if (map.own_lo != INT32_MIN || map.own_hi != INT32_MAX) {
@@ -1405,6 +1467,10 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
         set_error("unknown mode %d", cfg.mode);
         return SSF_ERR_INVALID;
     }
+    if (cfg.xch.world > 0 && cfg.mode != SSF_MODE_REFERENCE) {
+        xch_advance_kernel<<<1, 1, 0, st>>>(cfg.xch.epoch, (unsigned long long)cfg.num_iterations + 2);
+        SSF_LAUNCHED();
+    }
     results_kernel<<<(scans + 127) / 128, 128, 0, st>>>(S, b.results.p, scans, cfg.mode, cfg.acc_err);
     SSF_LAUNCHED();
     return SSF_OK;
@@ -1429,14 +1495,17 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
     SSF_TRY(search_grid(b, &grid, &wide));
     if (cfg.mode != SSF_MODE_REFERENCE) {  // allocations happen here, never inside a capture
         SSF_TRY(b.active.reserve(b.max_tiles ? b.max_tiles : 1));
-        SSF_TRY(b.counters.reserve((size_t)cfg.num_iterations + 3));
+        SSF_TRY(b.counters.reserve(2 * ((size_t)cfg.num_iterations + 1) + 2));
+        if (map.own_lo != INT32_MIN || map.own_hi != INT32_MAX) SSF_TRY(b.tile_box.reserve(2 * (b.max_tiles ? b.max_tiles : 1)));
         SSF_TRY(b.search_stats.reserve(2 * ((size_t)cfg.num_iterations + 1)));
         b.search_stats_len = cfg.num_iterations + (cfg.mode == SSF_MODE_O3D_P2P ? 1 : 0);
     } else {
         b.search_stats_len = 0;
     }
     const char *ng = getenv("SSF_NO_GRAPH");
-    const bool graphable = cfg.mode != SSF_MODE_REFERENCE && b.n_tiles > 0 && !cfg.allreduce && cfg.xch.world == 0 &&
+    // (the caller's all-reduce hook is a host action per iteration: not capturable; the in-kernel exchange and
+    // ncclAllReduce are)
+    const bool graphable = cfg.mode != SSF_MODE_REFERENCE && b.n_tiles > 0 && !(cfg.allreduce && !cfg.nccl_allreduce && cfg.xch.world == 0) &&
                            !(timer && timer->enabled) && !(ng && atoi(ng) != 0);
     if (!graphable) {
         if (cfg.mode != SSF_MODE_REFERENCE)
@@ -1457,11 +1526,13 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
     put(&cfg.max_corr, sizeof(float)); put(&cfg.acc_err, sizeof(float)); put(&cfg.eps, sizeof(float));
     const unsigned long long scalars[] = {(unsigned long long)cfg.num_iterations, (unsigned long long)cfg.mode,
                                           (unsigned long long)certs, (unsigned long long)grid, (unsigned long long)b.n_scans,
-                                          (unsigned long long)wide, (unsigned long long)b.trace_len};
+                                          (unsigned long long)wide, (unsigned long long)b.trace_len, (unsigned long long)cfg.xch.world,
+                                          (unsigned long long)cfg.xch.rank};
     put(scalars, sizeof(scalars));
     const void *ptrs[] = {b.src.p, b.corr.p, b.cert.p, b.pose_hist.p, b.tile_scan.p, b.active.p, b.counters.p,
                           b.partials.p, b.sums.p, b.state.p, b.results.p, b.trace_err.p, b.trace_search.p, T_init,
-                          b.search_stats.p};
+                          b.search_stats.p, b.tile_box.p, (const void *)cfg.xch.peers, (const void *)cfg.xch.epoch,
+                          (const void *)cfg.nccl_allreduce, cfg.nccl_user};
     put(ptrs, sizeof(ptrs));
     if (!b.graph_exec || key != b.graph_key) {
         if (b.graph_exec) {

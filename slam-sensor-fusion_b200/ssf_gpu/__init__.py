@@ -222,6 +222,14 @@ class ICPPointToPoint:
     def exchangeClose(self) -> None:
         capi.check(capi.lib().ssf_icp_exchange_close(self._h))
 
+    def ncclInit(self, unique_id: bytes, rank: int, world: int) -> None:
+        """Map sharding through ``ncclAllReduce`` on the library's stream (collective call: every rank, same id)."""
+        buf = (ctypes.c_ubyte * capi.NCCL_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        capi.check(capi.lib().ssf_icp_nccl_init(self._h, buf, int(rank), int(world)))
+
+    def ncclClose(self) -> None:
+        capi.check(capi.lib().ssf_icp_nccl_close(self._h))
+
     # -- calculateAlignment (icp_point_to_point.cpp:185-254) ---------------------------------------
     def calculateAlignment(self) -> ICPResult:
         r = IcpResult()
@@ -284,6 +292,13 @@ class ICPPointToPoint:
             self.close()
         except Exception:
             pass
+
+
+def nccl_unique_id() -> bytes:
+    """``ncclGetUniqueId`` through the library: call on rank 0, carry the bytes to every rank, ``ncclInit``."""
+    h = (ctypes.c_ubyte * capi.NCCL_ID_BYTES)()
+    capi.check(capi.lib().ssf_nccl_unique_id(h))
+    return bytes(h)
 
 
 class Batch:

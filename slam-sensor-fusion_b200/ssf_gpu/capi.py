@@ -12,12 +12,13 @@ SSF_OK = 0
 MODE_REFERENCE, MODE_GN_P2P, MODE_GN_P2PLANE, MODE_O3D_P2P = 0, 1, 2, 3
 REDUCE_STRICT, REDUCE_FAST = 0, 1
 XCH_HANDLE_BYTES = 128  # SSF_XCH_HANDLE_BYTES
+NCCL_ID_BYTES = 128  # SSF_NCCL_ID_BYTES
 
 EXPORTS = [
     "ssf_last_error", "ssf_version", "ssf_ctx_create", "ssf_ctx_destroy", "ssf_ctx_synchronize", "ssf_ctx_stream", "ssf_ctx_time_searches", "ssf_ctx_search_time", "ssf_ctx_search_times",
     "ssf_icp_create", "ssf_icp_destroy", "ssf_icp_set_params", "ssf_icp_get_params", "ssf_icp_set_target",
     "ssf_icp_set_source", "ssf_icp_set_initial", "ssf_icp_align", "ssf_icp_get_correspondences", "ssf_icp_get_trace",
-    "ssf_icp_target_size", "ssf_icp_set_target_shard", "ssf_icp_set_allreduce", "ssf_icp_exchange_create", "ssf_icp_exchange_open", "ssf_icp_exchange_close", "ssf_nn_search", "ssf_nn_search_bench", "ssf_voxel_downsample", "ssf_cloud_subsample", "ssf_cloud_remove_floor", "ssf_cloud_crop_radius", "ssf_bfa_pose_count", "ssf_bfa_align", "ssf_batch_create", "ssf_batch_destroy",
+    "ssf_icp_target_size", "ssf_icp_set_target_shard", "ssf_icp_set_allreduce", "ssf_icp_exchange_create", "ssf_icp_exchange_open", "ssf_icp_exchange_close", "ssf_nccl_unique_id", "ssf_icp_nccl_init", "ssf_icp_nccl_close", "ssf_nn_search", "ssf_nn_search_bench", "ssf_voxel_downsample", "ssf_cloud_subsample", "ssf_cloud_remove_floor", "ssf_cloud_crop_radius", "ssf_bfa_pose_count", "ssf_bfa_align", "ssf_batch_create", "ssf_batch_destroy",
     "ssf_batch_upload", "ssf_batch_upload_async", "ssf_batch_set_initial", "ssf_batch_run", "ssf_batch_results", "ssf_batch_search_stats", "ssf_icp_align_batch",
     "ssf_kernel_launches", "ssf_nn_queries",
 ]
@@ -89,6 +90,9 @@ def lib() -> ctypes.CDLL:
     L.ssf_icp_exchange_create.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, vp]
     L.ssf_icp_exchange_open.argtypes = [vp, vp]
     L.ssf_icp_exchange_close.argtypes = [vp]
+    L.ssf_nccl_unique_id.argtypes = [vp]
+    L.ssf_icp_nccl_init.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
+    L.ssf_icp_nccl_close.argtypes = [vp]
     L.ssf_nn_search.argtypes = [vp, vp, sz, sz, f32, vp, vp]
     L.ssf_nn_search_bench.argtypes = [vp, vp, sz, sz, f32, i32, P(f32), vp, vp]
     L.ssf_voxel_downsample.argtypes = [vp, vp, sz, sz, f32, vp, P(sz), P(i32)]

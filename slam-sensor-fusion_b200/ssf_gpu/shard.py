@@ -3,8 +3,9 @@
 * scans sharded, map replicated (offline reprocessing, BASELINE config 4): ``scan_range``;
 * map sharded by cell columns with a one-cell halo, scans replicated, one small all-reduce per
   iteration (configs 3 and 5): ``global_grid`` / ``partition_columns`` / ``shard_map`` and the
-  ``torch_allreduce_hook`` that plugs ``torch.distributed`` into ``ssf_icp_set_allreduce``, and
-  ``setup_peer_exchange`` for the in-kernel exchange over CUDA IPC peer memory.
+  ``setup_peer_exchange`` for the in-kernel exchange over CUDA IPC peer memory (default), ``setup_nccl``
+  for ``ncclAllReduce`` behind the C ABI, and the ``torch_allreduce_hook`` that plugs
+  ``torch.distributed`` into ``ssf_icp_set_allreduce``.
 
 Pure numpy (+ optional torch for the hook); covered on CPU by tests/test_sharding_gloo.py.
 """
@@ -91,6 +92,17 @@ def setup_peer_exchange(icp, rank: int, world: int, max_scans: int, group=None) 
     dist.all_gather_object(handles, mine, group=group)
     icp.exchangeOpen(handles)
     dist.barrier(group=group)  # nobody starts storing before every rank has its buffer mapped
+
+
+def setup_nccl(icp, rank: int, world: int, group=None) -> None:
+    """The per-iteration sum through the library's own ``ncclAllReduce`` (``ssf_icp_nccl_init``): rank 0
+    creates the unique id, ``torch.distributed`` only carries its 128 bytes to the other ranks."""
+    import torch.distributed as dist
+    import ssf_gpu
+    box = [ssf_gpu.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    icp.ncclInit(box[0], rank, world)
+    dist.barrier(group=group)
 
 
 class _DevArray:

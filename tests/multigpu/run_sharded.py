@@ -27,8 +27,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--map-points", type=int, default=1_000_000)
     ap.add_argument("--mode", default="p2plane", choices=["p2plane", "p2p", "o3d"])
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
-                    help="nccl: all-reduce hook per iteration; peer: in-kernel exchange over CUDA IPC peer memory")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer", "hook"],
+                    help="nccl: ncclAllReduce behind the C ABI; peer: in-kernel exchange over CUDA IPC peer memory; "
+                         "hook: the caller's all-reduce callback (torch.distributed)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -46,6 +47,8 @@ def main():
     icp.setTargetShard(s)
     if args.exchange == "peer":
         shard.setup_peer_exchange(icp, rank, world, max_scans=16)
+    elif args.exchange == "nccl":
+        shard.setup_nccl(icp, rank, world)
     else:
         icp.setAllreduce(shard.torch_allreduce_hook(local))
     res = icp.align_batch(scans, inits)

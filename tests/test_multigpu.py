@@ -18,7 +18,7 @@ def _n_gpus():
         return 0
 
 
-@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+@pytest.mark.parametrize("exchange", ["nccl", "peer", "hook"])
 @pytest.mark.parametrize("mode", ["p2plane", "o3d"])
 def test_map_sharded_equals_unsharded(mode, exchange):
     n = _n_gpus()
