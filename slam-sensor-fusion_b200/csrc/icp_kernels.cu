@@ -166,6 +166,16 @@ __device__ __forceinline__ void tile_bar_wait(unsigned long long *bar, uint32_t 
     }
 }
 
+// sharded maps: a tile left out of this rank's work lists is never written, so every row starts as
+// "owned by another rank, no certificate"
+__global__ void __launch_bounds__(256) reset_rows_kernel(int32_t *__restrict__ corr, uint2 *__restrict__ cert, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    corr[i] = -2;
+    cert[i] = make_uint2(0u, 0xFFFFFFFFu);
+}
+
 __global__ void zero_u32_kernel(uint32_t *p, uint32_t n)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1415,6 +1425,8 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
         SSF_LAUNCHED();
         if (sharded) {
             tile_box_kernel<<<tiles, 128, 0, st>>>(b.src.p, b.tile_scan.p, S, b.tile_box.p);
+            SSF_LAUNCHED();
+            reset_rows_kernel<<<(unsigned)((b.n_slots + 255) / 256), 256, 0, st>>>(b.corr.p, b.cert.p, (uint32_t)b.n_slots);
             SSF_LAUNCHED();
         }
         active_tiles_kernel<<<(scans * 32 + 127) / 128, 128, 0, st>>>(S, scans, shard, b.active.p, b.counters.p);
