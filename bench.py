@@ -44,13 +44,13 @@ WORKLOADS = {
                scans_per_step=64,
                desc="32-beam scan (~30k pts) reference point-to-point ICP (10 it, thr 0.5) vs 1M-point map"),
     "c3": dict(map_points=50_000_000, beams=32, azimuths=1024, leaf=0.0, mode="gn_p2plane", max_range=100.0,
-               sharded=True, scans_per_step=64,
+               sharded=True, scans_per_step=256,
                desc="32-beam scans (~30k pts) point-to-plane GN ICP (10 it, thr 0.5) vs 50M-point map, "
                     "map sharded by cell columns across ranks, one 32-double sum per scan per iteration"),
     # config 4: the offline sequence (10 000 scans of config 1's shape against the 5M-point map); scans are
     # independent, so ranks take disjoint scans and the sequence time is 10 000 / (scans/s over all ranks)
     "c4": dict(map_points=5_000_000, beams=32, azimuths=1024, leaf=0.0, mode="reference", max_range=100.0,
-               scans_per_step=128,
+               scans_per_step=512,
                desc="offline reprocessing: 32-beam scans (~30k pts) reference point-to-point ICP (10 it, thr 0.5) vs "
                     "5M-point map, scans sharded across ranks, no communication"),
     # config 5 per GPU: 62.5M map points per rank (500M on 8), dense scans, tight leaf, 30 iterations.
@@ -592,7 +592,7 @@ def run_gpu(args, rank, world, local_rank):
     peak, peak_kind = peaks()
     n_search = max(1, int(np.median(searches)))
     if w["mode"] == "reference":
-        roofline = reference_roofline(peak, peak_kind, search_ms, search_launches, dev_ms_timed, k2, res, clocks, B)
+        roofline = reference_roofline(peak, peak_kind, search_ms, search_launches, dev_ms_timed, k2, res, clocks, B, single_ms)
     else:
         # roofline of the dominant kernel (search_accum): algorithmic bytes of ONE launch over the batch
         cell = float(np.sqrt(np.float32(THR)) * np.float32(1.01))
@@ -645,26 +645,27 @@ def run_gpu(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def reference_roofline(peak, peak_kind, search_ms, search_launches, dev_ms_timed, k2, res, clocks, B):
+def reference_roofline(peak, peak_kind, search_ms, search_launches, dev_ms_timed, k2, res, clocks, B, single_ms):
     """REFERENCE-mode workloads (c1, c4): the dominant kernel is ref_reduce_kernel, a LATENCY-bound chain of
     dependent float adds in source-row order (what makes the result bit-identical to the reference), one
-    block per scan.  Its roofline is the 4.1-cycle FADD dependency floor per row and pass, not HBM bytes:
-    `achieved`/`peak` are rows per second per scan against that floor; the HBM fraction is reported beside."""
+    block per scan; a batch runs the chains of all its scans side by side.  Its roofline is the 4.1-cycle
+    FADD dependency floor per row and chain pass, not HBM bytes: `achieved` / `peak` are rows per cycle of ONE
+    scan, taken from the single-scan device latency (so searches and launches are charged to it as well --
+    an upper bound on the cycles per row).  The HBM fraction of the loop's bytes is reported beside it."""
     k_final = float(np.median([int(r.k_final) for r in res]))
     n_src = float(np.median([int(r.n_source) for r in res]))
     its = float(np.median([int(r.iterations) for r in res]))
     srch = float(np.median([int(r.n_searches) for r in res]))
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    reduce_ms = (dev_ms_timed - search_ms) / k2          # per step: everything but the first search launch
     chain_rows = n_src * (2.0 * its + (srch - 1.0))      # chain passes over the scan's rows: 2 per iteration + 1 per re-search
-    cyc_per_row = reduce_ms * 1e-3 * mhz * 1e6 / max(1.0, chain_rows)
+    cyc_per_row = single_ms * 1e-3 * mhz * 1e6 / max(1.0, chain_rows)
+    loop_ms = (dev_ms_timed - search_ms) / k2            # per step: everything but the first search launch
     alg_bytes = B * its * 48.0 * k_final                  # SURVEY 8(d): 48 K bytes per loop iteration
     return {"bound": "latency (dependent FADD chain)", "kernel": "ref_reduce_kernel", "achieved": 1.0 / max(cyc_per_row, 1e-9),
             "peak": 1.0 / 4.1, "unit": "rows/cycle/scan", "frac": 4.1 / max(cyc_per_row, 1e-9), "traffic": None,
-            "peak_kind": "4.1-cycle dependent FADD (profiles/exp/mb/chain.cu)", "cycles_per_row": cyc_per_row,
-            "note": "cycles_per_row is an upper bound: it charges the whole non-search part of the step (chains of all scans run "
-                    "concurrently, one block per scan) to the chain rows of the median scan",
-            "hbm_frac_of_loop_bytes": alg_bytes / max(reduce_ms * 1e-3, 1e-12) / 1e9 / peak, "hbm_peak_kind": peak_kind,
+            "peak_kind": "4.1-cycle dependent FADD (profiles/exp/mb/chain.cu: 4.09 registers only, 4.19 fed from shared memory)",
+            "cycles_per_row": cyc_per_row, "single_scan_ms": single_ms, "chain_passes_per_scan": 2.0 * its + (srch - 1.0),
+            "hbm_frac_of_loop_bytes": alg_bytes / max(loop_ms * 1e-3, 1e-12) / 1e9 / peak, "hbm_peak_kind": peak_kind,
             "first_search_ms": search_ms / max(1, search_launches),
             "share_of_step": 1.0 - search_ms / dev_ms_timed, "ms_per_step_with_events": dev_ms_timed / k2}
 

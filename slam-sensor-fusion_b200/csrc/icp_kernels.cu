@@ -864,7 +864,7 @@ __global__ void __launch_bounds__(256)
 // as dropped, and dropped rows add exact zeros to the ordered sums.
 __global__ void __launch_bounds__(kTile)
     ref_search_kernel(MapView map, const float4 *__restrict__ src, float4 *__restrict__ P, float4 *__restrict__ Q,
-                      int32_t *__restrict__ corr, const uint32_t *__restrict__ tile_scan,
+                      int32_t *__restrict__ corr, uint32_t *__restrict__ pos_of, const uint32_t *__restrict__ tile_scan,
                       const ScanState *__restrict__ states, float limit, int first)
 {
     __shared__ float sT[16];
@@ -881,6 +881,7 @@ __global__ void __launch_bounds__(kTile)
     const size_t slot = (size_t)z.pt_begin + row;
     bool active = row < z.n_pts;
     float3 p = make_float3(0.f, 0.f, 0.f);
+    uint32_t seed = kNoPos;
     if (active) {
         if (first) {
             const float4 s4 = src[slot];
@@ -891,15 +892,31 @@ __global__ void __launch_bounds__(kTile)
         } else {
             const float4 p4 = P[slot];
             p = make_float3(p4.x, p4.y, p4.z);
+            seed = pos_of[slot];  // the neighbour of the previous search: a bound to start the walk from
         }
     }
     if (!active) return;
-    const NNHit h = nn_query(map, p.x, p.y, p.z, limit);
+    // (a seed only tightens the bound the walk starts with; the result is that of the unseeded walk)
+    NNHit h;
+    h.d2 = limit; h.idx = -1; h.pos = 0;
+    if (limit > 0.f && map.n_pts > 0 && isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        NNBest<false> B;
+        if (nn_walk_near<false>(map, p.x, p.y, p.z, limit, 0.f, B, seed)) {
+            B.skip = kNoPos;
+            nn_walk_far<false>(map, p.x, p.y, p.z, B);
+        }
+        if ((uint32_t)(B.key >> 32) < __float_as_uint(limit)) {
+            h.d2 = B.bd();
+            h.idx = (int)(uint32_t)(B.key & 0xFFFFFFFFull);
+            h.pos = B.pos;
+        }
+    }
     corr[slot] = h.idx;
     if (h.idx >= 0) {
         float4 q = __ldg(&map.pts[h.pos]);
         q.w = 1.f;
         Q[slot] = q;
+        pos_of[slot] = h.pos;
     }
 }
 
@@ -1455,17 +1472,15 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
                       "across ranks); use a GN or O3D mode");
             return SSF_ERR_STATE;
         }
-        // function attributes are per device: set on every run (cheap) rather than once per process
-        SSF_CUDA(cudaFuncSetAttribute(ref_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainBuf)));
-        TIMED_SEARCH((ref_search_kernel<<<tiles, kTile, 0, st>>>(map, b.src.p, b.P.p, b.Q.p, b.corr.p, b.tile_scan.p, S,
-                                                                limit, 1)));
-        g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
+        uint32_t *pos_of = reinterpret_cast<uint32_t *>(b.cert.p);  // the certificate array is free in this mode
+        TIMED_SEARCH((ref_search_kernel<<<tiles, kTile, 0, st>>>(map, b.src.p, b.P.p, b.Q.p, b.corr.p, pos_of, b.tile_scan.p,
+                                                                S, limit, 1)));
         for (int i = 0; i < cfg.num_iterations; ++i) {
             ref_reduce_kernel<<<scans, kRefThreads, sizeof(ChainBuf), st>>>(S, b.P.p, b.Q.p, b.corr.p, i == 0 ? 0 : 1, i, cfg.reduce,
                                                              cfg.acc_err, cfg.eps, b.trace_err.p, b.trace_search.p,
                                                              b.trace_len);
             SSF_LAUNCHED();
-            ref_search_kernel<<<tiles, kTile, 0, st>>>(map, b.src.p, b.P.p, b.Q.p, b.corr.p, b.tile_scan.p, S, limit, 0);
+            ref_search_kernel<<<tiles, kTile, 0, st>>>(map, b.src.p, b.P.p, b.Q.p, b.corr.p, pos_of, b.tile_scan.p, S, limit, 0);
             SSF_LAUNCHED();
             ref_reduce_kernel<<<scans, kRefThreads, sizeof(ChainBuf), st>>>(S, b.P.p, b.Q.p, b.corr.p, 2, i, cfg.reduce, cfg.acc_err,
                                                              cfg.eps, b.trace_err.p, b.trace_search.p, b.trace_len);
@@ -1491,9 +1506,9 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
 // The Gauss-Newton / Open3D-flow loop is a fixed launch sequence whose shape depends only on the
 // batch capacity, the scan count and the parameters -- all data-dependent control lives in device
 // state -- so it is captured once into a CUDA graph and replayed: one graph launch per alignment,
-// no host round trip, no per-kernel launch latency.  (REFERENCE mode launches per-tile grids that
-// follow the upload's point count and is enqueued directly; so are runs with the search timer or
-// the cross-rank exchange hook, which are host-side actions.)
+// no host round trip, no per-kernel launch latency.  REFERENCE mode launches per-tile grids, so its
+// graph is re-captured when the upload's tile count changes.  Runs with the search timer or the caller's
+// all-reduce hook are host-side actions per launch and are enqueued directly.
 int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const float *T_init, cudaStream_t st,
               SearchTimer *timer)
 {
@@ -1514,10 +1529,15 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
     } else {
         b.search_stats_len = 0;
     }
+    if (cfg.mode == SSF_MODE_REFERENCE) {
+        // function attributes are per device: set on every run (cheap) rather than once per process
+        SSF_CUDA(cudaFuncSetAttribute(ref_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainBuf)));
+        g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
+    }
     const char *ng = getenv("SSF_NO_GRAPH");
     // (the caller's all-reduce hook is a host action per iteration: not capturable; the in-kernel exchange and
     // ncclAllReduce are)
-    const bool graphable = cfg.mode != SSF_MODE_REFERENCE && b.n_tiles > 0 && !(cfg.allreduce && !cfg.nccl_allreduce && cfg.xch.world == 0) &&
+    const bool graphable = b.n_tiles > 0 && !(cfg.allreduce && !cfg.nccl_allreduce && cfg.xch.world == 0) &&
                            !(timer && timer->enabled) && !(ng && atoi(ng) != 0);
     if (!graphable) {
         if (cfg.mode != SSF_MODE_REFERENCE)
@@ -1539,11 +1559,11 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
     const unsigned long long scalars[] = {(unsigned long long)cfg.num_iterations, (unsigned long long)cfg.mode,
                                           (unsigned long long)certs, (unsigned long long)grid, (unsigned long long)b.n_scans,
                                           (unsigned long long)wide, (unsigned long long)b.trace_len, (unsigned long long)cfg.xch.world,
-                                          (unsigned long long)cfg.xch.rank};
+                                          (unsigned long long)cfg.xch.rank, (unsigned long long)b.n_tiles, (unsigned long long)cfg.reduce};
     put(scalars, sizeof(scalars));
     const void *ptrs[] = {b.src.p, b.corr.p, b.cert.p, b.pose_hist.p, b.tile_scan.p, b.active.p, b.counters.p,
                           b.partials.p, b.sums.p, b.state.p, b.results.p, b.trace_err.p, b.trace_search.p, T_init,
-                          b.search_stats.p, b.tile_box.p, (const void *)cfg.xch.peers, (const void *)cfg.xch.epoch,
+                          b.search_stats.p, b.tile_box.p, b.P.p, b.Q.p, (const void *)cfg.xch.peers, (const void *)cfg.xch.epoch,
                           (const void *)cfg.nccl_allreduce, cfg.nccl_user};
     put(ptrs, sizeof(ptrs));
     if (!b.graph_exec || key != b.graph_key) {
@@ -1575,7 +1595,8 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
     }
     SSF_CUDA(cudaGraphLaunch(b.graph_exec, st));
     g_launches.fetch_add(b.graph_kernels, std::memory_order_relaxed);
-    g_queries.fetch_add((uint64_t)b.n_slots * (uint64_t)cfg.num_iterations, std::memory_order_relaxed);
+    if (cfg.mode != SSF_MODE_REFERENCE)
+        g_queries.fetch_add((uint64_t)b.n_slots * (uint64_t)cfg.num_iterations, std::memory_order_relaxed);
     return SSF_OK;
 }
 
