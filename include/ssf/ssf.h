@@ -32,6 +32,7 @@ extern "C" {
 typedef struct ssf_ctx ssf_ctx;     /* one CUDA device: stream, scratch memory            */
 typedef struct ssf_icp ssf_icp;     /* one ICPPointToPoint object: map in HBM + parameters */
 typedef struct ssf_batch ssf_batch; /* a set of scans resident in HBM, aligned together    */
+typedef struct ssf_map ssf_map;     /* the whole map cloud resident in HBM (source of target crops) */
 
 typedef enum {
     SSF_OK = 0,
@@ -149,6 +150,13 @@ int ssf_nn_search_bench(ssf_icp *icp, const float *queries, size_t n, size_t str
 int ssf_voxel_downsample(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, float leaf, float *out,
                          size_t *n_out, int *refused);
 
+/* open3d PointCloud.voxel_down_sample(voxel_size) of the Python node (localization_python/localization_python/
+ * localization_node.py:47): voxel origin = min_bound - voxel_size / 2, index = floor((p - origin) / voxel_size),
+ * centroid = sum / count, all in double on the float32 coordinates; output in ascending (z, y, x) voxel index
+ * (Open3D's own order is that of an unordered_map), rounded to float32.  out holds n float4. */
+int ssf_voxel_downsample_o3d(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, double voxel_size, float *out,
+                             size_t *n_out);
+
 /* ---- cloud pre-processing (localization/include/localization/point_cloud_processing.hpp) ---- */
 /* out buffers hold n float4 (16-byte stride, w = 1); *n_out receives the number written. */
 /* applyUniformSubsample (hpp:55-74): points 0, step, 2*step, ...; unchanged when n < step. */
@@ -162,6 +170,41 @@ int ssf_cloud_remove_floor(ssf_ctx *ctx, const float *xyz, size_t n, size_t stri
  * the original index of every output point. */
 int ssf_cloud_crop_radius(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, const float center[3],
                           double radius, float *out, size_t *n_out, int32_t *indices_out);
+
+/* ---- map ingestion and the resident map (rows N3 / N2 of the survey) ------------------------------ */
+/* pcl::io::loadPCDFile<PointXYZ> for the recorder's tiles (mapping/src/map_data_save_node.cpp:71-80; read at
+ * localization/src/global_map_frames_manager.cpp:101,129): DATA binary or ascii, x / y / z float32 or float64
+ * among any other fields.  xyz_out == NULL: only *n_points is set (size query); else n x 3 packed floats. */
+int ssf_pcd_read(const char *path, float *xyz_out, size_t cap_points, size_t *n_points);
+/* pcl::io::savePCDFileBinary of a PointXYZ cloud (global_map_frames_manager.cpp:148): FIELDS x y z, 12 B/point. */
+int ssf_pcd_write_binary(const char *path, const float *xyz, size_t n, size_t stride_bytes);
+/* pcl::fromROSMsg (localization_node.cpp:290-291, map_data_save_node.cpp:66) for the float32 x / y / z fields
+ * of a sensor_msgs/PointCloud2 byte buffer: n_points = width * height records of point_step bytes with the
+ * fields at the given offsets -> n x float4 (w = 1), extracted on the device. */
+int ssf_cloud_from_pointcloud2(ssf_ctx *ctx, const unsigned char *data, size_t n_points, size_t point_step,
+                               size_t off_x, size_t off_y, size_t off_z, int is_bigendian, float *xyz_out);
+/* The map cloud kept in HBM.  ssf_map_create uploads it once; ssf_map_from_pcd_folder is
+ * GlobalMapFramesManager::getMapCloud (global_map_frames_manager.cpp:93-151): <folder>/<map_name>.pcd if it
+ * exists (loaded as it is), else every *.pcd of the folder in readdir order, concatenated, pcl::VoxelGrid
+ * (voxel_size) on the device, saved as <map_name>.pcd when save != 0 -- tiles go pinned host -> HBM, the
+ * merged cloud never returns to the host. */
+int ssf_map_create(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, ssf_map **out);
+int ssf_map_from_pcd_folder(ssf_ctx *ctx, const char *data_folder, const char *map_name, float voxel_size, int save,
+                            ssf_map **out);
+void ssf_map_destroy(ssf_map *map);
+size_t ssf_map_size(const ssf_map *map);
+double ssf_map_ingest_ms(const ssf_map *map); /* device ms of the last H2D + extract + voxel filter */
+int ssf_map_download(ssf_map *map, float *xyz_out /* n x float4 */, size_t cap_points);
+/* applyUniformSubsample(map_cloud_, step) (localization_node.cpp:20), in place in HBM. */
+int ssf_map_subsample(ssf_map *map, size_t point_step);
+/* cropPointCloudThroughRadius(map_T_sensor_, radius, map_cloud_, cropped) (localization_node.cpp:302) on the
+ * resident map: same points, same order (ascending distance, ties by index) as ssf_cloud_crop_radius, with no
+ * upload.  xyz_out (n x float4) / indices_out optional (NULL: count only). */
+int ssf_map_crop_radius(ssf_map *map, const float center[3], double radius, float *xyz_out, size_t cap_points,
+                        size_t *n_out, int32_t *indices_out);
+/* The re-crop of localization_node.cpp:300-305 -- crop, then icp_->setTargetPointCloud(cropped) -- entirely in
+ * HBM: a window change of the resident map, no 16 B/point round trip through the host. */
+int ssf_map_crop_to_target(ssf_map *map, ssf_icp *icp, const float center[3], double radius, size_t *n_out);
 
 /* ---- brute-force pose-grid alignment (localization/src/brute_force_alignment.cpp) ------------- */
 /* setXYZStep / setXYZRange / setRotationStep / setRotationRange / setMeanErrorThreshold

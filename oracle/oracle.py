@@ -214,6 +214,17 @@ def voxel_grid(xyz, leaf: float):
     return out[:n].copy(), bool(st.value)
 
 
+def voxel_grid_o3d(xyz, voxel: float) -> np.ndarray:
+    """open3d voxel_down_sample semantics (double arithmetic, origin min_bound - voxel / 2); (n_out, 3) float32."""
+    a = _f32(xyz, (3, 4))
+    out = np.empty((max(1, a.shape[0]), 4), np.float32)
+    L = lib()
+    L.ssf_oracle_voxel_grid_o3d.restype = ctypes.c_int64
+    L.ssf_oracle_voxel_grid_o3d.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
+    n = L.ssf_oracle_voxel_grid_o3d(a.ctypes.data, a.shape[0], a.shape[1], float(voxel), out.ctypes.data)
+    return out[:n, :3].copy()
+
+
 def _preproc_setup():
     L = lib()
     if not getattr(L, "_preproc_ready", False):

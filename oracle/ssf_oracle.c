@@ -987,6 +987,67 @@ int64_t ssf_oracle_voxel_grid(const float *in, int64_t n, int stride, float leaf
     return n_out;
 }
 
+/* open3d::geometry::PointCloud::VoxelDownSample (localization_python/.../localization_node.py:47)  [ext]:
+ * origin = min_bound - voxel / 2, index = floor((p - origin) / voxel) per axis, AccumulatedPoint per voxel
+ * (points added in input order), centroid = sum / count -- all in double.  Open3D iterates an
+ * unordered_map for the output; the contract is ascending (z, y, x) voxel index.  Output float4 rows
+ * (centroid rounded to float).  Returns the number of output points. */
+typedef struct { uint64_t idx; int32_t pt; } vox64_pair_t;
+static int vox64_cmp(const void *a, const void *b)
+{
+    const vox64_pair_t *x = (const vox64_pair_t *)a, *y = (const vox64_pair_t *)b;
+    if (x->idx != y->idx) return x->idx < y->idx ? -1 : 1;
+    return x->pt < y->pt ? -1 : (x->pt > y->pt ? 1 : 0);
+}
+
+int64_t ssf_oracle_voxel_grid_o3d(const float *in, int64_t n, int stride, double voxel, float *out)
+{
+    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    int64_t n_finite = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float *p = in + i * stride;
+        if (!isfinite(p[0]) || !isfinite(p[1]) || !isfinite(p[2])) continue;
+        ++n_finite;
+        for (int k = 0; k < 3; ++k) { if (p[k] < mn[k]) mn[k] = p[k]; if (p[k] > mx[k]) mx[k] = p[k]; }
+    }
+    if (n_finite == 0) return 0;
+    double b[3];
+    uint64_t d[3];
+    for (int k = 0; k < 3; ++k) { b[k] = mn[k] - voxel * 0.5; d[k] = (uint64_t)floor((mx[k] - b[k]) / voxel) + 1u; }
+    vox64_pair_t *pairs = (vox64_pair_t *)malloc(sizeof(vox64_pair_t) * (size_t)n_finite);
+    int64_t m = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const float *p = in + i * stride;
+        if (!isfinite(p[0]) || !isfinite(p[1]) || !isfinite(p[2])) continue;
+        const uint64_t i0 = (uint64_t)(int64_t)floor(((double)p[0] - b[0]) / voxel);
+        const uint64_t i1 = (uint64_t)(int64_t)floor(((double)p[1] - b[1]) / voxel);
+        const uint64_t i2 = (uint64_t)(int64_t)floor(((double)p[2] - b[2]) / voxel);
+        pairs[m].idx = i0 + i1 * d[0] + i2 * d[0] * d[1];
+        pairs[m].pt = (int32_t)i;
+        ++m;
+    }
+    qsort(pairs, (size_t)m, sizeof(vox64_pair_t), vox64_cmp);
+    int64_t n_out = 0, i = 0;
+    while (i < m) {
+        int64_t j = i;
+        double c[3] = {0, 0, 0};
+        while (j < m && pairs[j].idx == pairs[i].idx) {
+            const float *p = in + (int64_t)pairs[j].pt * stride;
+            c[0] += p[0]; c[1] += p[1]; c[2] += p[2];
+            ++j;
+        }
+        const double cnt = (double)(j - i);
+        out[4 * n_out + 0] = (float)(c[0] / cnt);
+        out[4 * n_out + 1] = (float)(c[1] / cnt);
+        out[4 * n_out + 2] = (float)(c[2] / cnt);
+        out[4 * n_out + 3] = 1.0f;
+        ++n_out;
+        i = j;
+    }
+    free(pairs);
+    return n_out;
+}
+
 /* ======================================================================================
  * 6. Cloud pre-processing, reference localization/include/localization/point_cloud_processing.hpp.
  *    Outputs are float4 rows (x, y, z, 1); each function returns the number of rows written.

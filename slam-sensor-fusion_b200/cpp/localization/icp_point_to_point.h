@@ -28,34 +28,7 @@
 
 #include <Eigen/Core>
 #else
-namespace pcl {
-struct alignas(16) PointXYZ {
-    float x, y, z, data_pad;
-    PointXYZ() : x(0), y(0), z(0), data_pad(1.f) {}
-    PointXYZ(float x_, float y_, float z_) : x(x_), y(y_), z(z_), data_pad(1.f) {}
-};
-template <class P>
-struct PointCloud {
-    using Ptr = std::shared_ptr<PointCloud<P>>;
-    std::vector<P> points;
-    std::size_t size() const { return points.size(); }
-};
-}  // namespace pcl
-namespace Eigen {
-struct Matrix4f {  // column-major like Eigen
-    float m[16];
-    static Matrix4f Identity()
-    {
-        Matrix4f r;
-        for (int i = 0; i < 16; ++i) r.m[i] = (i % 5 == 0) ? 1.f : 0.f;
-        return r;
-    }
-    float &operator()(int r, int c) { return m[c * 4 + r]; }
-    float operator()(int r, int c) const { return m[c * 4 + r]; }
-    const float *data() const { return m; }
-    float *data() { return m; }
-};
-}  // namespace Eigen
+#include <localization/ssf_standalone_types.h>
 #endif
 
 using PointT = pcl::PointXYZ;
@@ -69,7 +42,7 @@ struct ICPResult {
     bool has_converged = false;
 
     ICPResult() = default;
-    explicit ICPResult(const Eigen::Matrix4f &T) : transformation(T) {}
+    ICPResult(const Eigen::Matrix4f &T) : transformation(T) {}  // implicit, like the reference (h:32)
     ICPResult(const Eigen::Matrix4f &T, float err, int its, bool converged)
         : transformation(T), error(err), iterations(its), has_converged(converged)
     {
@@ -166,8 +139,11 @@ public:
         return out;
     }
 
-    /// Extras the reference does not have: diagnostics of the last alignment.
+    /// Extras the reference does not have: diagnostics of the last alignment, and the C handle (for
+    /// ssf::ResidentMap::cropToTarget and ssf_batch_*).  An ICPPointToPoint and the free functions of
+    /// point_cloud_processing.hpp may sit on different contexts of the same device.
     const ssf_icp_result &lastDeviceResult() const { return last_; }
+    ssf_icp *handle() const { return icp_; }
 
 private:
     static int envInt(const char *name, int dflt)

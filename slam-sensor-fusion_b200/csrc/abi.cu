@@ -12,6 +12,7 @@
 
 #include "bfa.cuh"
 #include "icp.cuh"
+#include "ingest.cuh"
 #include "map_index.cuh"
 #include "nccl_link.cuh"
 #include "preprocess.cuh"
@@ -269,6 +270,15 @@ static int upload_cloud(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_
     return SSF_OK;
 }
 
+// ---- access for ingest.cu ---------------------------------------------------------------------------
+int ssf::ssf_ctx_ref::use() const { return use_device(c); }
+cudaStream_t ssf::ssf_ctx_ref::stream() const { return c->stream; }
+ssf::Scratch &ssf::ssf_ctx_ref::scratch() const { return c->scratch; }
+int ssf::ssf_ctx_ref::upload_cloud(const float *xyz, size_t n, size_t stride_bytes, float4 *dst) const
+{
+    return ::upload_cloud(c, xyz, n, stride_bytes, dst);
+}
+
 // ---- registration object ------------------------------------------------------------------------
 extern "C" int ssf_icp_create(ssf_ctx *ctx, const ssf_icp_params *params, ssf_icp **out)
 {
@@ -340,6 +350,30 @@ extern "C" int ssf_icp_set_target(ssf_icp *icp, const float *xyz, size_t n, size
         SSF_TRY(upload_cloud(ctx, normals, n, normals_stride_bytes, m.raw_nrm.p));
     }
     // the cell edge is chosen from the cloud's own density (map_build.cu), not from the threshold
+    SSF_TRY(build_map_index(m, 0.f, ctx->scratch, ctx->stream));
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    icp->has_target = true;
+    return SSF_OK;
+}
+
+int ssf::icp_set_target_device(ssf_icp *icp, const float4 *pts_dev, size_t n, const ssf_ctx_ref &from)
+{
+    SSF_ARG(icp && (pts_dev || n == 0), "set target from device: NULL argument");
+    SSF_ARG(n < ((size_t)1 << 31), "set target from device: more than 2^31 - 1 points");
+    ssf_ctx *ctx = icp->ctx;
+    SSF_ARG(from.c->device == ctx->device, "the resident map and the registration object are on different devices");
+    SSF_TRY(use_device(ctx));
+    icp->has_target = false;
+    MapIndex &m = icp->map;
+    m.sharded = false;
+    m.has_global_index = false;
+    m.own_lo = INT32_MIN;
+    m.own_hi = INT32_MAX;
+    m.n_raw = n;
+    m.has_normals = false;
+    SSF_TRY(m.raw.reserve(n ? n : 1));
+    if (from.c->stream != ctx->stream) SSF_CUDA(cudaStreamSynchronize(from.c->stream));  // the crop is complete
+    if (n) SSF_CUDA(cudaMemcpyAsync(m.raw.p, pts_dev, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
     SSF_TRY(build_map_index(m, 0.f, ctx->scratch, ctx->stream));
     SSF_CUDA(cudaStreamSynchronize(ctx->stream));
     icp->has_target = true;
@@ -715,6 +749,28 @@ extern "C" int ssf_voxel_downsample(ssf_ctx *ctx, const float *xyz, size_t n, si
     SSF_CUDA(cudaStreamSynchronize(ctx->stream));
     *n_out = cnt;
     if (refused) *refused = ref;
+    return SSF_OK;
+}
+
+extern "C" int ssf_voxel_downsample_o3d(ssf_ctx *ctx, const float *xyz, size_t n, size_t stride_bytes, double voxel_size,
+                                        float *out, size_t *n_out)
+{
+    SSF_ARG(ctx && n_out, "ssf_voxel_downsample_o3d: NULL argument");
+    SSF_ARG(n == 0 || (xyz && out), "ssf_voxel_downsample_o3d: NULL cloud");
+    SSF_ARG(voxel_size > 0.0 && std::isfinite(voxel_size), "ssf_voxel_downsample_o3d: voxel_size must be > 0");
+    SSF_ARG(n < ((size_t)1 << 31), "ssf_voxel_downsample_o3d: more than 2^31 - 1 points");
+    *n_out = 0;
+    if (n == 0) return SSF_OK;
+    SSF_TRY(use_device(ctx));
+    VoxelWork w;
+    SSF_TRY(w.in.reserve(n));
+    SSF_TRY(w.out.reserve(n));
+    SSF_TRY(upload_cloud(ctx, xyz, n, stride_bytes, w.in.p));
+    uint32_t cnt = 0;
+    SSF_TRY(voxel_downsample_o3d_device(w, n, voxel_size, ctx->scratch, ctx->stream, &cnt));
+    SSF_CUDA(cudaMemcpyAsync(out, w.out.p, (size_t)cnt * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    SSF_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_out = cnt;
     return SSF_OK;
 }
 

@@ -73,6 +73,98 @@ static int bit_width_u64(unsigned long long v)
     return b;
 }
 
+// ---- Open3D semantics (the Python node's pcd.voxel_down_sample, localization_node.py:47) -----------------
+// open3d::geometry::PointCloud::VoxelDownSample [ext]: voxel_min_bound = min_bound - voxel_size / 2,
+// index = floor((p - voxel_min_bound) / voxel_size) per axis, everything in double; one AccumulatedPoint per
+// occupied voxel, points added in input order, centroid = sum / count in double.  Open3D returns the voxels
+// in unordered_map iteration order (unspecified): the contract here is ascending (z, y, x) voxel index.
+__global__ void __launch_bounds__(256)
+    voxel_keys_o3d_kernel(const float4 *__restrict__ in, uint32_t n, double bx, double by, double bz, double v,
+                          unsigned long long dvx, unsigned long long dvy, unsigned long long sentinel,
+                          unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = in[i];
+    unsigned long long k = sentinel;
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        const long long i0 = (long long)floor(__ddiv_rn(__dsub_rn((double)p.x, bx), v));
+        const long long i1 = (long long)floor(__ddiv_rn(__dsub_rn((double)p.y, by), v));
+        const long long i2 = (long long)floor(__ddiv_rn(__dsub_rn((double)p.z, bz), v));
+        k = (unsigned long long)i0 + (unsigned long long)i1 * dvx + (unsigned long long)i2 * dvx * dvy;
+    }
+    keys[i] = k;
+    vals[i] = i;
+}
+
+__global__ void __launch_bounds__(128)
+    voxel_centroid_o3d_kernel(const float4 *__restrict__ in, const unsigned long long *__restrict__ keys,
+                              const uint32_t *__restrict__ vals, const uint32_t *__restrict__ flags,
+                              const uint32_t *__restrict__ scan, uint32_t n_finite, float4 *__restrict__ out)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_finite || !flags[j]) return;
+    const unsigned long long k = keys[j];
+    double cx = 0.0, cy = 0.0, cz = 0.0;
+    uint32_t e = j;
+    while (e < n_finite && keys[e] == k) {
+        const float4 p = in[vals[e]];
+        cx = __dadd_rn(cx, (double)p.x);
+        cy = __dadd_rn(cy, (double)p.y);
+        cz = __dadd_rn(cz, (double)p.z);
+        ++e;
+    }
+    const double cnt = (double)(e - j);
+    out[scan[j]] = make_float4((float)__ddiv_rn(cx, cnt), (float)__ddiv_rn(cy, cnt), (float)__ddiv_rn(cz, cnt), 1.0f);
+}
+
+int voxel_downsample_o3d_device(VoxelWork &w, size_t n, double voxel, Scratch &s, cudaStream_t st, uint32_t *n_out)
+{
+    *n_out = 0;
+    if (n == 0) return SSF_OK;
+    SSF_TRY(w.small.reserve(16));
+    float *bbox_dev = w.small.p;
+    uint32_t *cnt_dev = reinterpret_cast<uint32_t *>(w.small.p + 8);
+    SSF_TRY(bbox_finite(w.in.p, n, bbox_dev, cnt_dev, st));
+    float hb[6];
+    uint32_t n_finite = 0;
+    SSF_CUDA(cudaMemcpyAsync(hb, bbox_dev, sizeof(hb), cudaMemcpyDeviceToHost, st));
+    SSF_CUDA(cudaMemcpyAsync(&n_finite, cnt_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SSF_CUDA(cudaStreamSynchronize(st));
+    if (n_finite == 0) return SSF_OK;
+    double b[3];
+    unsigned long long d[3];
+    for (int k = 0; k < 3; ++k) {
+        b[k] = (double)hb[k] - voxel * 0.5;
+        d[k] = (unsigned long long)floor(((double)hb[3 + k] - b[k]) / voxel) + 1ull;
+    }
+    const double cells = (double)d[0] * (double)d[1] * (double)d[2];
+    if (!(cells < 9.0e18)) {
+        set_error("voxel_down_sample: voxel size %g is too small for the cloud's extent", voxel);
+        return SSF_ERR_INVALID;
+    }
+    const unsigned long long sentinel = d[0] * d[1] * d[2];
+    SSF_TRY(w.keys.reserve(n));
+    SSF_TRY(w.vals.reserve(n));
+    SSF_TRY(w.flags.reserve(n));
+    SSF_TRY(w.scan.reserve(n));
+    voxel_keys_o3d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.in.p, (uint32_t)n, b[0], b[1], b[2], voxel, d[0], d[1],
+                                                                       sentinel, w.keys.p, w.vals.p);
+    SSF_LAUNCHED();
+    SSF_TRY(radix_sort_pairs_u64(w.keys.p, w.vals.p, n, bit_width_u64(sentinel), s, st));
+    voxel_flags_kernel<<<(n_finite + 255) / 256, 256, 0, st>>>(w.keys.p, n_finite, w.flags.p);
+    SSF_LAUNCHED();
+    SSF_TRY(exclusive_scan_u32(w.flags.p, w.scan.p, n_finite, cnt_dev + 1, s, st));
+    voxel_centroid_o3d_kernel<<<(n_finite + 127) / 128, 128, 0, st>>>(w.in.p, w.keys.p, w.vals.p, w.flags.p, w.scan.p,
+                                                                     n_finite, w.out.p);
+    SSF_LAUNCHED();
+    uint32_t cnt = 0;
+    SSF_CUDA(cudaMemcpyAsync(&cnt, cnt_dev + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SSF_CUDA(cudaStreamSynchronize(st));
+    *n_out = cnt;
+    return SSF_OK;
+}
+
 int voxel_downsample_device(VoxelWork &w, size_t n, float leaf, Scratch &s, cudaStream_t st, uint32_t *n_out,
                             int *refused)
 {

@@ -17,6 +17,9 @@ struct VoxelWork {
 int voxel_downsample_device(VoxelWork &w, size_t n, float leaf, Scratch &s, cudaStream_t st, uint32_t *n_out,
                             int *refused);
 
+// Open3D semantics (double arithmetic, origin min_bound - voxel / 2): see voxel_grid.cu
+int voxel_downsample_o3d_device(VoxelWork &w, size_t n, double voxel, Scratch &s, cudaStream_t st, uint32_t *n_out);
+
 // Batched form: every scan of the batch (raw points in b.raw, tile-aligned slots, raw counts in
 // meta[5*s + 1]) is downsampled with ONE segmented sort; centroids land in b.src at the scan's
 // slots and ScanState::n_pts is set to the centroid count.  No host synchronisation.

@@ -21,7 +21,8 @@ from . import capi
 from .capi import (MODE_GN_P2P, MODE_GN_P2PLANE, MODE_O3D_P2P, MODE_REFERENCE, REDUCE_FAST, REDUCE_STRICT, IcpParams,
                    IcpResult, SsfError)
 
-__all__ = ["Context", "ICPPointToPoint", "ICPResult", "Batch", "registration_icp", "voxel_down_sample",
+__all__ = ["Context", "ICPPointToPoint", "ICPResult", "Batch", "ResidentMap", "from_pointcloud2", "nccl_unique_id",
+           "registration_icp", "voxel_down_sample",
            "RegistrationResult", "BruteForceAlignment", "applyUniformSubsample", "removeFloor", "cropPointCloudThroughRadius", "ICPConvergenceCriteria", "TransformationEstimationPointToPoint",
            "TransformationEstimationPointToPlane", "SsfError", "default_context",
            "MODE_REFERENCE", "MODE_GN_P2P", "MODE_GN_P2PLANE", "MODE_O3D_P2P", "REDUCE_STRICT", "REDUCE_FAST"]
@@ -423,13 +424,22 @@ def registration_icp(source, target, max_correspondence_distance: float, init=No
                               r.has_converged)
 
 
-def voxel_down_sample(xyz, voxel_size: float, context: Context | None = None):
-    """Voxel-grid downsample with pcl::VoxelGrid semantics (global_map_frames_manager.cpp:143-146;
-    stands in for ``pcd.voxel_down_sample`` at localization_node.py:47).  Returns (M, 3) float32."""
+def voxel_down_sample(xyz, voxel_size: float, context: Context | None = None, semantics: str = "pcl"):
+    """Voxel-grid downsample on the device.  ``semantics="pcl"``: pcl::VoxelGrid (the C++ node's map merge,
+    global_map_frames_manager.cpp:143-146; also the scan downsample in front of the loop);
+    ``semantics="open3d"``: ``pcd.voxel_down_sample(voxel_size)`` of the Python node (localization_node.py:47) --
+    voxel origin ``min_bound - voxel_size / 2``, double centroids, output in ascending voxel index.
+    Returns (M, 3) float32."""
     ctx = context or default_context()
     c = _cloud(xyz)
     out = np.empty((max(1, c.shape[0]), 4), np.float32)
     n_out = ctypes.c_size_t(0)
+    if semantics == "open3d":
+        capi.check(capi.lib().ssf_voxel_downsample_o3d(ctx._h, c.ctypes.data, c.shape[0], c.strides[0], float(voxel_size),
+                                                       out.ctypes.data, ctypes.byref(n_out)))
+        return out[:n_out.value, :3].copy()
+    if semantics != "pcl":
+        raise ValueError("semantics must be 'pcl' or 'open3d'")
     refused = ctypes.c_int(0)
     capi.check(capi.lib().ssf_voxel_downsample(ctx._h, c.ctypes.data, c.shape[0], c.strides[0], voxel_size,
                                                out.ctypes.data, ctypes.byref(n_out), ctypes.byref(refused)))
@@ -472,6 +482,88 @@ def cropPointCloudThroughRadius(T, radius: float, cloud, context: Context | None
                                                 float(radius), out.ctypes.data, ctypes.byref(n_out), idx.ctypes.data))
     pts = out[:n_out.value, :3].copy()
     return (pts, idx[:n_out.value].copy()) if return_indices else pts
+
+
+def from_pointcloud2(data, n_points: int, point_step: int, offsets=(0, 4, 8), is_bigendian: bool = False,
+                     context: Context | None = None) -> np.ndarray:
+    """``pcl::fromROSMsg`` for the float32 x / y / z fields of a ``sensor_msgs/PointCloud2`` byte buffer
+    (localization_node.cpp:290-291): (n_points, 3) float32, extracted on the device."""
+    ctx = context or default_context()
+    buf = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    if buf.size < n_points * point_step:
+        raise ValueError("PointCloud2 data shorter than width * height * point_step")
+    out = np.empty((max(1, n_points), 4), np.float32)
+    capi.check(capi.lib().ssf_cloud_from_pointcloud2(ctx._h, buf.ctypes.data, n_points, point_step, offsets[0], offsets[1],
+                                                     offsets[2], 1 if is_bigendian else 0, out.ctypes.data))
+    return out[:n_points, :3].copy()
+
+
+class ResidentMap:
+    """The map cloud kept in HBM (``ssf_map``): uploaded -- or merged from the recorder's PCD tiles by
+    ``from_pcd_folder`` = ``GlobalMapFramesManager::getMapCloud`` (global_map_frames_manager.cpp:93-151) --
+    once; the re-crop of localization_node.cpp:300-305 is then ``crop_to_target`` (a window change in HBM)."""
+
+    def __init__(self, cloud=None, context: Context | None = None, _handle=None):
+        self._ctx = context or default_context()
+        self._h = ctypes.c_void_p()
+        if _handle is not None:
+            self._h = _handle
+        else:
+            c = _cloud(cloud)
+            capi.check(capi.lib().ssf_map_create(self._ctx._h, c.ctypes.data, c.shape[0], c.strides[0], ctypes.byref(self._h)))
+
+    @staticmethod
+    def from_pcd_folder(data_folder: str, map_name: str, voxel_size: float, save: bool = True,
+                        context: Context | None = None) -> "ResidentMap":
+        ctx = context or default_context()
+        h = ctypes.c_void_p()
+        capi.check(capi.lib().ssf_map_from_pcd_folder(ctx._h, data_folder.encode(), map_name.encode(), voxel_size,
+                                                      1 if save else 0, ctypes.byref(h)))
+        return ResidentMap(context=ctx, _handle=h)
+
+    def __len__(self) -> int:
+        return int(capi.lib().ssf_map_size(self._h))
+
+    @property
+    def ingest_ms(self) -> float:
+        return float(capi.lib().ssf_map_ingest_ms(self._h))
+
+    def download(self) -> np.ndarray:
+        out = np.empty((max(1, len(self)), 4), np.float32)
+        capi.check(capi.lib().ssf_map_download(self._h, out.ctypes.data, out.shape[0]))
+        return out[:len(self), :3].copy()
+
+    def subsample(self, point_step: int) -> None:
+        capi.check(capi.lib().ssf_map_subsample(self._h, point_step))
+
+    def crop(self, T, radius: float, return_indices: bool = False):
+        center = np.ascontiguousarray(np.asarray(T, np.float32)[:3, 3])
+        n = len(self)
+        out = np.empty((max(1, n), 4), np.float32)
+        idx = np.empty(max(1, n), np.int32)
+        n_out = ctypes.c_size_t(0)
+        capi.check(capi.lib().ssf_map_crop_radius(self._h, center.ctypes.data, float(radius), out.ctypes.data, n,
+                                                  ctypes.byref(n_out), idx.ctypes.data))
+        pts = out[:n_out.value, :3].copy()
+        return (pts, idx[:n_out.value].copy()) if return_indices else pts
+
+    def crop_to_target(self, icp: "ICPPointToPoint", T, radius: float) -> int:
+        """``cropPointCloudThroughRadius`` + ``setTargetPointCloud`` without leaving HBM; returns the target size."""
+        center = np.ascontiguousarray(np.asarray(T, np.float32)[:3, 3])
+        n_out = ctypes.c_size_t(0)
+        capi.check(capi.lib().ssf_map_crop_to_target(self._h, icp._h, center.ctypes.data, float(radius), ctypes.byref(n_out)))
+        return int(n_out.value)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            capi.lib().ssf_map_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 # ---- BruteForceAlignment (reference localization/include/localization/brute_force_alignment.h) ----
