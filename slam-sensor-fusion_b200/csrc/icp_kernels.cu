@@ -176,6 +176,13 @@ __global__ void __launch_bounds__(256) reset_rows_kernel(int32_t *__restrict__ c
     cert[i] = make_uint2(0u, 0xFFFFFFFFu);
 }
 
+// ... and no tile carries the stamp of an earlier run (or of whatever the allocation held before)
+__global__ void __launch_bounds__(256) reset_stamps_kernel(double *__restrict__ partials, uint32_t n_tiles)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_tiles) partials[(size_t)t * kAccum + (kAccum - 1)] = 0.0;
+}
+
 __global__ void zero_u32_kernel(uint32_t *p, uint32_t n)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1444,6 +1451,8 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
             tile_box_kernel<<<tiles, 128, 0, st>>>(b.src.p, b.tile_scan.p, S, b.tile_box.p);
             SSF_LAUNCHED();
             reset_rows_kernel<<<(unsigned)((b.n_slots + 255) / 256), 256, 0, st>>>(b.corr.p, b.cert.p, (uint32_t)b.n_slots);
+            SSF_LAUNCHED();
+            reset_stamps_kernel<<<(tiles + 255) / 256, 256, 0, st>>>(b.partials.p, tiles);
             SSF_LAUNCHED();
         }
         active_tiles_kernel<<<(scans * 32 + 127) / 128, 128, 0, st>>>(S, scans, shard, b.active.p, b.counters.p);

@@ -172,32 +172,40 @@ int extract_xyz_device(const unsigned char *raw_dev, size_t n, size_t point_byte
     return SSF_OK;
 }
 
-// whole file -> host buffer of packed records (binary: the file's own records; ascii: float32 x y z)
-static int read_pcd_records(const char *path, PcdHeader &h, std::vector<unsigned char> &rec)
+// bytes the records of a file take in a host buffer (binary: the file's own records; ascii: float32 x y z)
+static size_t pcd_record_bytes(const PcdHeader &h) { return h.n_points * (h.binary ? h.point_bytes : 12); }
+
+static int open_pcd(const char *path, PcdHeader &h, FILE **f_out)
 {
     FILE *f = fopen(path, "rb");
     if (!f) {
         set_error("%s: %s", path, strerror(errno));
         return SSF_ERR_INVALID;
     }
-    int rc = parse_pcd_header(f, path, h);
+    const int rc = parse_pcd_header(f, path, h);
     if (rc != SSF_OK) {
         fclose(f);
         return rc;
     }
+    *f_out = f;
+    return SSF_OK;
+}
+
+// the data section of an opened file -> dst (pcd_record_bytes(h) bytes; may be pinned memory); closes f.
+// After an ascii file h describes packed float32 x y z records.
+static int read_pcd_body(const char *path, PcdHeader &h, FILE *f, unsigned char *dst)
+{
     if (h.binary) {
-        rec.resize(h.n_points * h.point_bytes);
-        const size_t got = rec.empty() ? 0 : fread(rec.data(), 1, rec.size(), f);
+        const size_t want = h.n_points * h.point_bytes;
+        const size_t got = want ? fread(dst, 1, want, f) : 0;
         fclose(f);
-        if (got != rec.size()) {
-            set_error("%s: truncated (%zu of %zu data bytes)", path, got, rec.size());
+        if (got != want) {
+            set_error("%s: truncated (%zu of %zu data bytes)", path, got, want);
             return SSF_ERR_INVALID;
         }
         return SSF_OK;
     }
-    // ascii: one point per line, n_cols numbers
-    rec.resize(h.n_points * 12);
-    float *out = reinterpret_cast<float *>(rec.data());
+    float *out = reinterpret_cast<float *>(dst);  // ascii: one point per line, n_cols numbers
     std::vector<double> row((size_t)h.n_cols);
     for (size_t i = 0; i < h.n_points; ++i) {
         for (int c = 0; c < h.n_cols; ++c)
@@ -213,6 +221,14 @@ static int read_pcd_records(const char *path, PcdHeader &h, std::vector<unsigned
     h.off[0] = 0; h.off[1] = 4; h.off[2] = 8;
     h.size[0] = h.size[1] = h.size[2] = 4;
     return SSF_OK;
+}
+
+static int read_pcd_records(const char *path, PcdHeader &h, std::vector<unsigned char> &rec)
+{
+    FILE *f = nullptr;
+    SSF_TRY(open_pcd(path, h, &f));
+    rec.resize(pcd_record_bytes(h));
+    return read_pcd_body(path, h, f, rec.data());
 }
 
 }  // namespace ssf
@@ -362,19 +378,29 @@ extern "C" int ssf_map_from_pcd_folder(ssf_ctx *ctx, const char *data_folder, co
         closedir(dir);
         merged = true;
     }
-    // tiles -> pinned host -> HBM: every tile's records are extracted to float4 at its offset of ONE cloud
+    // tiles -> pinned host -> HBM: every tile's records are read straight into pinned memory and extracted
+    // to float4 at the tile's offset of ONE cloud
     std::vector<PcdHeader> heads(files.size());
-    std::vector<std::vector<unsigned char>> recs(files.size());
+    std::vector<FILE *> fps(files.size(), nullptr);
     size_t total = 0, max_bytes = 0;
+    auto close_all = [&] { for (FILE *f : fps) if (f) fclose(f); };
     for (size_t i = 0; i < files.size(); ++i) {
-        SSF_TRY(read_pcd_records(files[i].c_str(), heads[i], recs[i]));
+        const int rc0 = open_pcd(files[i].c_str(), heads[i], &fps[i]);
+        if (rc0 != SSF_OK) {
+            close_all();
+            return rc0;
+        }
         total += heads[i].n_points;
-        max_bytes = std::max(max_bytes, recs[i].size());
+        max_bytes = std::max(max_bytes, pcd_record_bytes(heads[i]));
     }
+    if (!(total < ((size_t)1 << 31))) close_all();
     ING_ARG(total < ((size_t)1 << 31), "ssf_map_from_pcd_folder: more than 2^31 - 1 points");
     ssf_map *m = new (std::nothrow) ssf_map{ssf_ctx_ref(ctx)};
-    if (!m) return SSF_ERR_NOMEM;
-    auto bail = [&](int rc) { delete m; return rc; };
+    if (!m) {
+        close_all();
+        return SSF_ERR_NOMEM;
+    }
+    auto bail = [&](int rc) { close_all(); delete m; return rc; };
     VoxelWork vw;
     DevBuf<float4> &cat = merged ? vw.in : m->w.in;
     int rc = cat.reserve(total ? total : 1);
@@ -395,9 +421,10 @@ extern "C" int ssf_map_from_pcd_folder(ssf_ctx *ctx, const char *data_folder, co
     for (size_t i = 0; i < files.size() && rc == SSF_OK; ++i) {  // double-buffered: the copy of tile i overlaps the staging of tile i + 1
         const int k = (int)(i & 1);
         if (i >= 2) cudaEventSynchronize(done[k]);
-        if (!recs[i].empty()) memcpy(pin[k].p, recs[i].data(), recs[i].size());
-        std::vector<unsigned char>().swap(recs[i]);
-        const PcdHeader &h = heads[i];
+        PcdHeader &h = heads[i];
+        rc = read_pcd_body(files[i].c_str(), h, fps[i], pin[k].p);
+        fps[i] = nullptr;
+        if (rc != SSF_OK) break;
         if (h.n_points) {
             if (cudaMemcpyAsync(stage[k].p, pin[k].p, h.n_points * h.point_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = SSF_ERR_CUDA;
             if (rc == SSF_OK)

@@ -133,7 +133,8 @@ def test_pointcloud2_extraction():
     rec["intensity"] = 7.0
     got = ssf_gpu.from_pointcloud2(rec.tobytes(), n, 32, (0, 4, 8))
     assert np.array_equal(got, xyz)
-    be = rec.astype(np.dtype({"names": ["x", "y", "z"], "formats": [">f4", ">f4", ">f4"], "offsets": [8, 0, 4], "itemsize": 16}))
+    be = np.zeros(n, np.dtype({"names": ["x", "y", "z"], "formats": [">f4", ">f4", ">f4"], "offsets": [8, 0, 4], "itemsize": 16}))
+    be["x"], be["y"], be["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
     got = ssf_gpu.from_pointcloud2(be.tobytes(), n, 16, (8, 0, 4), is_bigendian=True)
     assert np.array_equal(got, xyz)
 
