@@ -436,6 +436,15 @@ __device__ __forceinline__ void gn_gram(const MapView &map, const float4 *s_q, c
     if (s1 >= 0) row[s1] = c1;
 }
 
+// first index of the next chunk of 32 items of a list the warps of a block consume together (counter in
+// shared memory, one atomic per warp and chunk).  Collective: every lane of the warp calls it.
+__device__ __forceinline__ uint32_t warp_claim(uint32_t *counter)
+{
+    uint32_t base = 0;
+    if ((threadIdx.x & 31u) == 0) base = atomicAdd(counter, 32u);
+    return __shfl_sync(0xffffffffu, base, 0);
+}
+
 // Persistent blocks fetch tiles (kTile consecutive queries of one scan) from a shared counter;
 // every thread takes kQ queries of a tile.
 //   V  transform; with use_cert, try to confirm last iteration's neighbour from its certificate
@@ -467,6 +476,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
     float *const s_b2 = reinterpret_cast<float *>(s_raw + kTile * 8);
     uint32_t *const s_skip = reinterpret_cast<uint32_t *>(s_raw + kTile * 12);
     __shared__ uint32_t s_nq, s_nfar, s_nfar_none, s_next;
+    __shared__ uint32_t s_take[2];  // next unclaimed chunk of 32 queued queries: near walks, far walks
     __shared__ float sT[16];
     constexpr int kQ_ = kTile / THREADS;  // queries per thread
     __shared__ double sred[THREADS / 32][kAccum];
@@ -487,6 +497,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
             s_nq = 0;
             s_nfar = 0;
             s_nfar_none = 0;
+            s_take[0] = 0;
+            s_take[1] = 0;
         }
         __syncthreads();
         const uint32_t ti = s_next;
@@ -562,8 +574,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
         // ---- S: near part of the walk for every queued query; the few that must go on to rings 2..
         // are queued again and finished afterwards, packed densely, so that a warp is not held up
         // by the lanes that drew a far query ----
+        // (a warp claims the next 32 queued queries when it is through with its last ones: the walks differ
+        // in length, and a fixed share per warp left the others waiting at the barrier -- first launch of a
+        // 256-scan step 1.90 -> 1.46 ms.  Dropping the barrier between the two parts as well, with warps
+        // starting on a far list that is still being filled, was measured slower: 1.54 ms)
         const uint32_t nq = s_nq;
-        for (uint32_t i = threadIdx.x; i < nq; i += THREADS) {
+        for (uint32_t base = warp_claim(&s_take[0]); base < nq; base = warp_claim(&s_take[0])) {
+            const uint32_t i = base + (threadIdx.x & 31u);
+            if (i >= nq) continue;
             const uint32_t r = s_queue[i];
             SSF_CHECK(r < n_here);
             const float4 p = s_q[r];
@@ -594,7 +612,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
         }
         __syncthreads();
         const uint32_t nfar = s_nfar, nfar_none = s_nfar_none;
-        for (uint32_t i = threadIdx.x; i < nfar + nfar_none; i += THREADS) {
+        for (uint32_t base = warp_claim(&s_take[1]); base < nfar + nfar_none; base = warp_claim(&s_take[1])) {
+            const uint32_t i = base + (threadIdx.x & 31u);
+            if (i >= nfar + nfar_none) continue;
             const uint32_t r = i < nfar_none ? s_far[kTile - 1 - i] : s_far[i - nfar_none];
             const float4 p = s_q[r];
             if (make_cert) {
