@@ -1,6 +1,6 @@
 """Turn the outputs of profiles/run_ncu.sh (gpurun_out/) into the tracked summaries under profiles/.
-   python profiles/summarize.py v7 [scans_per_step]
-Writes profiles/r1/search_accum_<tag>_raw.csv (the ten K3 launches of one step, ncu --set full),
+   python profiles/summarize.py v8 [scans_per_step] [round-dir, default r2]
+Writes profiles/<round>/search_accum_<tag>_raw.csv (the ten K3 launches of one step, ncu --set full),
 copies the launch list, rewrites profiles/traffic.json and prints the markdown tables for SUMMARY.md."""
 import csv, collections, io, json, os, shutil, subprocess, sys
 
@@ -8,7 +8,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
 sps = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 out = os.path.join(ROOT, "gpurun_out")
-dst = os.path.join(ROOT, "profiles", "r1")
+rnd = sys.argv[3] if len(sys.argv) > 3 else "r2"
+dst = os.path.join(ROOT, "profiles", rnd)
+os.makedirs(dst, exist_ok=True)
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct",
            "l1tex__t_sector_hit_rate.pct", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -40,7 +42,7 @@ wr = next(t for t in table if t[0] == "dram__bytes_write.sum")
 per = [to_bytes(a, rd[1]) + to_bytes(b, wr[1]) for a, b in zip(rd[2:], wr[2:])]
 json.dump({"workload": "c2", "scans_per_step": sps, "kernel": "search_accum_kernel<GN_P2PLANE, 128>",
            "dram_bytes_per_launch": int(sum(per) / len(per)),
-           "source": f"profiles/r1/search_accum_{tag}_raw.csv: mean over the {len(per)} launches of one {sps}-scan step of "
+           "source": f"profiles/{rnd}/search_accum_{tag}_raw.csv: mean over the {len(per)} launches of one {sps}-scan step of "
                      "dram__bytes_read.sum + dram__bytes_write.sum (one ncu --set full capture, final build); per launch "
                      + str([round(p / 1e6, 1) for p in per]) + " MB"},
           open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
@@ -52,6 +54,8 @@ for t in table:
 
 # launch list: one step
 src = os.path.join(out, f"launches_{tag}_c2.csv")
+if not os.path.exists(src):
+    src = os.path.join(out, f"launches_{tag}.csv")
 shutil.copy(src, os.path.join(dst, f"launches_{tag}_c2.csv"))
 rows = list(csv.reader(open(src)))
 hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
