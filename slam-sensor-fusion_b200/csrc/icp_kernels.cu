@@ -622,13 +622,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
                 B.key = s_key[r]; B.pos = s_pos[r]; B.b2 = s_b2[r]; B.mu = map.cert_mu;
                 B.skip = s_skip[r];
                 B.refresh();
-                nn_walk_far<true>(map, p.x, p.y, p.z, B);
+                nn_walk_far_flat<true>(map, p.x, p.y, p.z, B);
                 s_key[r] = B.key; s_pos[r] = B.pos; s_b2[r] = B.b2;
             } else {
                 NNBest<false> B;
                 B.key = s_key[r]; B.pos = s_pos[r];
                 B.skip = kNoPos;
-                nn_walk_far<false>(map, p.x, p.y, p.z, B);
+                nn_walk_far_flat<false>(map, p.x, p.y, p.z, B);
                 s_key[r] = B.key; s_pos[r] = B.pos;
             }
         }
