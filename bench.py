@@ -84,7 +84,19 @@ def make_workload(name: str, n_scans: int, rank: int, world: int = 1, with_map: 
     seed_rank = 0 if w.get("sharded") else rank  # map-sharded: every rank registers the SAME scans against its shard
     t0 = time.time()
     m_points = w["map_points"] * (world if w.get("per_rank") else 1)
-    if with_map:
+    if with_map and w.get("sharded") and world > 1 and m_points >= 100_000_000:
+        # a map of hundreds of millions of points is synthesised ONCE (rank 0, all host threads) and handed to the
+        # other ranks as a memory-mapped file; every rank then cuts its own shard out of it (shard.shard_map)
+        path = os.path.join(os.environ.get("SSF_BENCH_TMP", "/tmp"), f"ssf_bench_map_{name}_{m_points}.npy")
+        if rank == 0:
+            xyz, nrm, half = synth.make_map(m_points, normals=False)
+            np.save(path + ".tmp.npy", xyz)
+            os.replace(path + ".tmp.npy", path)
+            del xyz
+        while not os.path.exists(path):
+            time.sleep(0.5)
+        xyz, nrm, half = np.load(path, mmap_mode="r"), None, synth.map_half_extent(m_points)[0]
+    elif with_map:
         xyz, nrm, half = synth.make_map(m_points, normals=w.get("normals", True))
     else:
         xyz, nrm, half = None, None, synth.map_half_extent(m_points)[0]

@@ -970,12 +970,18 @@ __global__ void __launch_bounds__(kTile)
 }
 
 // ---- ordered float chains (STRICT) ------------------------------------------------------------
-constexpr int kRefThreads = 512;  // warp 0 walks the chains, 15 warps stage the next tile's values
-constexpr int kChainTile = 1024;  // rows staged per buffer: long enough that staging the next one hides behind the chain
+// Two shapes of the one-block-per-scan kernel (RT threads, CT rows staged per buffer).  A block is bound by the
+// latency of its chain warp, so a batch's throughput is the number of RESIDENT blocks:
+//   512 threads, 1024 rows (74 KB): warp 0 walks the chains, 15 warps stage the next tile's values -- the
+//       staging of a tile hides behind its chain even for one scan alone; 2 blocks per SM (62 registers)
+//   256 threads, 704 rows (51 KB): 4 blocks per SM, for batches of more scans than 2 x SMs (the offline sequence)
+constexpr int kRefThreads = 512, kChainTile = 1024;
+constexpr int kRefThreadsNarrow = 256, kChainTileNarrow = 704;
 constexpr int kChainMax = 9;
 
+template <int CT>
 struct ChainBuf {
-    float v[2][kChainMax][kChainTile + 4];  // 16-byte aligned columns (the chain warp reads them with 128-bit loads)
+    float v[2][kChainMax][CT + 4];  // 16-byte aligned columns (the chain warp reads them with 128-bit loads)
 };
 
 // per-row values of the first pass: |p - q| (cpp:166), p (cpp:119), q (cpp:120)
@@ -1012,9 +1018,9 @@ __device__ __forceinline__ void rowvals_pass2(const float4 &p, const float4 &q, 
 
 // Sequential float sums of NCH per-row value streams over the rows of one scan, in row order.
 // Warp 0 walks the chains (lane = chain) while warps 1.. compute the next tile's values.
-template <int NCH, int PASS>
+template <int NCH, int PASS, int kRefThreads, int kChainTile>
 __device__ void strict_chains(const float4 *P, const float4 *Q, const int32_t *corr, size_t base, uint32_t n,
-                              const float *cs, const float *ct, ChainBuf &buf, float *out /*[NCH] in smem*/)
+                              const float *cs, const float *ct, ChainBuf<kChainTile> &buf, float *out /*[NCH] in smem*/)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_tiles = (n + kChainTile - 1) / kChainTile;
@@ -1093,7 +1099,7 @@ __device__ void strict_chains(const float4 *P, const float4 *Q, const int32_t *c
 }
 
 // ---- parallel double sums (FAST) ----------------------------------------------------------------
-template <int NV, int PASS>
+template <int NV, int PASS, int kRefThreads>
 __device__ void fast_sums(const float4 *P, const float4 *Q, const int32_t *corr, size_t base, uint32_t n,
                           const float *cs, const float *ct, double *scratch /*[kRefThreads]*/, float *out)
 {
@@ -1121,6 +1127,7 @@ __device__ void fast_sums(const float4 *P, const float4 *Q, const int32_t *corr,
     }
 }
 
+template <int kRefThreads>
 __device__ uint32_t block_count_alive(const int32_t *corr, size_t base, uint32_t n, uint32_t *scratch)
 {
     uint32_t c = 0;
@@ -1139,13 +1146,14 @@ __device__ uint32_t block_count_alive(const int32_t *corr, size_t base, uint32_t
 //   phase 0: after the pre-loop search (cpp:195-205), then falls through to phase 1 of pass 0
 //   phase 1: top of pass i  -- error, break test, re-search test, else Kabsch step (cpp:209-234)
 //   phase 2: after a re-search -- Kabsch step on the new correspondences (cpp:226-234)
-__global__ void __launch_bounds__(kRefThreads)
+template <int kRefThreads, int kChainTile>
+__global__ void __launch_bounds__(kRefThreads, kRefThreads == kRefThreadsNarrow ? 4 : 1)
     ref_reduce_kernel(ScanState *states, const float4 *__restrict__ P, const float4 *__restrict__ Q,
                       const int32_t *__restrict__ corr, int phase, int pass, int reduce, float acc_err, float eps,
                       float *trace_err, int32_t *trace_search, int trace_len)
 {
-    extern __shared__ __align__(16) unsigned char ref_dyn_smem[];  // 2 x 9 x 1025 floats: above the static limit
-    ChainBuf &buf = *reinterpret_cast<ChainBuf *>(ref_dyn_smem);
+    extern __shared__ __align__(16) unsigned char ref_dyn_smem[];  // 2 x 9 x (rows + 4) floats: above the static limit
+    ChainBuf<kChainTile> &buf = *reinterpret_cast<ChainBuf<kChainTile> *>(ref_dyn_smem);
     __shared__ double dscratch[kRefThreads];
     __shared__ uint32_t uscratch[kRefThreads / 32];
     __shared__ float sums1[7], sums2[9], cs[3], ct[3];
@@ -1157,7 +1165,7 @@ __global__ void __launch_bounds__(kRefThreads)
     const uint32_t n = z.n_pts;
     uint32_t K = 0;
     if (phase != 2 && threadIdx.x == 0) z.have_step = 0;  // the previous pass's step has been applied
-    if (phase != 1) K = block_count_alive(corr, base, n, uscratch);
+    if (phase != 1) K = block_count_alive<kRefThreads>(corr, base, n, uscratch);
     if (phase == 0) {
         if (threadIdx.x == 0) {
             z.n_searches = 1;
@@ -1183,8 +1191,8 @@ __global__ void __launch_bounds__(kRefThreads)
         if (K == 0) return;
     }
     // centroid / error chains (phase 1 needs the error; both need the centroids)
-    if (reduce == SSF_REDUCE_STRICT) strict_chains<7, 1>(P, Q, corr, base, n, nullptr, nullptr, buf, sums1);
-    else fast_sums<7, 1>(P, Q, corr, base, n, nullptr, nullptr, dscratch, sums1);
+    if (reduce == SSF_REDUCE_STRICT) strict_chains<7, 1, kRefThreads, kChainTile>(P, Q, corr, base, n, nullptr, nullptr, buf, sums1);
+    else fast_sums<7, 1, kRefThreads>(P, Q, corr, base, n, nullptr, nullptr, dscratch, sums1);
     if (threadIdx.x == 0) {
         s_action = 1;
         const float kf = (float)z.k_last;
@@ -1210,8 +1218,8 @@ __global__ void __launch_bounds__(kRefThreads)
     }
     __syncthreads();
     if (!s_action) return;
-    if (reduce == SSF_REDUCE_STRICT) strict_chains<9, 2>(P, Q, corr, base, n, cs, ct, buf, sums2);
-    else fast_sums<9, 2>(P, Q, corr, base, n, cs, ct, dscratch, sums2);
+    if (reduce == SSF_REDUCE_STRICT) strict_chains<9, 2, kRefThreads, kChainTile>(P, Q, corr, base, n, cs, ct, buf, sums2);
+    else fast_sums<9, 2, kRefThreads>(P, Q, corr, base, n, cs, ct, dscratch, sums2);
     if (threadIdx.x == 0) {
         float H[9], T_step[16];
         for (int i = 0; i < 9; ++i) H[i] = sums2[i];
@@ -1410,13 +1418,14 @@ static void launch_search(bool wide, unsigned grid, cudaStream_t st, const MapVi
                                                                        b.search_stats.p + 2 * pass);
 }
 
-static int search_grid(const BatchBuffers &b, unsigned *grid, bool *wide)
+static int search_grid(const BatchBuffers &b, unsigned *grid, bool *wide, int *sms)
 {
     // queried per call: contexts on different devices share this code (a process-wide cache would
     // pin the first device's count), and the attribute read costs well under a microsecond
     int n_sm = 0, dev = 0;
     SSF_CUDA(cudaGetDevice(&dev));
     SSF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    *sms = n_sm;
     // persistent blocks; sized by the batch CAPACITY so that the launch shape (and a captured graph)
     // does not change with the number of points of an upload -- surplus blocks fetch once and exit
     size_t g = (size_t)n_sm * 8u;
@@ -1429,7 +1438,7 @@ static int search_grid(const BatchBuffers &b, unsigned *grid, bool *wide)
 
 // the launches of one batch alignment (everything after the voxel stage), in stream order
 static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const float *T_init, bool certs,
-                         unsigned grid, bool wide, cudaStream_t st, SearchTimer *timer)
+                         unsigned grid, bool wide, int n_sm, cudaStream_t st, SearchTimer *timer)
 {
     SSF_TRY(init_states(b, T_init, st));
     const unsigned tiles = (unsigned)b.n_tiles, scans = (unsigned)b.n_scans;
@@ -1504,15 +1513,23 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
         uint32_t *pos_of = reinterpret_cast<uint32_t *>(b.cert.p);  // the certificate array is free in this mode
         TIMED_SEARCH((ref_search_kernel<<<tiles, kTile, 0, st>>>(map, b.src.p, b.P.p, b.Q.p, b.corr.p, pos_of, b.tile_scan.p,
                                                                 S, limit, 1)));
+        // ordered chains are the same sums in either shape; the double tree of FAST depends on the thread count,
+        // so only STRICT batches switch (a scan must give the same result alone and in a batch)
+        const bool narrow = cfg.reduce == SSF_REDUCE_STRICT && scans > 2u * (unsigned)n_sm;
+        auto reduce = [&](int phase, int pass) {
+            if (narrow)
+                ref_reduce_kernel<kRefThreadsNarrow, kChainTileNarrow><<<scans, kRefThreadsNarrow, sizeof(ChainBuf<kChainTileNarrow>), st>>>(
+                    S, b.P.p, b.Q.p, b.corr.p, phase, pass, cfg.reduce, cfg.acc_err, cfg.eps, b.trace_err.p, b.trace_search.p, b.trace_len);
+            else
+                ref_reduce_kernel<kRefThreads, kChainTile><<<scans, kRefThreads, sizeof(ChainBuf<kChainTile>), st>>>(
+                    S, b.P.p, b.Q.p, b.corr.p, phase, pass, cfg.reduce, cfg.acc_err, cfg.eps, b.trace_err.p, b.trace_search.p, b.trace_len);
+        };
         for (int i = 0; i < cfg.num_iterations; ++i) {
-            ref_reduce_kernel<<<scans, kRefThreads, sizeof(ChainBuf), st>>>(S, b.P.p, b.Q.p, b.corr.p, i == 0 ? 0 : 1, i, cfg.reduce,
-                                                             cfg.acc_err, cfg.eps, b.trace_err.p, b.trace_search.p,
-                                                             b.trace_len);
+            reduce(i == 0 ? 0 : 1, i);
             SSF_LAUNCHED();
             ref_search_kernel<<<tiles, kTile, 0, st>>>(map, b.src.p, b.P.p, b.Q.p, b.corr.p, pos_of, b.tile_scan.p, S, limit, 0);
             SSF_LAUNCHED();
-            ref_reduce_kernel<<<scans, kRefThreads, sizeof(ChainBuf), st>>>(S, b.P.p, b.Q.p, b.corr.p, 2, i, cfg.reduce, cfg.acc_err,
-                                                             cfg.eps, b.trace_err.p, b.trace_search.p, b.trace_len);
+            reduce(2, i);
             SSF_LAUNCHED();
             if (i + 1 < cfg.num_iterations) {
                 ref_step_kernel<<<tiles, kTile, 0, st>>>(b.P.p, b.corr.p, b.tile_scan.p, S);
@@ -1548,7 +1565,8 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
     const bool certs = !(nc && atoi(nc) != 0);
     unsigned grid = 1;
     bool wide = false;
-    SSF_TRY(search_grid(b, &grid, &wide));
+    int n_sm = 0;
+    SSF_TRY(search_grid(b, &grid, &wide, &n_sm));
     if (cfg.mode != SSF_MODE_REFERENCE) {  // allocations happen here, never inside a capture
         SSF_TRY(b.active.reserve(b.max_tiles ? b.max_tiles : 1));
         SSF_TRY(b.counters.reserve(2 * ((size_t)cfg.num_iterations + 1) + 2));
@@ -1560,7 +1578,10 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
     }
     if (cfg.mode == SSF_MODE_REFERENCE) {
         // function attributes are per device: set on every run (cheap) rather than once per process
-        SSF_CUDA(cudaFuncSetAttribute(ref_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ChainBuf)));
+        SSF_CUDA(cudaFuncSetAttribute(ref_reduce_kernel<kRefThreads, kChainTile>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(ChainBuf<kChainTile>)));
+        SSF_CUDA(cudaFuncSetAttribute(ref_reduce_kernel<kRefThreadsNarrow, kChainTileNarrow>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(ChainBuf<kChainTileNarrow>)));
         g_queries.fetch_add(b.n_slots, std::memory_order_relaxed);
     }
     const char *ng = getenv("SSF_NO_GRAPH");
@@ -1571,7 +1592,7 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
     if (!graphable) {
         if (cfg.mode != SSF_MODE_REFERENCE)
             g_queries.fetch_add((uint64_t)b.n_slots * (uint64_t)cfg.num_iterations, std::memory_order_relaxed);
-        return enqueue_batch(map, cfg, b, T_init, certs, grid, wide, st, timer);
+        return enqueue_batch(map, cfg, b, T_init, certs, grid, wide, n_sm, st, timer);
     }
 
     std::vector<unsigned long long> key;
@@ -1603,7 +1624,7 @@ int run_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers &b, const f
         cudaGraph_t graph = nullptr;
         SSF_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         const uint64_t before = g_launches.load();
-        const int rc = enqueue_batch(map, cfg, b, T_init, certs, grid, wide, st, nullptr);
+        const int rc = enqueue_batch(map, cfg, b, T_init, certs, grid, wide, n_sm, st, nullptr);
         const cudaError_t ce = cudaStreamEndCapture(st, &graph);
         b.graph_kernels = g_launches.load() - before;
         g_launches.fetch_sub(b.graph_kernels);  // counted when the graph is launched

@@ -129,6 +129,34 @@ def test_c4_reference_loop_bit_exact_on_5M_map(gpu, ora, big):
     assert np.array_equal(icp.correspondences(), ocorr)
 
 
+def test_offline_sequence_many_scans_bit_exact(gpu, ora, big):
+    """Config 4's shape in the many: more scans than two per SM switch the reference loop to its
+    4-blocks-per-SM shape (256 threads, 704-row stages).  The ordered chains are the same sums in either
+    shape: every scan of a 320-scan batch equals the same scan run in batches of 64, bit for bit, and the
+    oracle on a sample."""
+    from ssf_gpu import synth
+    icp = gpu.ICPPointToPoint(0.5, 10, 0.05, 1e-5, mode=gpu.MODE_REFERENCE, reduce=gpu.REDUCE_STRICT)
+    icp.setTargetPointCloud(big["map"])
+    scans, inits = [], []
+    for d in range(320):
+        T = synth.street_pose(9 * d + 2, half=big["half"])
+        scans.append(synth.make_scan(T, 16, 256, scan_id=5000 + d, max_range=60.0))
+        inits.append(synth.perturb_pose(T, 5000 + d))
+    many = icp.align_batch(scans, inits)
+    few = []
+    for a in range(0, 320, 64):
+        few += icp.align_batch(scans[a:a + 64], inits[a:a + 64])
+    for x, y in zip(many, few):
+        assert np.array_equal(x.transformation.view(np.uint32), y.transformation.view(np.uint32))
+        assert np.float32(x.error).view(np.uint32) == np.float32(y.error).view(np.uint32)
+        assert (x.iterations, x.n_searches, x.k_final, x.has_converged) == (y.iterations, y.n_searches, y.k_final,
+                                                                           y.has_converged)
+    for d in (0, 131, 319):
+        o, _, _ = ora.icp_reference(big["tree"], scans[d], inits[d], threads=8)
+        assert np.array_equal(many[d].transformation.view(np.uint32), o.T.view(np.uint32))
+        assert (many[d].iterations, many[d].n_searches, many[d].k_final) == (o.iterations, o.n_searches, o.k_final)
+
+
 def test_gpu_equals_reference_sources_directly(gpu, c1_world):
     """The CUDA path against oracle/_ref (the reference's own icp_point_to_point.cpp compiled unmodified),
     with no restatement in between: config 1 at full size, fine and coarse parameter sets."""
