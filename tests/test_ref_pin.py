@@ -175,3 +175,16 @@ def test_preprocessing_equals_ref(small_world):
     a = ref.crop_radius(np.eye(4), 10.0, ref.subsample(cloud, 2))
     b = oracle.crop_radius(np.eye(4), 10.0, oracle.subsample(cloud, 2))[0]
     assert np.array_equal(a, b)
+
+
+def test_golden_fixture_is_what_the_reference_sources_return():
+    """tests/golden/c1_mini.npz was generated by the oracle (tests/golden/make_golden.py); its reference-loop
+    entries are, bit for bit, what the reference's own unmodified icp_point_to_point.cpp returns for the
+    fixture's inputs with the node's fine parameters (localization_node.cpp:24-27)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_mini.npz"))
+    r, _ = _ref_icp(g["map"], g["scan"], g["T0"], FINE)
+    assert np.array_equal(r.T.view(np.uint32), g["ref_T"].view(np.uint32))
+    assert np.float32(r.error).view(np.uint32) == g["ref_error"].view(np.uint32)
+    assert r.iterations == int(g["ref_iterations"])
+
