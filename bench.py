@@ -89,7 +89,9 @@ def make_workload(name: str, n_scans: int, rank: int, world: int = 1, with_map: 
         # other ranks as a memory-mapped file; every rank then cuts its own shard out of it (shard.shard_map)
         path = os.path.join(os.environ.get("SSF_BENCH_TMP", "/tmp"), f"ssf_bench_map_{name}_{m_points}.npy")
         if rank == 0:
+            synth.set_threads(len(os.sched_getaffinity(0)))  # the other ranks only wait meanwhile
             xyz, nrm, half = synth.make_map(m_points, normals=False)
+            synth.set_threads(max(1, len(os.sched_getaffinity(0)) // world))
             np.save(path + ".tmp.npy", xyz)
             os.replace(path + ".tmp.npy", path)
             del xyz
@@ -833,6 +835,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+        # torchrun's default for its workers; the scan / map generator and the oracle are OpenMP code and would
+        # crawl on one thread: give every rank its share of the host cores (set before the libraries load)
+        os.environ["OMP_NUM_THREADS"] = str(max(1, len(os.sched_getaffinity(0)) // int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     if args.impl == "reference":
         run_cpu(args, rank, world)
         return

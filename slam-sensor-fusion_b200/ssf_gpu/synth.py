@@ -50,9 +50,26 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+# map_half_extent() of the sizes the bench uses (default seed and spacing): the search costs a dozen counting
+# passes over the candidate square, which matters at hundreds of millions of points
+_KNOWN_HALF = {1_000_000: 71.0, 5_000_000: 156.0, 50_000_000: 483.0, 125_000_000: 774.0, 250_000_000: 1092.0,
+               500_000_000: 1550.0}
+
+
+def set_threads(n: int) -> None:
+    """OpenMP threads of the generator (torchrun starts its workers with OMP_NUM_THREADS=1)."""
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(max(1, n)))
+    except OSError:
+        pass
+
+
 def map_half_extent(m_points: int, spacing: float = MAP_SPACING, seed: int = SEED_WORLD) -> tuple[float, int]:
     """Smallest half-extent (multiple of 1 m) whose candidate count reaches ``m_points``."""
     L = lib()
+    if spacing == MAP_SPACING and seed == SEED_WORLD and m_points in _KNOWN_HALF:
+        half = _KNOWN_HALF[m_points]
+        return half, int(L.ssf_synth_map_count(seed, half, spacing))
     lo, hi = 1.0, 8.0
     while L.ssf_synth_map_count(seed, hi, spacing) < m_points:
         lo, hi = hi, hi * 2.0

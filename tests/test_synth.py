@@ -37,3 +37,17 @@ def test_perturbation_ranges():
         d = np.linalg.inv(T) @ synth.perturb_pose(T, k)
         assert abs(d[0, 3]) <= 0.3 and abs(d[1, 3]) <= 0.3 and abs(d[2, 3]) <= 0.05
         assert abs(np.degrees(np.arctan2(d[1, 0], d[0, 0]))) <= 2.0
+
+
+def test_known_half_extents_match_the_search():
+    """The cached half extents (bench sizes) are what the counting search returns."""
+    from ssf_gpu import synth
+    for m in (1_000_000, 5_000_000):
+        cached = synth.map_half_extent(m)
+        known = dict(synth._KNOWN_HALF)
+        try:
+            synth._KNOWN_HALF.clear()
+            searched = synth.map_half_extent(m)
+        finally:
+            synth._KNOWN_HALF.update(known)
+        assert cached == searched
