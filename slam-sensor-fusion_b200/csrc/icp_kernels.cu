@@ -9,15 +9,17 @@
 //
 //   search_accum_kernel<KIND, THREADS>   persistent blocks over the tiles that hold points: TMA tile load,
 //                                         transform, certificate check or exact walk (near part, then the
-//                                         far rings packed densely), residual / Jacobian partial sums
+//                                         far rings packed densely; the warps of a block claim chunks of 32
+//                                         queued walks as they finish), residual / Jacobian partial sums
 //                                         (Gauss-Newton: an 8x8 Gram matrix on the FP64 tensor core, gn_gram)
 //   rowsum_solve_kernel                   ordered sum of a scan's partial rows + 6x6 Cholesky or 3x3 SVD +
-//                                         pose update + stop rules (map-sharded: rowsum_xchg / solve_xchg
-//                                         exchange the rows across ranks over peer memory, or rowsum_kernel
-//                                         + the caller's all-reduce hook + solve_kernel)
-//   ref_search_kernel / ref_reduce_kernel / ref_step_kernel   the reference's own state machine, STRICT
-//                                         (sequential float chains) or FAST
-//   run_batch                             the launch sequence; the GN / Open3D-flow loop as one CUDA graph
+//                                         pose update + stop rules (map-sharded: rowsum_xchg_solve_kernel
+//                                         exchanges the rows across ranks over peer memory inside the same
+//                                         launch; or rowsum_kernel + ncclAllReduce / the caller's hook +
+//                                         solve_kernel)
+//   ref_search_kernel / ref_reduce_kernel<RT, CT> / ref_step_kernel   the reference's own state machine,
+//                                         STRICT (sequential float chains) or FAST; two block shapes
+//   run_batch                             the launch sequence, captured once per shape into a CUDA graph
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -453,6 +455,9 @@ __device__ __forceinline__ uint32_t warp_claim(uint32_t *counter)
 //      new certificate;
 //   K4 residual / Jacobian terms of the matched queries: gn_gram (128-thread blocks, tensor core),
 //      gn_half x 2 (512-thread blocks) or the Kabsch moments with a 32-value warp transpose.
+// resident 128-thread blocks per SM (64 registers each).  Measured on the 256-scan step: 6 -> 40.3 k scans/s,
+// 7 -> 42.6 k, 8 -> 42.8 k, 9 (56 registers) -> 40.4 k, 10 (48 registers) -> 40.7 k: more blocks take shared
+// memory away from the L1 the gathers live in (converged launches 135 -> 169 us at 9)
 #ifndef SSF_MINB
 #define SSF_MINB 8
 #endif
@@ -1428,7 +1433,7 @@ static int search_grid(const BatchBuffers &b, unsigned *grid, bool *wide, int *s
     *sms = n_sm;
     // persistent blocks; sized by the batch CAPACITY so that the launch shape (and a captured graph)
     // does not change with the number of points of an upload -- surplus blocks fetch once and exit
-    size_t g = (size_t)n_sm * 8u;
+    size_t g = (size_t)n_sm * (size_t)SSF_MINB;
     *wide = b.max_tiles < 4u * g;  // fewer than four tiles per resident 128-thread block: latency matters
     if (*wide) g = (size_t)n_sm * 2u;  // 512-thread blocks, two per SM
     if (g > b.max_tiles) g = b.max_tiles;
