@@ -473,13 +473,15 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
     __shared__ __align__(128) float4 s_q[kTile];  // TMA destination; transformed in place, w = owned by this rank
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_pos[kTile];
-    __shared__ unsigned short s_queue[kTile], s_far[kTile];
-    // walk state per query; dead once the correspondences are written, when the same 8 KB hold the
-    // feature tiles of the Gauss-Newton Gram matrix (gram_round)
+    // walk state per query (running best, second-smallest d2) and the two work lists; all of it is dead
+    // once the correspondences are written, when the same 8 KB hold the feature tiles of the Gauss-Newton
+    // Gram matrix (gram_round).  Shared memory per block decides the L1 the walks and gathers live in:
+    // 8 blocks of < 19.5 KB fit the 164 KB carve-out (92 KB of L1 per SM); at 21.6 KB the driver took 196 KB
     __shared__ __align__(16) unsigned char s_raw[kTile * 16];
     unsigned long long *const s_key = reinterpret_cast<unsigned long long *>(s_raw);
     float *const s_b2 = reinterpret_cast<float *>(s_raw + kTile * 8);
-    uint32_t *const s_skip = reinterpret_cast<uint32_t *>(s_raw + kTile * 12);
+    unsigned short *const s_queue = reinterpret_cast<unsigned short *>(s_raw + kTile * 12);
+    unsigned short *const s_far = reinterpret_cast<unsigned short *>(s_raw + kTile * 14);
     __shared__ uint32_t s_nq, s_nfar, s_nfar_none, s_next;
     __shared__ uint32_t s_take[2];  // next unclaimed chunk of 32 queued queries: near walks, far walks
     __shared__ float sT[16];
@@ -603,7 +605,6 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
                 far = nn_walk_near<false>(map, p.x, p.y, p.z, limit, 0.f, B, s_pos[r]);
                 key = B.key; pos = B.pos;
             }
-            if (far) s_skip[r] = s_pos[r];  // (read before s_pos is overwritten)
             s_key[r] = key;
             s_pos[r] = pos;
             s_b2[r] = b2;
@@ -625,7 +626,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? SSF_MINB : 2)
             if (make_cert) {
                 NNBest<true> B;
                 B.key = s_key[r]; B.pos = s_pos[r]; B.b2 = s_b2[r]; B.mu = map.cert_mu;
-                B.skip = s_skip[r];
+                // the seed of the near part: last iteration's neighbour, still in the certificate array
+                B.skip = use_cert ? cert[slot0 + r].y : kNoPos;
                 B.refresh();
                 nn_walk_far_flat<true>(map, p.x, p.y, p.z, B);
                 s_key[r] = B.key; s_pos[r] = B.pos; s_b2[r] = B.b2;
