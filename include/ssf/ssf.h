@@ -193,7 +193,8 @@ int ssf_map_from_pcd_folder(ssf_ctx *ctx, const char *data_folder, const char *m
                             ssf_map **out);
 void ssf_map_destroy(ssf_map *map);
 size_t ssf_map_size(const ssf_map *map);
-double ssf_map_ingest_ms(const ssf_map *map); /* device ms of the last H2D + extract + voxel filter */
+double ssf_map_ingest_ms(const ssf_map *map); /* stream ms of the last tiles -> HBM -> voxel filter (includes waits for file reads) */
+double ssf_map_merge_ms(const ssf_map *map);  /* ... of which the voxel filter over the concatenated cloud (device ms) */
 int ssf_map_download(ssf_map *map, float *xyz_out /* n x float4 */, size_t cap_points);
 /* applyUniformSubsample(map_cloud_, step) (localization_node.cpp:20), in place in HBM. */
 int ssf_map_subsample(ssf_map *map, size_t point_step);

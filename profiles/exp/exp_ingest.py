@@ -20,6 +20,7 @@ with tempfile.TemporaryDirectory(dir=os.environ.get("SSF_BENCH_TMP", "/tmp")) as
         rm = ssf_gpu.ResidentMap.from_pcd_folder(d, "map", 0.1, save=False)
         wall = time.time() - t0
         gbs = 2 * 16 * M / (rm.ingest_ms * 1e-3) / 1e9
-        print(f"ingest: {M} points -> {len(rm)} voxels; device {rm.ingest_ms:.1f} ms ({gbs:.1f} GB/s against 2 x 16 x M), "
+        print(f"ingest: {M} points -> {len(rm)} voxels; stream {rm.ingest_ms:.1f} ms ({gbs:.1f} GB/s against 2 x 16 x M), of which "
+              f"the voxel filter {rm.merge_ms:.1f} ms ({2 * 16 * M / (rm.merge_ms * 1e-3) / 1e9:.0f} GB/s); "
               f"wall {wall:.2f}s incl. file reads ({M * 12 / wall / 1e9:.2f} GB/s of PCD)", flush=True)
         del rm

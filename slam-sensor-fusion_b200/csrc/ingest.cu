@@ -241,7 +241,8 @@ struct ssf_map {
     PreprocWork w;       // w.in = the resident cloud (float4), w.out / w.idx = the last crop
     size_t n = 0;
     uint32_t last_crop = 0;
-    double ingest_ms = 0.0;  // device time of the last merge + voxel filter
+    double ingest_ms = 0.0;  // stream time of the last tiles -> HBM -> merge (includes waiting for the host's file reads)
+    double merge_ms = 0.0;   // ... of which the voxel filter over the concatenated cloud
 };
 
 #define ING_ARG(cond, msg)                 \
@@ -350,6 +351,7 @@ extern "C" void ssf_map_destroy(ssf_map *m)
 
 extern "C" size_t ssf_map_size(const ssf_map *m) { return m ? m->n : 0; }
 extern "C" double ssf_map_ingest_ms(const ssf_map *m) { return m ? m->ingest_ms : 0.0; }
+extern "C" double ssf_map_merge_ms(const ssf_map *m) { return m ? m->merge_ms : 0.0; }
 
 // getMapCloud / mergeScansAndSave (global_map_frames_manager.cpp:93-151)
 extern "C" int ssf_map_from_pcd_folder(ssf_ctx *ctx, const char *data_folder, const char *map_name, float voxel_size,
@@ -407,7 +409,7 @@ extern "C" int ssf_map_from_pcd_folder(ssf_ctx *ctx, const char *data_folder, co
     if (rc != SSF_OK) return bail(rc);
     PinnedBuf<unsigned char> pin[2];
     DevBuf<unsigned char> stage[2];
-    cudaEvent_t done[2] = {nullptr, nullptr}, e0 = nullptr, e1 = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr}, e0 = nullptr, e1 = nullptr, ev = nullptr;
     for (int k = 0; k < 2; ++k) {
         if ((rc = pin[k].reserve(max_bytes ? max_bytes : 1)) != SSF_OK) return bail(rc);
         if ((rc = stage[k].reserve(max_bytes ? max_bytes : 1)) != SSF_OK) return bail(rc);
@@ -415,6 +417,7 @@ extern "C" int ssf_map_from_pcd_folder(ssf_ctx *ctx, const char *data_folder, co
     }
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
+    cudaEventCreate(&ev);
     cudaStream_t st = c.stream();
     cudaEventRecord(e0, st);
     size_t at = 0;
@@ -435,6 +438,7 @@ extern "C" int ssf_map_from_pcd_folder(ssf_ctx *ctx, const char *data_folder, co
         at += h.n_points;
     }
     uint32_t n_out = (uint32_t)total;
+    cudaEventRecord(ev, st);
     if (rc == SSF_OK && merged && total > 0) {  // :143-146 pcl::VoxelGrid(voxel_size)
         int refused = 0;
         rc = vw.out.reserve(total);
@@ -446,17 +450,20 @@ extern "C" int ssf_map_from_pcd_folder(ssf_ctx *ctx, const char *data_folder, co
     }
     cudaEventRecord(e1, st);
     if (rc == SSF_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = SSF_ERR_CUDA;
-    float ms = 0.f;
+    float ms = 0.f, ms_merge = 0.f;
     if (rc == SSF_OK) cudaEventElapsedTime(&ms, e0, e1);
+    if (rc == SSF_OK) cudaEventElapsedTime(&ms_merge, ev, e1);
     for (int k = 0; k < 2; ++k) cudaEventDestroy(done[k]);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    cudaEventDestroy(ev);
     if (rc != SSF_OK) {
         if (rc == SSF_ERR_CUDA) set_error("ssf_map_from_pcd_folder: CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
         return bail(rc);
     }
     m->n = n_out;
     m->ingest_ms = ms;
+    m->merge_ms = ms_merge;
     if ((rc = m->w.out.reserve(m->n ? m->n : 1)) != SSF_OK) return bail(rc);
     if (merged && save) {  // :148 savePCDFileBinary(<folder>/<map_name>.pcd)
         std::vector<float> host((size_t)n_out * 4);

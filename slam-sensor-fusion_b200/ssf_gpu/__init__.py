@@ -528,6 +528,11 @@ class ResidentMap:
     def ingest_ms(self) -> float:
         return float(capi.lib().ssf_map_ingest_ms(self._h))
 
+    @property
+    def merge_ms(self) -> float:
+        """Device ms of the voxel filter over the concatenated tiles (part of ``ingest_ms``)."""
+        return float(capi.lib().ssf_map_merge_ms(self._h))
+
     def download(self) -> np.ndarray:
         out = np.empty((max(1, len(self)), 4), np.float32)
         capi.check(capi.lib().ssf_map_download(self._h, out.ctypes.data, out.shape[0]))

@@ -18,7 +18,7 @@ EXPORTS = [
     "ssf_last_error", "ssf_version", "ssf_ctx_create", "ssf_ctx_destroy", "ssf_ctx_synchronize", "ssf_ctx_stream", "ssf_ctx_time_searches", "ssf_ctx_search_time", "ssf_ctx_search_times",
     "ssf_icp_create", "ssf_icp_destroy", "ssf_icp_set_params", "ssf_icp_get_params", "ssf_icp_set_target",
     "ssf_icp_set_source", "ssf_icp_set_initial", "ssf_icp_align", "ssf_icp_get_correspondences", "ssf_icp_get_trace",
-    "ssf_icp_target_size", "ssf_icp_set_target_shard", "ssf_icp_set_allreduce", "ssf_icp_exchange_create", "ssf_icp_exchange_open", "ssf_icp_exchange_close", "ssf_nccl_unique_id", "ssf_icp_nccl_init", "ssf_icp_nccl_close", "ssf_nn_search", "ssf_nn_search_bench", "ssf_voxel_downsample", "ssf_voxel_downsample_o3d", "ssf_pcd_read", "ssf_pcd_write_binary", "ssf_cloud_from_pointcloud2", "ssf_map_create", "ssf_map_from_pcd_folder", "ssf_map_destroy", "ssf_map_size", "ssf_map_ingest_ms", "ssf_map_download", "ssf_map_subsample", "ssf_map_crop_radius", "ssf_map_crop_to_target", "ssf_cloud_subsample", "ssf_cloud_remove_floor", "ssf_cloud_crop_radius", "ssf_bfa_pose_count", "ssf_bfa_align", "ssf_batch_create", "ssf_batch_destroy",
+    "ssf_icp_target_size", "ssf_icp_set_target_shard", "ssf_icp_set_allreduce", "ssf_icp_exchange_create", "ssf_icp_exchange_open", "ssf_icp_exchange_close", "ssf_nccl_unique_id", "ssf_icp_nccl_init", "ssf_icp_nccl_close", "ssf_nn_search", "ssf_nn_search_bench", "ssf_voxel_downsample", "ssf_voxel_downsample_o3d", "ssf_pcd_read", "ssf_pcd_write_binary", "ssf_cloud_from_pointcloud2", "ssf_map_create", "ssf_map_from_pcd_folder", "ssf_map_destroy", "ssf_map_size", "ssf_map_ingest_ms", "ssf_map_merge_ms", "ssf_map_download", "ssf_map_subsample", "ssf_map_crop_radius", "ssf_map_crop_to_target", "ssf_cloud_subsample", "ssf_cloud_remove_floor", "ssf_cloud_crop_radius", "ssf_bfa_pose_count", "ssf_bfa_align", "ssf_batch_create", "ssf_batch_destroy",
     "ssf_batch_upload", "ssf_batch_upload_async", "ssf_batch_set_initial", "ssf_batch_run", "ssf_batch_results", "ssf_batch_search_stats", "ssf_icp_align_batch",
     "ssf_kernel_launches", "ssf_nn_queries",
 ]
@@ -108,6 +108,8 @@ def lib() -> ctypes.CDLL:
     L.ssf_map_size.restype = sz
     L.ssf_map_ingest_ms.argtypes = [vp]
     L.ssf_map_ingest_ms.restype = ctypes.c_double
+    L.ssf_map_merge_ms.argtypes = [vp]
+    L.ssf_map_merge_ms.restype = ctypes.c_double
     L.ssf_map_download.argtypes = [vp, vp, sz]
     L.ssf_map_subsample.argtypes = [vp, sz]
     L.ssf_map_crop_radius.argtypes = [vp, vp, ctypes.c_double, vp, sz, P(sz), vp]
