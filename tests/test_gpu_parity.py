@@ -218,6 +218,28 @@ def test_o3d_flow(gpu, ora, small_world):
     assert r.correspondence_set.shape[0] == ores.k_final
 
 
+def test_o3d_flow_python_node_on_1M_map(gpu, ora, c1_world):
+    """The Python node's own call (localization_python/localization_python/localization_node.py:233-237:
+    registration_icp(scan, map, threshold, identity-composed prior, PointToPoint, max_iteration=30)) on config 1's
+    1M-point map, after the node's map voxel_down_sample(0.1) in Open3D semantics (:47), against the oracle's
+    Open3D-flow restatement."""
+    w = c1_world
+    m = gpu.voxel_down_sample(w["map"], 0.1, semantics="open3d")
+    om = ora.voxel_grid_o3d(w["map"], 0.1)
+    assert np.array_equal(m.view(np.uint32), om.view(np.uint32))
+    tree = ora.KdTree(om)
+    for thr in (0.5, 0.25):
+        ores, ofit, ocorr = ora.icp_o3d(tree, w["scan"], w["T0"], thr, 30)
+        r = gpu.registration_icp(w["scan"][:, :3].astype(np.float64), m, thr, w["T0"],
+                                 gpu.TransformationEstimationPointToPoint(), gpu.ICPConvergenceCriteria(max_iteration=30))
+        assert abs(r.iterations - ores.iterations) <= 1
+        dt, dr = pose_delta(r.transformation, ores.T)
+        assert dt < TOL_T and dr < TOL_R, (thr, dt, dr)
+        assert r.fitness == pytest.approx(ofit, abs=1e-4)
+        assert r.inlier_rmse == pytest.approx(ores.error, rel=1e-4)
+        assert r.correspondence_set.shape[0] == ores.k_final
+
+
 def test_voxel_grid_bit_exact(gpu, ora, small_world):
     rng = np.random.default_rng(5)
     clouds = [small_world["scan"], small_world["map"][:50_000],
