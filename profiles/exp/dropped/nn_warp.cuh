@@ -1,3 +1,12 @@
+// ARCHIVED EXPERIMENT (round 2) -- not part of the build.  Warp-cooperative candidate evaluation for the
+// fused search kernel: parity-green (70 / 70 GPU tests), but slower than the one-thread-per-query walk it was
+// meant to replace (first launches of a 256-scan step 1.85 / 1.26 / 1.22 / 0.60 ms against 1.46 / 0.90 / 0.58 /
+// 0.42 ms; 1152 M warp instructions in the first launch against 929 M).  See DESIGN.md section 4 and
+// profiles/r2/SUMMARY.md.  It was included from icp_kernels.cu in place of nn_device.cuh, with
+//     WarpWalk<CERT> W(map, s_wq[warp], {s_q, s_key, s_b2, s_skip, s_pos}, mu, none_hi, lane);
+//     far = warp_walk_near<CERT>(W, has, r, limit);  ...  warp_walk_far<CERT>(W, has, r);
+// in the S phase (one __shared__ WarpQueue per warp).
+//
 // nn_warp.cuh -- the exact walk of nn_device.cuh, one query per lane, with the CANDIDATE evaluation
 // shared by the warp (device side of K3 inside search_accum_kernel).
 //
