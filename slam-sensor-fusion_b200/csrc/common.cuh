@@ -124,7 +124,8 @@ struct PinnedBuf {
 // ---------------------------------------------------------------------------------------
 struct MapView {
     const float4 *pts;  // sorted by key; .w carries the ORIGINAL index (bit pattern of an int)
-    const float4 *nrm;  // normals in sorted order, or nullptr
+    const float4 *pn;   // (point, normal) pairs in sorted order -- pn[2 i] == pts[i], pn[2 i + 1] = its normal -- or
+                        // nullptr: the point-to-plane sums read both with ONE 256-bit load (ld_point_normal)
     const uint2 *dir;   // directory, ntz*nty*nbx*16 entries
     const uint32_t *cell_start;  // n_cells + 1 offsets into pts
     uint32_t n_pts;  // finite target points
@@ -162,6 +163,14 @@ __device__ __forceinline__ int cell_coord(float v, float o, float inv_h, int n)
     float u = __fmul_rn(__fsub_rn(v, o), inv_h);
     u = fminf(fmaxf(u, -2.0f), (float)n + 1.0f);
     return (int)floorf(u);
+}
+// 32-byte (point, normal) record of MapView::pn with one 256-bit load (sm_100: LDG.E.ENL2.256): half the L1
+// wavefronts of two scattered 128-bit gathers
+__device__ __forceinline__ void ld_point_normal(const float4 *rec, float4 &p, float4 &n)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=f"(p.w), "=f"(n.x), "=f"(n.y), "=f"(n.z), "=f"(n.w)
+                 : "l"(rec));
 }
 // order-preserving float <-> int map, so float min/max can use integer atomics
 __device__ __forceinline__ int float_ordered(float f)

@@ -309,11 +309,12 @@ __device__ __forceinline__ double gn_half(const MapView &map, const float4 *s_q,
         const uint32_t pos = s_pos[r];
         if (pos == kNoPos) continue;
         const float4 p = s_q[r];
-        const float4 q = __ldg(&map.pts[pos]);
+        float4 q, nf;
+        if (KIND == ACC_GN_P2PLANE) ld_point_normal(map.pn + 2 * (size_t)pos, q, nf);
+        else q = __ldg(&map.pts[pos]);
         const double px = p.x, py = p.y, pz = p.z;
         const double e[3] = {px - (double)q.x, py - (double)q.y, pz - (double)q.z};
         if (KIND == ACC_GN_P2PLANE) {
-            const float4 nf = __ldg(&map.nrm[pos]);
             const double n[3] = {nf.x, nf.y, nf.z};
             const double a[6] = {fma(py, n[2], -(pz * n[1])), fma(pz, n[0], -(px * n[2])),
                                  fma(px, n[1], -(py * n[0])), n[0], n[1], n[2]};
@@ -410,8 +411,8 @@ __device__ __forceinline__ void gn_gram(const MapView &map, const float4 *s_q, c
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = p, nf = p;
         if (hit) {
             p = s_q[r];
-            q = __ldg(&map.pts[pos]);
-            if (KIND == ACC_GN_P2PLANE) nf = __ldg(&map.nrm[pos]);
+            if (KIND == ACC_GN_P2PLANE) ld_point_normal(map.pn + 2 * (size_t)pos, q, nf);
+            else q = __ldg(&map.pts[pos]);
         }
         const double px = p.x, py = p.y, pz = p.z;
         const double e[3] = {px - (double)q.x, py - (double)q.y, pz - (double)q.z};
@@ -1495,7 +1496,7 @@ static int enqueue_batch(const MapView &map, const IcpConfig &cfg, BatchBuffers 
         SSF_LAUNCHED();
     }
     if (cfg.mode == SSF_MODE_GN_P2P || cfg.mode == SSF_MODE_GN_P2PLANE) {
-        if (cfg.mode == SSF_MODE_GN_P2PLANE && !map.nrm) {
+        if (cfg.mode == SSF_MODE_GN_P2PLANE && !map.pn) {
             set_error("SSF_MODE_GN_P2PLANE needs target normals (ssf_icp_set_target normals == NULL)");
             return SSF_ERR_STATE;
         }

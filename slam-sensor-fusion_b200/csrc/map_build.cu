@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(256)
     float4 p = raw[src];
     p.w = __int_as_float(global_index ? global_index[src] : (int)src);
     pts[j] = p;
-    if (raw_nrm) nrm[j] = raw_nrm[src];
+    if (raw_nrm) {  // (point, normal) side by side: one 32-byte record per point for the residual gathers
+        nrm[2 * (size_t)j] = p;
+        nrm[2 * (size_t)j + 1] = raw_nrm[src];
+    }
 }
 
 // cell c (= exclusive scan of the flags at its first point) starts at point j; the first cell of
@@ -171,7 +174,7 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
         SSF_TRY(m.cell_start.reserve(1));
         SSF_TRY(m.pts.reserve(1));
         SSF_CUDA(cudaMemsetAsync(m.dir.p, 0, 16 * sizeof(uint2), st));
-        v.dir = m.dir.p; v.cell_start = m.cell_start.p; v.pts = m.pts.p; v.nrm = nullptr;
+        v.dir = m.dir.p; v.cell_start = m.cell_start.p; v.pts = m.pts.p; v.pn = nullptr;
         m.n_dir = 16;
         m.cell_size = 1.f;
         m.view = v;
@@ -246,7 +249,7 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
     v.cert_step = (getenv("SSF_CERT_STEP") ? (float)atof(getenv("SSF_CERT_STEP")) : 4.0f) * v.cert_mu;
 
     SSF_TRY(m.pts.reserve(n_finite));
-    if (m.has_normals) SSF_TRY(m.nrm.reserve(n_finite));
+    if (m.has_normals) SSF_TRY(m.nrm.reserve(2 * (size_t)n_finite));
     SSF_TRY(m.cell_start.reserve((size_t)n_cells + 1));
     SSF_TRY(m.dir.reserve((size_t)g.n_dir));
     SSF_CUDA(cudaMemsetAsync(m.dir.p, 0, (size_t)g.n_dir * sizeof(uint2), st));
@@ -259,7 +262,7 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
                                                m.dir.p);
     SSF_LAUNCHED();
     v.pts = m.pts.p;
-    v.nrm = m.has_normals ? m.nrm.p : nullptr;
+    v.pn = m.has_normals ? m.nrm.p : nullptr;
     v.dir = m.dir.p;
     v.cell_start = m.cell_start.p;
     v.n_cells = n_cells;

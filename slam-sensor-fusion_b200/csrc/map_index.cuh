@@ -16,7 +16,7 @@ struct MapIndex {
     float shard_cell = 0.f;
     int own_lo = INT32_MIN, own_hi = INT32_MAX;
     DevBuf<float4> pts;      // sorted by directory key, w = original index
-    DevBuf<float4> nrm;      // sorted normals
+    DevBuf<float4> nrm;      // sorted (point, normal) records, 32 bytes each (MapView::pn)
     DevBuf<unsigned long long> keys;
     DevBuf<uint32_t> vals;
     DevBuf<uint32_t> flags;
