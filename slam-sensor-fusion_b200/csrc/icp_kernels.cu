@@ -1035,14 +1035,18 @@ __device__ void strict_chains(const float4 *P, const float4 *Q, const int32_t *c
     // staging by warps 1..: every thread issues the loads of ALL its rows of the tile first (three
     // independent loads per row; P / Q of a dropped row are stale or unset and never used), then
     // computes and stores -- one memory latency per tile instead of one per row
-    constexpr int kFillThreads = kRefThreads - 32;
+    // the staging warps are the ones that do NOT share warp 0's scheduler (warp id mod 4 != 0): nothing else is
+    // issued on the sub-partition the dependent adds run on
+    constexpr int kFillThreads = kRefThreads - kRefThreads / 4;
     constexpr int kFillRows = (kChainTile + kFillThreads - 1) / kFillThreads;
+    const bool filler = (warp & 3) != 0;
+    const uint32_t fidx = (uint32_t)(warp - 1 - (warp >> 2)) * 32u + (uint32_t)lane;  // 0 .. kFillThreads-1 over the staging warps
     auto fill = [&](uint32_t t, int which) {
         int32_t c[kFillRows];
         float4 p[kFillRows], q[kFillRows];
 #pragma unroll
         for (int k = 0; k < kFillRows; ++k) {
-            const uint32_t j = threadIdx.x - 32 + (uint32_t)k * kFillThreads, row = t * kChainTile + j;
+            const uint32_t j = fidx + (uint32_t)k * kFillThreads, row = t * kChainTile + j;
             c[k] = -1;
             p[k] = q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (j < (uint32_t)kChainTile && row < n) {
@@ -1053,7 +1057,7 @@ __device__ void strict_chains(const float4 *P, const float4 *Q, const int32_t *c
         }
 #pragma unroll
         for (int k = 0; k < kFillRows; ++k) {
-            const uint32_t j = threadIdx.x - 32 + (uint32_t)k * kFillThreads;
+            const uint32_t j = fidx + (uint32_t)k * kFillThreads;
             if (j >= (uint32_t)kChainTile) continue;
             float o[kChainMax];
             const bool alive = c[k] >= 0;  // rows past the end of the scan: c = -1 -> exact zeros
@@ -1064,7 +1068,7 @@ __device__ void strict_chains(const float4 *P, const float4 *Q, const int32_t *c
         }
     };
     float acc = 0.f;
-    if (warp != 0 && n_tiles > 0) fill(0, 0);
+    if (filler && n_tiles > 0) fill(0, 0);
     __syncthreads();
     for (uint32_t t = 0; t < n_tiles; ++t) {
         if (warp == 0) {
@@ -1097,7 +1101,7 @@ __device__ void strict_chains(const float4 *P, const float4 *Q, const int32_t *c
                     }
                 }
             }
-        } else if (t + 1 < n_tiles) {
+        } else if (filler && t + 1 < n_tiles) {
             fill(t + 1, (t + 1) & 1);
         }
         __syncthreads();
