@@ -329,20 +329,12 @@ def test_target_with_ten_copies_of_every_point(gpu, ora, points_per_cell, monkey
 
 
 # ---- config 3: map sharded, on one GPU ----------------------------------------------------------------
-@pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("mode", ["p2plane", "p2p"])
-def test_map_sharded_on_one_gpu_equals_oracle(gpu, ora, c1_world, world, mode):
+def _run_sharded_on_one_gpu(gpu, map_xyz, normals, scan, T0, world, m):
     """R shards of the map as R handles on ONE device (own stream each), driven by R host threads; the
     per-iteration hook sums the ranks' rows on the host behind a barrier (no kernel ever waits for
-    another).  Every rank must report the oracle's unsharded result: pose, counts, and -- merged over the
-    owners -- every correspondence, in GLOBAL indices."""
-    import ctypes
+    another).  Returns (results per rank, correspondences per rank)."""
     import torch
     from ssf_gpu import shard
-    w = c1_world
-    m = gpu.MODE_GN_P2PLANE if mode == "p2plane" else gpu.MODE_GN_P2P
-    tree = ora.KdTree(w["map"])
-    o, ocorr = ora.icp_gn(tree, w["scan"], w["T0"], mode=mode, normals=w["normals"], num_iterations=10, threads=8)
     dev = torch.device("cuda", 0)
     barrier = threading.Barrier(world)
     slots = [None] * world
@@ -354,11 +346,11 @@ def test_map_sharded_on_one_gpu_equals_oracle(gpu, ora, c1_world, world, mode):
                 t = torch.as_tensor(shard._DevArray(int(buf), int(count)), device=dev)
                 torch.cuda.ExternalStream(int(stream), device=dev).synchronize()
                 slots[rank] = t.cpu().numpy().copy()
-                barrier.wait(timeout=60)
+                barrier.wait(timeout=120)
                 tot = slots[0].copy()
                 for k in range(1, world):
                     tot = tot + slots[k]     # rank order on every rank
-                barrier.wait(timeout=60)
+                barrier.wait(timeout=120)
                 t.copy_(torch.from_numpy(tot))
                 torch.cuda.synchronize(dev)
                 return 0
@@ -372,11 +364,11 @@ def test_map_sharded_on_one_gpu_equals_oracle(gpu, ora, c1_world, world, mode):
         try:
             ctx = gpu.Context(0)
             icp = gpu.ICPPointToPoint(0.5, 10, 0.0, 0.0, mode=m, context=ctx)
-            icp.setTargetShard(shard.shard_map(w["map"], w["normals"], rank, world, 0.5))
+            icp.setTargetShard(shard.shard_map(map_xyz, normals, rank, world, 0.5))
             hooks.append(make_hook(rank))
             icp.setAllreduce(hooks[-1])
-            icp.setSourcePointCloud(w["scan"])
-            icp.setInitialTransformation(w["T0"])
+            icp.setSourcePointCloud(scan)
+            icp.setInitialTransformation(T0)
             results[rank] = icp.calculateAlignment()
             corrs[rank] = icp.correspondences()
         except Exception as e:  # pragma: no cover
@@ -387,8 +379,12 @@ def test_map_sharded_on_one_gpu_equals_oracle(gpu, ora, c1_world, world, mode):
     for t in threads:
         t.start()
     for t in threads:
-        t.join(timeout=300)
+        t.join(timeout=600)
     assert not errors, errors
+    return results, corrs
+
+
+def _check_sharded(results, corrs, o, ocorr):
     for r in results:
         assert np.array_equal(r.transformation.view(np.uint32), results[0].transformation.view(np.uint32))
         dt, dr = pose_delta(r.transformation, o.T)
@@ -400,3 +396,42 @@ def test_map_sharded_on_one_gpu_equals_oracle(gpu, ora, c1_world, world, mode):
     merged = stack.max(0)
     assert (merged == ocorr).mean() >= 0.999
     assert (merged >= 0).sum() == o.k_final
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("mode", ["p2plane", "p2p"])
+def test_map_sharded_on_one_gpu_equals_oracle(gpu, ora, c1_world, world, mode):
+    """Every rank of a map sharded R ways must report the oracle's unsharded result: pose, counts, and --
+    merged over the owners -- every correspondence, in GLOBAL indices."""
+    w = c1_world
+    m = gpu.MODE_GN_P2PLANE if mode == "p2plane" else gpu.MODE_GN_P2P
+    tree = ora.KdTree(w["map"])
+    o, ocorr = ora.icp_gn(tree, w["scan"], w["T0"], mode=mode, normals=w["normals"], num_iterations=10, threads=8)
+    results, corrs = _run_sharded_on_one_gpu(gpu, w["map"], w["normals"], w["scan"], w["T0"], world, m)
+    _check_sharded(results, corrs, o, ocorr)
+
+
+def test_c3_full_size_50M_map_unsharded_and_sharded(gpu, ora):
+    """Config 3 at its full map size: the 50M-point city map with normals, a 32x1024 scan, point-to-plane GN.
+    The map on one GPU as a whole, and cut into 4 column shards (run one after the other on this GPU), against
+    the oracle's KD-tree over all 50M points."""
+    from ssf_gpu import synth
+    xyz, nrm, half = synth.make_map(50_000_000, normals=True)
+    T = synth.street_pose(4321, half=half)
+    scan = synth.make_scan(T, 32, 1024, scan_id=4321)
+    T0 = synth.perturb_pose(T, 4321)
+    tree = ora.KdTree(xyz)
+    o, ocorr = ora.icp_gn(tree, scan, T0, mode="p2plane", normals=nrm, num_iterations=10, threads=8)
+    del tree
+    icp = gpu.ICPPointToPoint(0.5, 10, 0.0, 0.0, mode=gpu.MODE_GN_P2PLANE)
+    icp.setTargetPointCloud(xyz, nrm)
+    icp.setSourcePointCloud(scan)
+    icp.setInitialTransformation(T0)
+    r = icp.calculateAlignment()
+    dt, dr = pose_delta(r.transformation, o.T)
+    assert dt < TOL_T and dr < TOL_R, (dt, dr)
+    assert abs(r.iterations - o.iterations) <= 1 and r.k_final == o.k_final
+    assert (icp.correspondences() == ocorr).mean() >= 0.999
+    icp.close()
+    results, corrs = _run_sharded_on_one_gpu(gpu, xyz, nrm, scan, T0, 4, gpu.MODE_GN_P2PLANE)
+    _check_sharded(results, corrs, o, ocorr)
