@@ -1446,7 +1446,11 @@ static int search_grid(const BatchBuffers &b, unsigned *grid, bool *wide, int *s
     // persistent blocks; sized by the batch CAPACITY so that the launch shape (and a captured graph)
     // does not change with the number of points of an upload -- surplus blocks fetch once and exit
     size_t g = (size_t)n_sm * (size_t)SSF_MINB;
-    *wide = b.max_tiles < 4u * g;  // fewer than four tiles per resident 128-thread block: latency matters
+    // few tiles: latency matters.  Crossover measured with 32x1024 scans against the 5M-point map (profiles/exp/
+    // exp_shape.py): 8 scans (496 tiles) 0.38 ms wide / 0.44 narrow, 16 scans (992 tiles) 0.58 / 0.54,
+    // 64 scans 1.63 / 1.14
+    *wide = b.max_tiles < 5u * (size_t)n_sm;
+    if (const char *fw = getenv("SSF_SEARCH_WIDE")) *wide = atoi(fw) != 0;  // (experiments: force one shape)
     if (*wide) g = (size_t)n_sm * 2u;  // 512-thread blocks, two per SM
     if (g > b.max_tiles) g = b.max_tiles;
     *grid = (unsigned)(g ? g : 1);
