@@ -246,7 +246,7 @@ int build_map_index(MapIndex &m, float cell_size, Scratch &s, cudaStream_t st)
     v.nbx = g.nbx; v.nty = g.nty;
     for (int k = 0; k < 3; ++k) { v.bmin[k] = hb[k]; v.bmax[k] = hb[3 + k]; }
     v.cert_mu = (getenv("SSF_CERT_MU") ? (float)atof(getenv("SSF_CERT_MU")) : 0.1f) * h;
-    v.cert_step = (getenv("SSF_CERT_STEP") ? (float)atof(getenv("SSF_CERT_STEP")) : 4.0f) * v.cert_mu;
+    v.cert_step = (getenv("SSF_CERT_STEP") ? (float)atof(getenv("SSF_CERT_STEP")) : 6.0f) * v.cert_mu;
 
     SSF_TRY(m.pts.reserve(n_finite));
     if (m.has_normals) SSF_TRY(m.nrm.reserve(2 * (size_t)n_finite));
