@@ -9,6 +9,9 @@ import ssf_gpu
 from ssf_gpu import synth, pcd
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 50_000_000
+# leaf 0.1 over the 966 m extent of this map overflows PCL's int32 voxel index (9660 x 9660 x 300): pcl::VoxelGrid
+# refuses and returns the input -- and so does the device path.  0.3 m is the finest leaf that runs.
+LEAF = float(sys.argv[2]) if len(sys.argv) > 2 else 0.3
 xyz, _, _ = synth.make_map(M)
 with tempfile.TemporaryDirectory(dir=os.environ.get("SSF_BENCH_TMP", "/tmp")) as d:
     t0 = time.time()
@@ -17,10 +20,10 @@ with tempfile.TemporaryDirectory(dir=os.environ.get("SSF_BENCH_TMP", "/tmp")) as
     print(f"wrote 50 tiles ({M * 12 / 1e6:.0f} MB) in {time.time() - t0:.1f}s", flush=True)
     for rep in range(2):
         t0 = time.time()
-        rm = ssf_gpu.ResidentMap.from_pcd_folder(d, "map", 0.1, save=False)
+        rm = ssf_gpu.ResidentMap.from_pcd_folder(d, "map", LEAF, save=False)
         wall = time.time() - t0
         gbs = 2 * 16 * M / (rm.ingest_ms * 1e-3) / 1e9
-        print(f"ingest: {M} points -> {len(rm)} voxels; stream {rm.ingest_ms:.1f} ms ({gbs:.1f} GB/s against 2 x 16 x M), of which "
+        print(f"ingest (leaf {LEAF}): {M} points -> {len(rm)} voxels; stream {rm.ingest_ms:.1f} ms ({gbs:.1f} GB/s against 2 x 16 x M), of which "
               f"the voxel filter {rm.merge_ms:.1f} ms ({2 * 16 * M / (rm.merge_ms * 1e-3) / 1e9:.0f} GB/s); "
               f"wall {wall:.2f}s incl. file reads ({M * 12 / wall / 1e9:.2f} GB/s of PCD)", flush=True)
         del rm
